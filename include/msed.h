@@ -1,0 +1,207 @@
+/*
+ * msed.h -- C ABI of libmsed_b200.so: the B200-native fabm_sediment column solver.
+ *
+ * This is the drop-in boundary for MOSSCO's sediment hot path.  Each entry point names the
+ * reference interface it replaces (paths relative to the MOSSCO source tree):
+ *   src/utilities/solver_library.F90         type_rhs_driver :37-49, ode_solver :80-189
+ *   src/drivers/fabm_sediment_driver.F90     type_sed :69-113 and its type-bound procedures
+ *   src/components/fabm_sediment_component.F90  Run inner loop :1700-1769,
+ *                                            get_boundary_conditions :1865-2030, export :1773-1822
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types.  Fortran binds it with
+ *     ISO_C_BINDING (mossco_code_b200/fortran/msed_b200.F90).
+ *   - every host array is caller-owned, fp64, Fortran order, exactly the reference's shapes:
+ *       conc(inum,jnum,knum,nvar)  bdys(inum,jnum,nvar+1)  fluxes(inum,jnum,nvar)
+ *       3-D fields (inum,jnum,knum), 2-D fields (inum,jnum); mask is int32 (inum,jnum), >0 = land.
+ *     The library owns all device memory (same layout: variable-major, layer-major,
+ *     cell-contiguous, plane stride padded to 128 B).
+ *   - one handle == one type_sed instance (one horizontal tile on one GPU).  Not thread safe.
+ *   - return value: 0 success; >0 model conditions (MSED_NAN_DETECTED, MSED_BAD_DOMAIN, ...);
+ *     <0 usage/CUDA/NCCL errors.  The library never aborts the process and never falls back
+ *     to a CPU path: without a CUDA device every compute entry returns MSED_ERR_CUDA.
+ */
+#ifndef MSED_H
+#define MSED_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSED_ABI_VERSION 1
+#define MSED_NVAR 8          /* hzg_omexdia_p state variables */
+#define MSED_MAX_LAYERS 64   /* knum limit (per-layer tables live in kernel-parameter constant space) */
+
+/* ode_solver method ids, solver_library.F90:32-35 */
+#define MSED_EULER 0
+#define MSED_RUNGE_KUTTA_4 1
+#define MSED_ADAPTIVE_EULER 2
+#define MSED_RUNGE_KUTTA_4_38 3
+
+/* reaction model: stands in for the FABM model tree built at fabm_sediment_driver.F90:328-350 */
+#define MSED_MODEL_OMEXDIA_P 0   /* hzg_omexdia_p, 8 state variables */
+#define MSED_MODEL_NONE 1        /* transport only (base_get_rhs-like zero reaction) */
+#define MSED_MODEL_TEST_SOLVER 2 /* rhs(i,j,k,:)=(i+j+k)*1e-8, src/test/test_Solver.F90:40 (KAT) */
+
+/* return codes */
+#define MSED_OK 0
+#define MSED_NAN_DETECTED 1      /* check_NaN, fabm_sediment_component.F90:2377-2421 */
+#define MSED_BAD_DOMAIN 2        /* fabm_sed_check_domain stops, fabm_sediment_driver.F90:503-530 */
+#define MSED_ERR_ARG (-1)
+#define MSED_ERR_CUDA (-2)
+#define MSED_ERR_NCCL (-3)
+#define MSED_ERR_ALLOC (-4)
+#define MSED_ERR_STATE (-5)
+
+/* msed_get_field selectors: the export_states catalogue, fabm_sediment_driver.F90:877-924 */
+#define MSED_FIELD_POROSITY 0
+#define MSED_FIELD_LAYER_HEIGHT 1
+#define MSED_FIELD_LAYER_CENTER_DEPTH 2
+#define MSED_FIELD_TEMPERATURE 3
+#define MSED_FIELD_PAR 4
+#define MSED_FIELD_BIOMASS 5
+#define MSED_FIELD_BIOTURBATION 6
+#define MSED_FIELD_WEIGHTED_TOC 7
+#define MSED_FIELD_DENIT 8           /* FABM diagnostic hzg_omexdia_p_denit */
+#define MSED_FIELD_INTF_POROSITY 9
+#define MSED_FIELD_FLUX_CAP 10
+
+typedef struct msed_handle msed_handle;
+
+/* sed_nml (fabm_sediment_driver.F90:211-231), run_nml solver entries
+ * (fabm_sediment_component.F90:59-67,83-88) and the hzg_omexdia_p namelist
+ * (examples/standalone/omexdia_p/fabm_sed.nml:51-77) in one plain struct. */
+typedef struct msed_config {
+    int32_t abi_version;          /* MSED_ABI_VERSION */
+    int32_t inum, jnum, knum;     /* local tile, type_rhs_driver :38 */
+    int32_t device;               /* CUDA ordinal; -1 = current device */
+    int32_t model;                /* MSED_MODEL_* */
+    double dzmin;                 /* fabm_sed_grid%dzmin */
+    /* sed_nml */
+    double diffusivity, bioturbation, porosity_max, porosity_fac, k_par, pom_flux_max;
+    double bioturbation_depth, bioturbation_min;
+    double bioturb_k_l, bioturb_L1, bioturb_L2, bioturb_beta, bioturb_b, bioturb_dry_density;
+    int32_t bioturbation_profile, distributed_pom_flux;
+    /* run_nml */
+    double dt_min, relative_change_min;
+    int32_t bcup_dissolved_variables, adaptive_solver_diagnostics;
+    /* hzg_omexdia_p (rates per day, as in the namelist) */
+    double rLabile, rSemilabile, NCrLdet, NCrSdet, PAds, PAdsODU, NH3Ads, CprodMax;
+    double rnit, ksO2nitri, rODUox, ksO2oduox, ksO2oxic, ksNO3denit, kinO2denit;
+    double kinNO3anox, kinO2anox;
+    double initial_value[MSED_NVAR]; /* ldetC sdetC detP po4 no3 nh3 oxy odu */
+    double minimum[MSED_NVAR];
+    /* tile origin in the global grid (only used by MSED_MODEL_TEST_SOLVER and minloc reporting) */
+    int32_t i_offset, j_offset;
+} msed_config;
+
+/* what a stepping call did; mirrors type_rhs_driver diagnostics (solver_library.F90:44-46) */
+typedef struct msed_step_info {
+    int64_t steps_done;           /* completed ode_solver calls */
+    int64_t rhs_evaluations;      /* get_rhs calls issued (attempts or RK stages) */
+    int64_t subcycle_warnings;    /* "solver subcycles" events, solver_library.F90:128 */
+    double last_min_dt;           /* :44,:132 */
+    int32_t last_min_dt_grid_cell[4]; /* :45,:133 (1-based i,j,k,n; -99 when unset) */
+    int32_t nan_detected;
+    double kernel_ms;             /* device time of the stepping kernels (CUDA events) */
+    int64_t kernel_launches;      /* launches of this library's kernels in the call */
+} msed_step_info;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+/* fills cfg with the reference defaults (fabm_sediment_driver.F90:217-231,
+ * fabm_sediment_component.F90:59-67, fabm_sed.nml:51-77) */
+int msed_config_defaults(msed_config *cfg);
+/* fabm_sed_grid%init_grid (:127-177) + type_sed%initialize (:191-388): grid, porosity,
+ * flux_cap, bioturbation_factor, scratch; allocates device state (conc zeroed, mask all wet) */
+int msed_create(const msed_config *cfg, msed_handle **out);
+/* type_sed%finalize (:723-732) + component Finalize deallocation */
+int msed_destroy(msed_handle *h);
+const char *msed_last_error(const msed_handle *h);
+/* library identification: "msed_b200 <abi> sm_100a" */
+const char *msed_version(void);
+
+/* ---- static fields ------------------------------------------------------------------------ */
+/* grid%zi(knum+1), zc(knum), dz(knum), dzc(knum-1) of init_grid (horizontally uniform); any may be NULL */
+int msed_get_grid(const msed_handle *h, double *zi, double *zc, double *dz, double *dzc);
+/* sed%mask from ESMF_GRIDITEM_MASK (component :489-502): mask2d>0 = masked. Applies the
+ * side effects of check_domain/update_porosity: porosity=1 (:431,:541) and conc=1e20 (:535) there */
+int msed_set_mask(msed_handle *h, const int32_t *mask2d);
+/* sed%porosity(:,:,:) direct assignment (ReadRestart, component :1462-1470) */
+int msed_set_porosity(msed_handle *h, const double *porosity3d);
+/* update_porosity(from_surface=.true.) after porosity(:,:,1)=porosity_at_soil_surface
+ * (component :1642-1643; driver :393-442) */
+int msed_update_porosity_from_surface(msed_handle *h, const double *porosity_surface2d);
+/* sed%par_surface, component :1596 */
+int msed_set_par_surface(msed_handle *h, const double *par_surface2d);
+/* fabm_sed_check_domain, driver :488-545 */
+int msed_check_domain(msed_handle *h);
+
+/* ---- state -------------------------------------------------------------------------------- */
+/* init_concentrations, driver :449-481 */
+int msed_init_concentrations(msed_handle *h);
+int msed_set_state(msed_handle *h, const double *conc);   /* sed%conc => conc */
+int msed_get_state(msed_handle *h, double *conc);
+/* apply a (1,1,knum,nvar) profile to every unmasked column, component :628-632 */
+int msed_set_state_from_column(msed_handle *h, const double *conc1d);
+
+/* ---- boundary ----------------------------------------------------------------------------- */
+/* sed%bdys => bdys ; sed%fluxes => fluxes (component :1666-1667, main.F90:121-122) */
+int msed_set_boundary(msed_handle *h, const double *bdys, const double *fluxes);
+/* get_boundary_conditions on device, component :1865-2030.  temperature, csurf[n], wz[n] are
+ * (inum,jnum) import fields; NULL entries mean "field not in the import state" */
+int msed_get_boundary_conditions(msed_handle *h, const double *temperature2d,
+                                 const double *const *csurf, const double *const *wz);
+int msed_get_boundary(msed_handle *h, double *bdys, double *fluxes);
+/* sed%fluxes after stepping (dissolved entries = intFlux(:,:,1), driver :692) */
+int msed_get_fluxes(msed_handle *h, double *fluxes);
+/* <var>_upward_flux_at_soil_surface = -fluxes(:,:,n), component :1819 */
+int msed_get_upward_fluxes(msed_handle *h, double *upward_fluxes);
+/* export_states(n)%data / diagnostics for <name>_in_soil, component :1773-1822 */
+int msed_get_field(msed_handle *h, int which, double *out3d);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* type_sed%get_rhs, driver :575-717 (one RHS evaluation incl. its side effect on sed%fluxes) */
+int msed_get_rhs(msed_handle *h, double *rhs);
+/* ode_solver(sed, dt, method), solver_library.F90:80-189: exactly one call, no NaN check/clip */
+int msed_ode_solver(msed_handle *h, double dt, int method, msed_step_info *info);
+/* nsteps iterations of the Run loop body (component :1715-1732): ode_solver -> check_NaN ->
+ * clip to state_variables(n)%minimum, fused on device.  Stops at the first NaN step. */
+int msed_step(msed_handle *h, double dt, int method, int64_t nsteps, msed_step_info *info);
+/* the whole `do while (.not.stopTime)` loop (component :1700-1769): steps of dt until
+ * run_seconds are covered, the last one shortened (:1705-1708) */
+int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_step_info *info);
+/* 1-D pre-simulation (component :557-632) for the handle's configuration; conc1d(1,1,knum,nvar) out.
+ * bdys1d(nvar+1), fluxes1d(nvar). Runs a 1x1 tile on the same device. */
+int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const double *fluxes1d,
+                       int64_t nsteps, int method, double *conc1d, msed_step_info *info);
+
+/* ---- execution control -------------------------------------------------------------------- */
+/* all work is enqueued on this cudaStream_t (default: a private non-blocking stream) */
+int msed_set_stream(msed_handle *h, void *cuda_stream);
+int msed_synchronize(msed_handle *h);
+/* device pointers for zero-copy plumbing (torch/NCCL): state [nvar][knum][ld], ld in doubles */
+int msed_device_state(msed_handle *h, void **dev_ptr, size_t *ld);
+/* same entry points with DEVICE-resident inputs (already in the library's padded layout is not
+ * required: plain [n][ncol] contiguous device arrays) */
+int msed_set_boundary_device(msed_handle *h, const void *bdys_dev, const void *fluxes_dev);
+int msed_get_fluxes_device(msed_handle *h, void *fluxes_dev);
+
+/* ---- multi-GPU (one handle per rank, j-slab tiles, no halo) -------------------------------- */
+/* NCCL is bound at run time (dlopen libnccl.so.2); only the accept/reject + NaN flags of the
+ * adaptive step (solver_library.F90:121) are reduced.  id is a 128-byte ncclUniqueId. */
+int msed_nccl_unique_id(char id[128]);
+int msed_comm_init(msed_handle *h, const char id[128], int nranks, int rank);
+int msed_comm_destroy(msed_handle *h);
+/* split phase for hosts that own the collective themselves (e.g. torch.distributed):
+ * msed_step runs attempt kernels and calls hook(user, dev_flags, 2, stream) to MAX-reduce
+ * two int32 device flags across ranks before each accept/reject decision. */
+typedef int (*msed_allreduce_hook)(void *user, void *dev_flags_i32, int count, void *cuda_stream);
+int msed_set_allreduce_hook(msed_handle *h, msed_allreduce_hook hook, void *user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSED_H */

@@ -1,0 +1,996 @@
+// msed.cu -- host side and C ABI (include/msed.h) of the B200-native fabm_sediment column solver.
+//
+// Host-side restatement of type_sed (src/drivers/fabm_sediment_driver.F90:69-113) and of the
+// scalar control flow of ode_solver (src/utilities/solver_library.F90:80-189): the arrays live on
+// the device in the reference's own Fortran layout, the column kernels in msed_kernels.cuh do the
+// array work.  There is no CPU compute path in this file.
+#include "msed_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace msed;
+
+// ---- NCCL bound at run time (no link-time dependency) -----------------------------------------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl_api()
+{
+    static NcclApi api;
+    if (api.lib) return api;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return api;
+    api.GetUniqueId = (int (*)(NcclUniqueId *))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(ncclComm_t *, int, NcclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.lib, "ncclCommDestroy");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(
+        api.lib, "ncclAllReduce");
+    api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
+    return api;
+}
+constexpr int kNcclInt32 = 2;  // ncclInt32
+constexpr int kNcclMax = 2;    // ncclMax
+}  // namespace
+
+// ---- handle -----------------------------------------------------------------------------------
+struct msed_handle {
+    msed_config cfg;
+    int K = 0, ncol = 0;
+    size_t ld = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    double *buf[2] = {nullptr, nullptr};
+    double *aux[2] = {nullptr, nullptr};
+    double *por = nullptr, *bdys = nullptr, *fluxes = nullptr, *par_surface = nullptr;
+    double *scratch = nullptr;  // [nvar][K][ld] staging (rhs / fields / packed transfers)
+    double *tables = nullptr;   // device copies of zc[K], cumdepth[K], porosity profile[K]
+    unsigned char *mask = nullptr;
+    Ctl *ctl = nullptr;         // device
+    Ctl *ctl_host = nullptr;    // pinned mirror
+    double *minloc_val = nullptr;
+    long long *minloc_idx = nullptr;
+    int cur = 0;
+    std::vector<double> zi, zc, dz, dzc, bf, por_profile, cumdepth;
+    double bioturbation_eff = 0.0;  // sed%bioturbation (profile 3 overwrites it with 1, driver :623)
+    double last_min_dt = (double)1.e20f;  // solver_library.F90:44 (default-real literal)
+    int last_min_dt_grid_cell[4] = {-99, -99, -99, -99};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    msed_allreduce_hook hook = nullptr;
+    void *hook_user = nullptr;
+    std::string err;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(msed_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(h, MSED_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(e_));     \
+    } while (0)
+
+inline int nblocks(int ncol, int bs = 256) { return (ncol + bs - 1) / bs; }
+
+// host <-> device copies between the caller's dense Fortran arrays (row length ncol) and the
+// padded device planes (row length ld)
+int upload_rows(msed_handle *h, double *dst, const double *src, size_t rows)
+{
+    CUDA_TRY(h, cudaMemcpy2DAsync(dst, h->ld * sizeof(double), src, (size_t)h->ncol * sizeof(double),
+                                  (size_t)h->ncol * sizeof(double), rows, cudaMemcpyHostToDevice,
+                                  h->stream));
+    return MSED_OK;
+}
+int download_rows(msed_handle *h, double *dst, const double *src, size_t rows)
+{
+    CUDA_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->ncol * sizeof(double), src, h->ld * sizeof(double),
+                                  (size_t)h->ncol * sizeof(double), rows, cudaMemcpyDeviceToHost,
+                                  h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+void fill_params(const msed_handle *h, KParams &p)
+{
+    std::memset(&p, 0, sizeof(p));
+    const msed_config &c = h->cfg;
+    p.buf[0] = h->buf[0];
+    p.buf[1] = h->buf[1];
+    p.aux1 = h->aux[0];
+    p.aux2 = h->aux[1];
+    p.rhs_out = h->scratch;
+    p.por = h->por;
+    p.bdys = h->bdys;
+    p.fluxes = h->fluxes;
+    p.mask = h->mask;
+    p.ctl = h->ctl;
+    p.ld = h->ld;
+    p.ncol = h->ncol;
+    p.K = h->K;
+    p.inum = c.inum;
+    p.i_offset = c.i_offset;
+    p.j_offset = c.j_offset;
+    p.bcup_diss = c.bcup_dissolved_variables;
+    p.bcup_part = c.distributed_pom_flux ? 4 : 1;  // driver :239-243
+    p.profile = c.bioturbation_profile;
+    p.use_ctl = 1;
+    p.dt = 0.0;
+    p.fac = 1.0 + c.relative_change_min;           // solver_library.F90:121
+    p.bioturbation = h->bioturbation_eff;
+    p.diffusivity = c.diffusivity;
+    p.pom_flux_rate = c.pom_flux_max / 86400.0;     // driver :284
+    p.beta = c.bioturb_beta;
+    p.b = c.bioturb_b;
+    p.L1 = c.bioturb_L1;
+    p.L2 = c.bioturb_L2;
+    p.poc_factor[0] = 1.0 / 1.2 * 12.01 / c.bioturb_dry_density / 1000.0;  // driver :383
+    p.poc_factor[1] = 1.0 / 6.0 * 12.01 / c.bioturb_dry_density / 1000.0;  // driver :386
+    p.cumdepth_last = h->cumdepth[h->K - 1];
+    OmexDev &m = p.om;
+    m.rLabile = c.rLabile / 86400.0;
+    m.rSemilabile = c.rSemilabile / 86400.0;
+    m.NCrLdet = c.NCrLdet;
+    m.NCrSdet = c.NCrSdet;
+    m.PAds_rS = c.PAds * m.rSemilabile;
+    m.PAdsODU = c.PAdsODU;
+    m.rNH3Ads = 1.0 / (1.0 + c.NH3Ads);
+    m.CprodMax = c.CprodMax / 86400.0;
+    m.rnit = c.rnit / 86400.0;
+    m.ksO2nitri = c.ksO2nitri;
+    m.rODUox = c.rODUox / 86400.0;
+    m.ksO2oduox = c.ksO2oduox;
+    m.ksO2oxic = c.ksO2oxic;
+    m.ksNO3denit = c.ksNO3denit;
+    m.kinO2denit = c.kinO2denit;
+    m.kinNO3anox = c.kinNO3anox;
+    m.kinO2anox = c.kinO2anox;
+    m.E_a = 0.1 * std::log(1.5) * 288.15 * (288.15 + 10.0);
+    for (int n = 0; n < NV; ++n) m.minimum[n] = c.minimum[n];
+    for (int k = 0; k < h->K; ++k) {
+        p.dz[k] = h->dz[k];
+        p.rdzc[k] = (k < h->K - 1) ? 1.0 / h->dzc[k] : 0.0;
+        p.bf[k] = h->bf[k];
+        p.e1[k] = std::exp(h->zc[k] * 100.0 * c.bioturb_k_l);  // driver :639
+        p.e2[k] = std::exp(h->zc[k] * 200.0 * c.bioturb_k_l);  // driver :640
+    }
+}
+
+template <int MODEL, bool P3>
+cudaError_t launch_op(int op, const KParams &p, cudaStream_t s)
+{
+    const dim3 grid(nblocks(p.ncol, COL_BLOCK)), block(COL_BLOCK);
+    switch (op) {
+#define MSED_CASE(OPV) \
+    case OPV: column_kernel<MODEL, OPV, P3><<<grid, block, 0, s>>>(p); break;
+        MSED_CASE(OP_RHS)
+        MSED_CASE(OP_EULER)
+        MSED_CASE(OP_ADAPTIVE)
+        MSED_CASE(OP_RK4_S1)
+        MSED_CASE(OP_RK4_S2)
+        MSED_CASE(OP_RK4_S3)
+        MSED_CASE(OP_RK4_S4)
+        MSED_CASE(OP_RK38_S1)
+        MSED_CASE(OP_RK38_S2)
+        MSED_CASE(OP_RK38_S3)
+        MSED_CASE(OP_RK38_S4)
+#undef MSED_CASE
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_column(const msed_handle *h, int op, const KParams &p)
+{
+    const bool p3 = h->cfg.bioturbation_profile == 3;
+    switch (h->cfg.model) {
+    case MSED_MODEL_OMEXDIA_P:
+        return p3 ? launch_op<MSED_MODEL_OMEXDIA_P, true>(op, p, h->stream)
+                  : launch_op<MSED_MODEL_OMEXDIA_P, false>(op, p, h->stream);
+    case MSED_MODEL_NONE:
+        return p3 ? launch_op<MSED_MODEL_NONE, true>(op, p, h->stream)
+                  : launch_op<MSED_MODEL_NONE, false>(op, p, h->stream);
+    case MSED_MODEL_TEST_SOLVER:
+        if (op != OP_RHS && op != OP_EULER) return cudaErrorInvalidValue;
+        return launch_op<MSED_MODEL_TEST_SOLVER, false>(op, p, h->stream);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+int ensure_aux(msed_handle *h, int count)
+{
+    const size_t bytes = (size_t)NV * h->K * h->ld * sizeof(double);
+    for (int a = 0; a < count; ++a)
+        if (!h->aux[a]) {
+            CUDA_TRY(h, cudaMalloc(&h->aux[a], bytes));
+            CUDA_TRY(h, cudaMemsetAsync(h->aux[a], 0, bytes, h->stream));
+        }
+    return MSED_OK;
+}
+
+int ensure_scratch(msed_handle *h)
+{
+    if (!h->scratch) {
+        const size_t bytes = (size_t)NV * h->K * h->ld * sizeof(double);
+        CUDA_TRY(h, cudaMalloc(&h->scratch, bytes));
+    }
+    return MSED_OK;
+}
+
+int reduce_flags(msed_handle *h)
+{
+    if (h->hook) {
+        void *flags = (void *)((char *)h->ctl + offsetof(Ctl, flags));
+        if (h->hook(h->hook_user, flags, 2, (void *)h->stream) != 0)
+            return fail(h, MSED_ERR_NCCL, "allreduce hook failed");
+    } else if (h->comm) {
+        NcclApi &api = nccl_api();
+        int *flags = (int *)((char *)h->ctl + offsetof(Ctl, flags));
+        int rc = api.AllReduce(flags, flags, 2, kNcclInt32, kNcclMax, h->comm, h->stream);
+        if (rc != 0)
+            return fail(h, MSED_ERR_NCCL, std::string("ncclAllReduce: ") +
+                                              (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+    }
+    return MSED_OK;
+}
+
+// the step loop shared by msed_ode_solver / msed_step / msed_run
+int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrapper, msed_step_info *info)
+{
+    if (nsteps < 0) return fail(h, MSED_ERR_ARG, "nsteps < 0");
+    if (method < 0 || method > 3) return fail(h, MSED_ERR_ARG, "unknown ode_method");
+    if (h->cfg.model == MSED_MODEL_TEST_SOLVER && method != MSED_EULER)
+        return fail(h, MSED_ERR_ARG, "MSED_MODEL_TEST_SOLVER supports MSED_EULER only");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool diag = h->cfg.adaptive_solver_diagnostics && method == MSED_ADAPTIVE_EULER;
+    int rc;
+    if (method == MSED_RUNGE_KUTTA_4) { if ((rc = ensure_aux(h, 1))) return rc; }
+    if (method == MSED_RUNGE_KUTTA_4_38) { if ((rc = ensure_aux(h, 2))) return rc; }
+
+    if (h->cfg.bioturbation_profile == 3) h->bioturbation_eff = 1.0;  // driver :623
+
+    Ctl c;
+    std::memset(&c, 0, sizeof(c));
+    c.dt = dt;
+    c.dt_int = 0.0;
+    c.dt_red = dt;
+    c.dt_min = h->cfg.dt_min;
+    c.last_min_dt = h->last_min_dt;
+    c.steps_done = 0;
+    c.steps_target = nsteps;
+    c.cur = h->cur;
+    c.do_clip = (wrapper && !diag) ? 1 : 0;
+    c.diagnostics = diag ? 1 : 0;
+    *h->ctl_host = c;
+    CUDA_TRY(h, cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+
+    KParams p;
+    fill_params(h, p);
+    InitVals minimum;
+    for (int n = 0; n < NV; ++n) minimum.v[n] = h->cfg.minimum[n];
+    const bool collective = (h->comm != nullptr || h->hook != nullptr);
+    long long launches = 0;
+
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    long long remaining = nsteps;
+    const long long max_batch = 256;
+    int guard = 0;
+    while (remaining > 0) {
+        const long long batch = remaining < max_batch ? remaining : max_batch;
+        for (long long s = 0; s < batch; ++s) {
+            if (method == MSED_EULER) {
+                CUDA_TRY(h, launch_column(h, OP_EULER, p));
+                launches += 1;
+            } else if (method == MSED_ADAPTIVE_EULER) {
+                CUDA_TRY(h, launch_column(h, OP_ADAPTIVE, p));
+                launches += 1;
+            } else {
+                const int first = (method == MSED_RUNGE_KUTTA_4) ? OP_RK4_S1 : OP_RK38_S1;
+                for (int st = 0; st < 4; ++st) CUDA_TRY(h, launch_column(h, first + st, p));
+                launches += 4;
+            }
+            if (collective && (method == MSED_ADAPTIVE_EULER || wrapper))
+                if ((rc = reduce_flags(h))) return rc;
+            controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method);
+            launches += 1;
+            if (diag) {
+                minloc_kernel<<<1, 256, 0, h->stream>>>(h->ctl, h->buf[0], h->buf[1], h->ld, h->ncol,
+                                                        NV * h->K, h->minloc_val, h->minloc_idx);
+                launches += 1;
+                if (wrapper) {
+                    clip_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->ctl, h->buf[0], h->buf[1],
+                                                                         h->mask, h->ld, h->ncol, h->K,
+                                                                         minimum);
+                    launches += 1;
+                }
+            }
+        }
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (h->ctl_host->stop) break;
+        remaining = nsteps - h->ctl_host->steps_done;
+        // sub-cycling needs more attempts than steps: keep going until the controller reports done
+        if (++guard > 1000000) return fail(h, MSED_ERR_STATE, "step loop did not terminate");
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (nsteps == 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+
+    const Ctl &r = *h->ctl_host;
+    h->cur = r.cur;
+    if (diag && r.last_min_dt < h->last_min_dt) {
+        long long idx = -1;
+        CUDA_TRY(h, cudaMemcpy(&idx, h->minloc_idx, sizeof(idx), cudaMemcpyDeviceToHost));
+        if (idx >= 0) {  // rows are (n*K+k), columns i + inum*j -> Fortran (i,j,k,n), 1-based
+            const long long row = idx / h->ncol, col = idx % h->ncol;
+            h->last_min_dt_grid_cell[0] = (int)(col % h->cfg.inum) + 1;
+            h->last_min_dt_grid_cell[1] = (int)(col / h->cfg.inum) + 1;
+            h->last_min_dt_grid_cell[2] = (int)(row % h->K) + 1;
+            h->last_min_dt_grid_cell[3] = (int)(row / h->K) + 1;
+        }
+    }
+    h->last_min_dt = r.last_min_dt;
+    if (info) {
+        info->steps_done = r.steps_done;
+        info->rhs_evaluations = r.rhs_evals;
+        info->subcycle_warnings = r.subcycles;
+        info->last_min_dt = h->last_min_dt;
+        for (int q = 0; q < 4; ++q) info->last_min_dt_grid_cell[q] = h->last_min_dt_grid_cell[q];
+        info->nan_detected = r.nan_detected;
+        info->kernel_ms = ms;
+        info->kernel_launches = launches;
+    }
+    return r.nan_detected ? MSED_NAN_DETECTED : MSED_OK;
+}
+
+}  // namespace
+
+// ---- C ABI --------------------------------------------------------------------------------------
+extern "C" {
+
+const char *msed_version(void) { return "msed_b200 abi1 sm_100a"; }
+
+const char *msed_last_error(const msed_handle *h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int msed_config_defaults(msed_config *c)
+{
+    if (!c) return MSED_ERR_ARG;
+    std::memset(c, 0, sizeof(*c));
+    c->abi_version = MSED_ABI_VERSION;
+    c->inum = c->jnum = 1;
+    c->knum = 10;                   // main.F90:49
+    c->device = -1;
+    c->model = MSED_MODEL_OMEXDIA_P;
+    c->dzmin = 0.005;               // main.F90:50
+    c->bioturbation_profile = 1;    // fabm_sediment_driver.F90:217-231
+    c->diffusivity = 0.9;
+    c->bioturbation = 0.9;
+    c->bioturbation_depth = 5.0;
+    c->bioturbation_min = 0.2;
+    c->porosity_max = 0.7;
+    c->porosity_fac = 0.9;
+    c->k_par = 2.0e-3;
+    c->pom_flux_max = 2.0e4;
+    c->bioturb_k_l = 0.11;
+    c->bioturb_L1 = 0.2;
+    c->bioturb_L2 = 0.6;
+    c->bioturb_beta = 0.22;
+    c->bioturb_b = 1.334;
+    c->bioturb_dry_density = 1000.;
+    c->distributed_pom_flux = 0;
+    c->dt_min = 1.0e-8;             // fabm_sediment_component.F90:60
+    c->relative_change_min = -0.9;
+    c->bcup_dissolved_variables = 2;  // :64
+    c->adaptive_solver_diagnostics = 0;
+    c->rLabile = 0.043;             // fabm_sed.nml:51-77
+    c->rSemilabile = 0.001;
+    c->NCrLdet = 0.22;
+    c->NCrSdet = 0.005;
+    c->PAds = 0.01;
+    c->PAdsODU = 70.;
+    c->NH3Ads = 0.0;
+    c->CprodMax = 9600.0;
+    c->rnit = 200.;
+    c->ksO2nitri = 20.;
+    c->rODUox = 20.;
+    c->ksO2oduox = 1.;
+    c->ksO2oxic = 3.;
+    c->ksNO3denit = 1.;
+    c->kinO2denit = 70.;
+    c->kinNO3anox = 1.;
+    c->kinO2anox = 1.;
+    const double init[NV] = {4.e3, 4.e3, 4.e1, 10., 20., 40., 100., 100.};
+    for (int n = 0; n < NV; ++n) { c->initial_value[n] = init[n]; c->minimum[n] = 0.0; }
+    return MSED_OK;
+}
+
+int msed_create(const msed_config *cfg, msed_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, MSED_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != MSED_ABI_VERSION) return fail(nullptr, MSED_ERR_ARG, "abi_version mismatch");
+    if (cfg->inum < 1 || cfg->jnum < 1) return fail(nullptr, MSED_ERR_ARG, "grid size < 1");  // driver :139
+    if (cfg->knum < 2 || cfg->knum > MSED_MAX_LAYERS)
+        return fail(nullptr, MSED_ERR_ARG, "knum must be in [2, MSED_MAX_LAYERS]");
+    if ((long long)cfg->inum * cfg->jnum > 0x7fffffffLL / 2)
+        return fail(nullptr, MSED_ERR_ARG, "tile too large (inum*jnum)");
+    if (cfg->model < 0 || cfg->model > 2) return fail(nullptr, MSED_ERR_ARG, "unknown model");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, MSED_ERR_CUDA, "no CUDA device: libmsed_b200 has no CPU path");
+    }
+    msed_handle *h = new (std::nothrow) msed_handle();
+    if (!h) return fail(nullptr, MSED_ERR_ALLOC, "host allocation failed");
+    h->cfg = *cfg;
+    int dev = cfg->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    h->device = dev;
+    h->K = cfg->knum;
+    h->ncol = cfg->inum * cfg->jnum;
+    h->ld = ((size_t)h->ncol + 15) / 16 * 16;  // 128-byte aligned planes
+    h->bioturbation_eff = cfg->bioturbation;
+    const int K = h->K;
+
+    // init_grid, driver :147-168
+    h->zi.assign(K + 1, 0.0); h->zc.assign(K, 0.0); h->dz.assign(K, 0.0); h->dzc.assign(K - 1, 0.0);
+    const double self_fac = 0.18 / ((K + 1) / 2.0 * cfg->dzmin) - 1.0;
+    for (int k = 1; k <= K; ++k) {
+        h->dz[k - 1] = (1.0 + (self_fac - 1.0) * (double)(k - 1) / (double)(K - 1)) * cfg->dzmin;
+        h->zc[k - 1] = h->zi[k - 1] + 0.5 * h->dz[k - 1];
+        h->zi[k] = h->zi[k - 1] + h->dz[k - 1];
+    }
+    for (int k = 0; k < K - 1; ++k) h->dzc[k] = h->zc[k + 1] - h->zc[k];
+    // initialize, driver :278-304
+    h->bf.assign(K, 1.0); h->por_profile.assign(K, 0.0); h->cumdepth.assign(K, 0.0);
+    for (int k = 0; k < K; ++k) {
+        h->por_profile[k] = cfg->porosity_max * (1.0 - cfg->porosity_fac * h->zc[k]);
+        if (cfg->bioturbation_profile == 1)
+            h->bf[k] = std::fmax(cfg->bioturbation_min / cfg->bioturbation,
+                                 std::fmax(cfg->bioturbation_depth - 100.0 * h->zi[k], 0.0) /
+                                     cfg->bioturbation_depth);
+        else if (cfg->bioturbation_profile == 2)
+            h->bf[k] = std::exp(-100.0 * h->zi[k] / cfg->bioturbation_depth);
+        double s = 0.0;  // sum(dz(:,:,1:k-1)), driver :597
+        for (int m = 0; m < k; ++m) s += h->dz[m];
+        h->cumdepth[k] = s;
+    }
+
+#define CREATE_TRY(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            int rc_ = fail(nullptr, MSED_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(e_)); \
+            msed_destroy(h);                                                                      \
+            return rc_;                                                                           \
+        }                                                                                         \
+    } while (0)
+
+    CREATE_TRY(cudaSetDevice(h->device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    CREATE_TRY(cudaEventCreate(&h->ev0));
+    CREATE_TRY(cudaEventCreate(&h->ev1));
+    const size_t state_bytes = (size_t)NV * K * h->ld * sizeof(double);
+    CREATE_TRY(cudaMalloc(&h->buf[0], state_bytes));
+    CREATE_TRY(cudaMalloc(&h->buf[1], state_bytes));
+    CREATE_TRY(cudaMalloc(&h->por, (size_t)K * h->ld * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->bdys, (size_t)(NV + 1) * h->ld * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->fluxes, (size_t)NV * h->ld * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->par_surface, h->ld * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->mask, h->ld));
+    CREATE_TRY(cudaMalloc(&h->tables, (size_t)3 * MAXK * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->ctl, sizeof(Ctl)));
+    CREATE_TRY(cudaMalloc(&h->minloc_val, sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->minloc_idx, sizeof(long long)));
+    CREATE_TRY(cudaMallocHost(&h->ctl_host, sizeof(Ctl)));
+    CREATE_TRY(cudaMemsetAsync(h->buf[0], 0, state_bytes, h->stream));  // conc = 0.0_rk, component :531
+    CREATE_TRY(cudaMemsetAsync(h->buf[1], 0, state_bytes, h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->bdys, 0, (size_t)(NV + 1) * h->ld * sizeof(double), h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->fluxes, 0, (size_t)NV * h->ld * sizeof(double), h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->par_surface, 0, h->ld * sizeof(double), h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->mask, 0, h->ld, h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->ctl, 0, sizeof(Ctl), h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->minloc_idx, 0xff, sizeof(long long), h->stream));
+    std::vector<double> t(3 * MAXK, 0.0);
+    for (int k = 0; k < K; ++k) { t[k] = h->zc[k]; t[MAXK + k] = h->cumdepth[k]; t[2 * MAXK + k] = h->por_profile[k]; }
+    CREATE_TRY(cudaMemcpyAsync(h->tables, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    fill_porosity_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->por, h->mask, h->ld, h->ncol, K,
+                                                                  h->tables + 2 * MAXK);
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(cudaStreamSynchronize(h->stream));
+#undef CREATE_TRY
+    *out = h;
+    return MSED_OK;
+}
+
+int msed_destroy(msed_handle *h)
+{
+    if (!h) return MSED_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
+    cudaFree(h->buf[0]); cudaFree(h->buf[1]); cudaFree(h->aux[0]); cudaFree(h->aux[1]);
+    cudaFree(h->por); cudaFree(h->bdys); cudaFree(h->fluxes); cudaFree(h->par_surface);
+    cudaFree(h->scratch); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->ctl);
+    cudaFree(h->minloc_val); cudaFree(h->minloc_idx);
+    if (h->ctl_host) cudaFreeHost(h->ctl_host);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MSED_OK;
+}
+
+int msed_get_grid(const msed_handle *h, double *zi, double *zc, double *dz, double *dzc)
+{
+    if (!h) return MSED_ERR_ARG;
+    if (zi) std::memcpy(zi, h->zi.data(), h->zi.size() * sizeof(double));
+    if (zc) std::memcpy(zc, h->zc.data(), h->zc.size() * sizeof(double));
+    if (dz) std::memcpy(dz, h->dz.data(), h->dz.size() * sizeof(double));
+    if (dzc) std::memcpy(dzc, h->dzc.data(), h->dzc.size() * sizeof(double));
+    return MSED_OK;
+}
+
+int msed_set_mask(msed_handle *h, const int32_t *mask2d)
+{
+    if (!h || !mask2d) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    std::vector<unsigned char> m(h->ld, 0);
+    for (int c = 0; c < h->ncol; ++c) m[c] = mask2d[c] > 0 ? 1 : 0;
+    CUDA_TRY(h, cudaMemcpyAsync(h->mask, m.data(), h->ld, cudaMemcpyHostToDevice, h->stream));
+    apply_mask_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->por, h->buf[0], h->buf[1], h->mask, h->ld,
+                                                               h->ncol, h->K);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_set_porosity(msed_handle *h, const double *porosity3d)
+{
+    if (!h || !porosity3d) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = upload_rows(h, h->por, porosity3d, h->K);
+    if (rc) return rc;
+    apply_mask_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->por, h->buf[0], h->buf[1], h->mask, h->ld,
+                                                               h->ncol, h->K);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_update_porosity_from_surface(msed_handle *h, const double *porosity_surface2d)
+{
+    if (!h || !porosity_surface2d) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->scratch, porosity_surface2d, (size_t)h->ncol * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    porosity_from_surface_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
+        h->por, h->scratch, h->mask, h->ld, h->ncol, h->K, h->cfg.porosity_fac, h->tables);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_set_par_surface(msed_handle *h, const double *par_surface2d)
+{
+    if (!h || !par_surface2d) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->par_surface, par_surface2d, (size_t)h->ncol * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_check_domain(msed_handle *h)
+{
+    if (!h) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // grid conditions (driver :513-530) are properties of init_grid's closed form
+    for (int k = 0; k < h->K - 1; ++k)
+        if (h->dzc[k] <= 0) return fail(h, MSED_BAD_DOMAIN, "sediment central layer difference <= 0");
+    for (int k = 0; k < h->K; ++k)
+        if (h->dz[k] < h->cfg.dzmin) return fail(h, MSED_BAD_DOMAIN, "sediment layer height < minimum value");
+    // porosity conditions (driver :503-511) need the field
+    std::vector<double> por((size_t)h->K * h->ncol);
+    std::vector<unsigned char> m(h->ld);
+    int rc = download_rows(h, por.data(), h->por, h->K);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpy(m.data(), h->mask, h->ld, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < h->K; ++k)
+        for (int c = 0; c < h->ncol; ++c) {
+            if (m[c]) continue;
+            const double v = por[(size_t)k * h->ncol + c];
+            if (v <= 0) return fail(h, MSED_BAD_DOMAIN, "sediment porosity <=0");
+            if (v > 1) return fail(h, MSED_BAD_DOMAIN, "sediment porosity > 1");
+        }
+    apply_mask_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->por, h->buf[0], h->buf[1], h->mask, h->ld,
+                                                               h->ncol, h->K);  // driver :532-541
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_init_concentrations(msed_handle *h)
+{
+    if (!h) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    InitVals iv;
+    for (int n = 0; n < NV; ++n) iv.v[n] = h->cfg.initial_value[n];
+    init_conc_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->por, h->mask, h->ld,
+                                                              h->ncol, h->K, iv, 1.e20);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_set_state(msed_handle *h, const double *conc)
+{
+    if (!h || !conc) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = upload_rows(h, h->buf[h->cur], conc, (size_t)NV * h->K);
+    if (rc) return rc;
+    // masked columns must hold the same values in both buffers (the step kernels skip them)
+    copy_state_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->buf[1 - h->cur], h->buf[h->cur], h->ld,
+                                                               h->ncol, NV * h->K);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_get_state(msed_handle *h, double *conc)
+{
+    if (!h || !conc) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return download_rows(h, conc, h->buf[h->cur], (size_t)NV * h->K);
+}
+
+int msed_set_state_from_column(msed_handle *h, const double *conc1d)
+{
+    if (!h || !conc1d) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->scratch, conc1d, (size_t)NV * h->K * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    broadcast_column_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->scratch,
+                                                                     h->mask, h->ld, h->ncol, h->K);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_set_boundary(msed_handle *h, const double *bdys, const double *fluxes)
+{
+    if (!h) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    if (bdys && (rc = upload_rows(h, h->bdys, bdys, NV + 1))) return rc;
+    if (fluxes && (rc = upload_rows(h, h->fluxes, fluxes, NV))) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_set_boundary_device(msed_handle *h, const void *bdys_dev, const void *fluxes_dev)
+{
+    if (!h) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t w = (size_t)h->ncol * sizeof(double);
+    if (bdys_dev)
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->bdys, h->ld * sizeof(double), bdys_dev, w, w, NV + 1,
+                                      cudaMemcpyDeviceToDevice, h->stream));
+    if (fluxes_dev)
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->fluxes, h->ld * sizeof(double), fluxes_dev, w, w, NV,
+                                      cudaMemcpyDeviceToDevice, h->stream));
+    return MSED_OK;
+}
+
+int msed_get_fluxes_device(msed_handle *h, void *fluxes_dev)
+{
+    if (!h || !fluxes_dev) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t w = (size_t)h->ncol * sizeof(double);
+    CUDA_TRY(h, cudaMemcpy2DAsync(fluxes_dev, w, h->fluxes, h->ld * sizeof(double), w, NV,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+    return MSED_OK;
+}
+
+int msed_get_boundary_conditions(msed_handle *h, const double *temperature2d, const double *const *csurf,
+                                 const double *const *wz)
+{
+    if (!h) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    // pack the import fields that are present into the staging buffer (dense rows of ncol)
+    BcPtrs in;
+    std::memset(&in, 0, sizeof(in));
+    double *stage = h->scratch;
+    size_t row = 0;
+    const size_t w = (size_t)h->ncol;
+    auto push = [&](const double *src, const double **dst) -> int {
+        CUDA_TRY(h, cudaMemcpyAsync(stage + row * w, src, w * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        *dst = stage + row * w;
+        ++row;
+        return MSED_OK;
+    };
+    if (temperature2d && (rc = push(temperature2d, &in.temperature))) return rc;
+    for (int n = 0; n < NV; ++n) {
+        if (!csurf || !csurf[n]) continue;
+        if (n < NPART) {
+            if (!wz || !wz[n]) return fail(h, MSED_ERR_ARG, "particulate variable without z_velocity field");
+            if ((rc = push(wz[n], &in.wz[n]))) return rc;
+        }
+        if ((rc = push(csurf[n], &in.csurf[n]))) return rc;
+    }
+    boundary_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
+        h->bdys, h->fluxes, h->buf[h->cur], h->por, in, h->ld, w, h->ncol, h->K,
+        h->cfg.bcup_dissolved_variables, h->bioturbation_eff, h->cfg.diffusivity, h->dz[0]);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_get_boundary(msed_handle *h, double *bdys, double *fluxes)
+{
+    if (!h) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    if (bdys && (rc = download_rows(h, bdys, h->bdys, NV + 1))) return rc;
+    if (fluxes && (rc = download_rows(h, fluxes, h->fluxes, NV))) return rc;
+    return MSED_OK;
+}
+
+int msed_get_fluxes(msed_handle *h, double *fluxes)
+{
+    if (!h || !fluxes) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return download_rows(h, fluxes, h->fluxes, NV);
+}
+
+int msed_get_upward_fluxes(msed_handle *h, double *upward)
+{
+    if (!h || !upward) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    negate_rows_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->scratch, h->fluxes, h->ld, h->ncol, NV);
+    CUDA_TRY(h, cudaGetLastError());
+    return download_rows(h, upward, h->scratch, NV);
+}
+
+int msed_get_field(msed_handle *h, int which, double *out3d)
+{
+    if (!h || !out3d) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n2 = (size_t)h->ncol;
+    if (which == MSED_FIELD_POROSITY) return download_rows(h, out3d, h->por, h->K);
+    if (which == MSED_FIELD_LAYER_HEIGHT || which == MSED_FIELD_LAYER_CENTER_DEPTH) {
+        const std::vector<double> &t = (which == MSED_FIELD_LAYER_HEIGHT) ? h->dz : h->zc;
+        for (int k = 0; k < h->K; ++k)
+            for (size_t c = 0; c < n2; ++c) out3d[(size_t)k * n2 + c] = t[k];
+        return MSED_OK;
+    }
+    if (which < 0 || which > MSED_FIELD_FLUX_CAP) return fail(h, MSED_ERR_ARG, "unknown field");
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    KParams p;
+    fill_params(h, p);
+    // FABM diagnostics describe the state of the last get_rhs call: for Euler / adaptive Euler
+    // that is the buffer the accepted attempt read; for RK the last stage state c1 (same buffer)
+    const double *state = h->buf[h->cur];
+    if (which == MSED_FIELD_DENIT) state = h->buf[1 - h->cur];
+    field_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->scratch, which, p, h->par_surface, state,
+                                                          h->tables + MAXK, h->cfg.k_par, -999.0);
+    CUDA_TRY(h, cudaGetLastError());
+    return download_rows(h, out3d, h->scratch, h->K);
+}
+
+int msed_get_rhs(msed_handle *h, double *rhs)
+{
+    if (!h || !rhs) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    if (h->cfg.bioturbation_profile == 3) h->bioturbation_eff = 1.0;
+    KParams p;
+    fill_params(h, p);
+    p.use_ctl = 0;
+    p.buf[0] = h->buf[h->cur];
+    p.buf[1] = h->buf[1 - h->cur];
+    CUDA_TRY(h, launch_column(h, OP_RHS, p));
+    rc = download_rows(h, rhs, h->scratch, (size_t)NV * h->K);
+    if (rc) return rc;
+    // diagnostics now describe the current state: mirror it into the "last rhs state" buffer
+    copy_state_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->buf[1 - h->cur], h->buf[h->cur], h->ld,
+                                                               h->ncol, NV * h->K);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_ode_solver(msed_handle *h, double dt, int method, msed_step_info *info)
+{
+    if (!h) return MSED_ERR_ARG;
+    return run_steps(h, dt, method, 1, false, info);
+}
+
+int msed_step(msed_handle *h, double dt, int method, int64_t nsteps, msed_step_info *info)
+{
+    if (!h) return MSED_ERR_ARG;
+    return run_steps(h, dt, method, nsteps, true, info);
+}
+
+int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_step_info *info)
+{
+    if (!h) return MSED_ERR_ARG;
+    if (!(dt > 0.0) || run_seconds < 0.0) return fail(h, MSED_ERR_ARG, "dt <= 0 or run_seconds < 0");
+    // component :1700-1769: full steps of dt, the last one shortened to hit stopTime (:1705-1708)
+    long long nfull = (long long)std::floor(run_seconds / dt * (1.0 + 1e-14));
+    double rem = run_seconds - (double)nfull * dt;
+    if (rem < 1e-9 * dt) rem = 0.0;
+    msed_step_info a, b;
+    std::memset(&a, 0, sizeof(a));
+    std::memset(&b, 0, sizeof(b));
+    int rc = run_steps(h, dt, method, nfull, true, &a);
+    if (rc == MSED_OK && rem > 0.0) rc = run_steps(h, rem, method, 1, true, &b);
+    if (info) {
+        *info = a;
+        if (rem > 0.0) {
+            info->steps_done += b.steps_done;
+            info->rhs_evaluations += b.rhs_evaluations;
+            info->subcycle_warnings += b.subcycle_warnings;
+            info->last_min_dt = b.last_min_dt;
+            for (int q = 0; q < 4; ++q) info->last_min_dt_grid_cell[q] = b.last_min_dt_grid_cell[q];
+            info->nan_detected |= b.nan_detected;
+            info->kernel_ms += b.kernel_ms;
+            info->kernel_launches += b.kernel_launches;
+        }
+    }
+    return rc;
+}
+
+int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const double *fluxes1d, int64_t nsteps,
+                       int method, double *conc1d, msed_step_info *info)
+{
+    if (!cfg || !bdys1d || !fluxes1d || !conc1d) return fail(nullptr, MSED_ERR_ARG, "null argument");
+    // sed1d: a 1x1xknum clone with Dirichlet boundaries, constant bioturbation and solver
+    // diagnostics switched on (component :557-611); dt_spinup = 3600 s (:574)
+    msed_config c1 = *cfg;
+    c1.inum = c1.jnum = 1;
+    c1.i_offset = c1.j_offset = 0;
+    c1.bcup_dissolved_variables = 2;
+    c1.adaptive_solver_diagnostics = 1;
+    msed_handle *h = nullptr;
+    int rc = msed_create(&c1, &h);
+    if (rc) return rc;
+    // sed1d%bioturbation_profile=0 is set AFTER initialize (:611): the bioturbation_factor table
+    // keeps the shape it was initialised with; only the profile-3 branch is switched off
+    h->cfg.bioturbation_profile = (c1.bioturbation_profile == 3) ? 0 : c1.bioturbation_profile;
+    if ((rc = msed_check_domain(h)) || (rc = msed_init_concentrations(h)) ||
+        (rc = msed_set_boundary(h, bdys1d, fluxes1d))) {
+        g_err = h->err;
+        msed_destroy(h);
+        return rc;
+    }
+    rc = run_steps(h, 3600.0, method, nsteps, false, info);  // ode_solver only, no clipping (:614-618)
+    if (rc == MSED_OK) rc = msed_get_state(h, conc1d);
+    if (rc) g_err = h->err;
+    msed_destroy(h);
+    return rc;
+}
+
+int msed_set_stream(msed_handle *h, void *cuda_stream)
+{
+    if (!h) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = (cudaStream_t)cuda_stream;
+    return MSED_OK;
+}
+
+int msed_synchronize(msed_handle *h)
+{
+    if (!h) return MSED_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_device_state(msed_handle *h, void **dev_ptr, size_t *ld)
+{
+    if (!h || !dev_ptr || !ld) return MSED_ERR_ARG;
+    *dev_ptr = h->buf[h->cur];
+    *ld = h->ld;
+    return MSED_OK;
+}
+
+int msed_nccl_unique_id(char id[128])
+{
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(nullptr, MSED_ERR_NCCL, "libnccl.so.2 not found");
+    NcclUniqueId u;
+    int rc = api.GetUniqueId(&u);
+    if (rc != 0) return fail(nullptr, MSED_ERR_NCCL, "ncclGetUniqueId failed");
+    std::memcpy(id, u.internal, 128);
+    return MSED_OK;
+}
+
+int msed_comm_init(msed_handle *h, const char id[128], int nranks, int rank)
+{
+    if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, MSED_ERR_ARG, "bad comm arguments");
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(h, MSED_ERR_NCCL, "libnccl.so.2 not found");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    NcclUniqueId u;
+    std::memcpy(u.internal, id, 128);
+    int rc = api.CommInitRank(&h->comm, nranks, u, rank);
+    if (rc != 0) {
+        h->comm = nullptr;
+        return fail(h, MSED_ERR_NCCL, std::string("ncclCommInitRank: ") +
+                                          (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+    }
+    h->nranks = nranks;
+    h->rank = rank;
+    return MSED_OK;
+}
+
+int msed_comm_destroy(msed_handle *h)
+{
+    if (!h) return MSED_ERR_ARG;
+    if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
+    h->nranks = 1;
+    h->rank = 0;
+    return MSED_OK;
+}
+
+int msed_set_allreduce_hook(msed_handle *h, msed_allreduce_hook hook, void *user)
+{
+    if (!h) return MSED_ERR_ARG;
+    h->hook = hook;
+    h->hook_user = user;
+    return MSED_OK;
+}
+
+}  // extern "C"

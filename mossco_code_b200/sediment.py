@@ -1,0 +1,297 @@
+"""Host-side mirror of the reference's driver/solver contract over the C ABI.
+
+``SedimentDriver`` plays the role of ``type_sed`` (src/drivers/fabm_sediment_driver.F90:69-113,
+which extends ``type_rhs_driver``, src/utilities/solver_library.F90:37-49) and keeps the reference's
+names: ``init_grid``/``initialize`` (folded into the constructor as in the component), ``update_porosity``,
+``init_concentrations``, ``check_domain``, ``get_rhs`` and the module-level ``ode_solver(sed, dt, method)``.
+Arrays cross the boundary as numpy fp64 in Fortran order with the reference's shapes.
+
+Everything here calls libmsed_b200.so; there is no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import (ADAPTIVE_EULER, EULER, MODEL_NONE, MODEL_OMEXDIA_P, MODEL_TEST_SOLVER, NVAR,
+                   RUNGE_KUTTA_4, RUNGE_KUTTA_4_38, Config, MsedError, StepInfo)
+
+# hzg_omexdia_p state variables in FABM order (examples/standalone/omexdia_p/plotbulknutrients.py:57-62)
+STATE_NAMES = ("ldetC", "sdetC", "detP", "po4", "no3", "nh3", "oxy", "odu")
+# import/export names: standard name if set else only_var_name(long_name)
+# (src/components/fabm_sediment_component.F90:1941-1947; src/mediators/pelagic_benthic_coupler.F90:399-481)
+VARIABLE_NAMES = (
+    "detritus_labile_carbon", "detritus_semilabile_carbon", "detritus_labile_phosphorus",
+    "mole_concentration_of_phosphate", "mole_concentration_of_nitrate",
+    "mole_concentration_of_ammonium", "dissolved_oxygen", "dissolved_reduced_substances",
+)
+PARTICULATE = (True, True, True, False, False, False, False, False)  # main.F90:92-101
+
+
+def default_config(**kw) -> Config:
+    """Reference defaults (fabm_sediment_driver.F90:217-231, component :59-67, fabm_sed.nml:51-77)."""
+    cfg = Config()
+    rc = _abi.load().msed_config_defaults(C.byref(cfg))
+    if rc:
+        raise MsedError(rc, "msed_config_defaults")
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(f"msed_config has no field {k!r}")
+        if k in ("initial_value", "minimum"):
+            for n in range(NVAR):
+                getattr(cfg, k)[n] = float(v[n])
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def _f64(a, shape=None, name="array") -> np.ndarray:
+    a = np.asarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return np.asfortranarray(a)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class SedimentDriver:
+    """``type_sed`` on the GPU: one horizontal tile (inum x jnum columns, knum layers)."""
+
+    def __init__(self, cfg: Config):
+        self._lib = _abi.load()
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = self._lib.msed_create(C.byref(cfg), C.byref(self._h))
+        if rc:
+            raise MsedError(rc, (self._lib.msed_last_error(None) or b"").decode())
+        self.inum, self.jnum, self.knum, self.nvar = cfg.inum, cfg.jnum, cfg.knum, NVAR
+        self.info = StepInfo()
+        self._hook_ref = None
+
+    # -- lifecycle ------------------------------------------------------------------------
+    def finalize(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.msed_destroy(self._h)
+            self._h = C.c_void_p()
+
+    close = finalize
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.finalize()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.finalize()
+
+    def _check(self, rc: int, allow: Sequence[int] = ()):
+        if rc and rc not in allow:
+            raise MsedError(rc, (self._lib.msed_last_error(self._h) or b"").decode())
+        return rc
+
+    # -- shapes ---------------------------------------------------------------------------
+    @property
+    def shape2d(self):
+        return (self.inum, self.jnum)
+
+    @property
+    def shape3d(self):
+        return (self.inum, self.jnum, self.knum)
+
+    @property
+    def shape4d(self):
+        return (self.inum, self.jnum, self.knum, self.nvar)
+
+    # -- grid / static fields -------------------------------------------------------------
+    def grid(self):
+        """(zi, zc, dz, dzc) of ``init_grid`` (fabm_sediment_driver.F90:147-168)."""
+        K = self.knum
+        zi, zc, dz, dzc = np.zeros(K + 1), np.zeros(K), np.zeros(K), np.zeros(K - 1)
+        self._check(self._lib.msed_get_grid(self._h, _ptr(zi), _ptr(zc), _ptr(dz), _ptr(dzc)))
+        return zi, zc, dz, dzc
+
+    def set_mask(self, mask2d):
+        m = np.asfortranarray(np.asarray(mask2d, dtype=np.int32))
+        if m.shape != self.shape2d:
+            raise ValueError(f"mask: expected {self.shape2d}, got {m.shape}")
+        self._check(self._lib.msed_set_mask(self._h, m.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def set_porosity(self, porosity3d):
+        a = _f64(porosity3d, self.shape3d, "porosity")
+        self._check(self._lib.msed_set_porosity(self._h, _ptr(a)))
+
+    def update_porosity(self, porosity_surface=None, from_surface: bool = True):
+        """``update_porosity(from_surface=.true.)`` (fabm_sediment_driver.F90:393-442)."""
+        if not from_surface:
+            return
+        a = _f64(porosity_surface, self.shape2d, "porosity_surface")
+        self._check(self._lib.msed_update_porosity_from_surface(self._h, _ptr(a)))
+
+    def set_par_surface(self, par2d):
+        a = _f64(par2d, self.shape2d, "par_surface")
+        self._check(self._lib.msed_set_par_surface(self._h, _ptr(a)))
+
+    def check_domain(self):
+        return self._check(self._lib.msed_check_domain(self._h))
+
+    # -- state ----------------------------------------------------------------------------
+    def init_concentrations(self):
+        self._check(self._lib.msed_init_concentrations(self._h))
+
+    @property
+    def conc(self) -> np.ndarray:
+        out = np.zeros(self.shape4d, order="F")
+        self._check(self._lib.msed_get_state(self._h, _ptr(out)))
+        return out
+
+    @conc.setter
+    def conc(self, value):
+        a = _f64(value, self.shape4d, "conc")
+        self._check(self._lib.msed_set_state(self._h, _ptr(a)))
+
+    def set_state_from_column(self, conc1d):
+        a = _f64(conc1d, (1, 1, self.knum, self.nvar), "conc1d")
+        self._check(self._lib.msed_set_state_from_column(self._h, _ptr(a)))
+
+    # -- boundary -------------------------------------------------------------------------
+    def set_boundary(self, bdys=None, fluxes=None):
+        """``sed%bdys => bdys; sed%fluxes => fluxes`` (component :1666-1667)."""
+        b = None if bdys is None else _f64(bdys, self.shape2d + (self.nvar + 1,), "bdys")
+        f = None if fluxes is None else _f64(fluxes, self.shape2d + (self.nvar,), "fluxes")
+        self._check(self._lib.msed_set_boundary(self._h, _ptr(b), _ptr(f)))
+
+    def get_boundary_conditions(self, temperature=None, csurf=None, wz=None):
+        """``get_boundary_conditions`` (component :1865-2030). ``csurf``/``wz``: per-variable 2-D
+        import fields or None (== field not in the import state)."""
+        keep = []
+        t = None if temperature is None else _f64(temperature, self.shape2d, "temperature")
+        cs = (C.POINTER(C.c_double) * NVAR)()
+        ws = (C.POINTER(C.c_double) * NVAR)()
+        for n in range(NVAR):
+            for arr, src in ((cs, csurf), (ws, wz)):
+                if src is not None and src[n] is not None:
+                    a = _f64(src[n], self.shape2d, "import field")
+                    keep.append(a)
+                    arr[n] = _ptr(a)
+        self._check(self._lib.msed_get_boundary_conditions(self._h, _ptr(t), cs, ws))
+
+    @property
+    def bdys(self) -> np.ndarray:
+        out = np.zeros(self.shape2d + (self.nvar + 1,), order="F")
+        self._check(self._lib.msed_get_boundary(self._h, _ptr(out), None))
+        return out
+
+    @property
+    def fluxes(self) -> np.ndarray:
+        out = np.zeros(self.shape2d + (self.nvar,), order="F")
+        self._check(self._lib.msed_get_fluxes(self._h, _ptr(out)))
+        return out
+
+    def upward_fluxes(self) -> np.ndarray:
+        """``<var>_upward_flux_at_soil_surface`` = -fluxes (component :1819)."""
+        out = np.zeros(self.shape2d + (self.nvar,), order="F")
+        self._check(self._lib.msed_get_upward_fluxes(self._h, _ptr(out)))
+        return out
+
+    def field(self, name: str) -> np.ndarray:
+        out = np.zeros(self.shape3d, order="F")
+        self._check(self._lib.msed_get_field(self._h, _abi.FIELDS[name], _ptr(out)))
+        return out
+
+    # -- hot path -------------------------------------------------------------------------
+    def get_rhs(self) -> np.ndarray:
+        """``type_sed%get_rhs`` (fabm_sediment_driver.F90:575-717)."""
+        out = np.zeros(self.shape4d, order="F")
+        self._check(self._lib.msed_get_rhs(self._h, _ptr(out)))
+        return out
+
+    def ode_solver(self, dt: float, method: int = ADAPTIVE_EULER) -> StepInfo:
+        """One ``ode_solver(sed, dt, method)`` call (solver_library.F90:80-189)."""
+        self._check(self._lib.msed_ode_solver(self._h, float(dt), int(method), C.byref(self.info)))
+        return self.info
+
+    def step(self, dt: float, method: int = ADAPTIVE_EULER, nsteps: int = 1) -> int:
+        """``nsteps`` iterations of the Run loop body: ode_solver + check_NaN + clip
+        (component :1715-1732).  Returns 0 or NAN_DETECTED."""
+        return self._check(self._lib.msed_step(self._h, float(dt), int(method), int(nsteps),
+                                               C.byref(self.info)), allow=(_abi.NAN_DETECTED,))
+
+    def run(self, dt: float, method: int, run_seconds: float) -> int:
+        """The component's ``do while (.not.stopTime)`` loop (component :1700-1769)."""
+        return self._check(self._lib.msed_run(self._h, float(dt), int(method), float(run_seconds),
+                                              C.byref(self.info)), allow=(_abi.NAN_DETECTED,))
+
+    # -- execution / multi-GPU ---------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.msed_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._lib.msed_synchronize(self._h))
+
+    def device_state(self):
+        p, ld = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.msed_device_state(self._h, C.byref(p), C.byref(ld)))
+        return p.value, ld.value
+
+    def comm_init(self, unique_id: bytes, nranks: int, rank: int):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.msed_comm_init(self._h, buf, nranks, rank))
+
+    def set_allreduce_hook(self, fn):
+        """fn(dev_ptr:int, count:int, stream:int) -> int ; MAX-reduce ``count`` int32 device flags."""
+        if fn is None:
+            self._hook_ref = None
+            self._check(self._lib.msed_set_allreduce_hook(self._h, _abi.ALLREDUCE_HOOK(0), None))
+            return
+
+        def tramp(user, ptr, count, stream):
+            try:
+                return int(fn(ptr or 0, count, stream or 0) or 0)
+            except Exception:  # pragma: no cover
+                return 1
+
+        self._hook_ref = _abi.ALLREDUCE_HOOK(tramp)
+        self._check(self._lib.msed_set_allreduce_hook(self._h, self._hook_ref, None))
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_char * 128)()
+    rc = _abi.load().msed_nccl_unique_id(buf)
+    if rc:
+        raise MsedError(rc, (_abi.load().msed_last_error(None) or b"").decode())
+    return bytes(buf)
+
+
+def ode_solver(rhs_driver: SedimentDriver, dt: float, method: int) -> StepInfo:
+    """``call ode_solver(sed, dt, ode_method)`` (src/utilities/solver_library.F90:80)."""
+    return rhs_driver.ode_solver(dt, method)
+
+
+def spinup_column(cfg: Config, bdys1d, fluxes1d, nsteps: int, method: int = ADAPTIVE_EULER):
+    """1-D pre-simulation (component :557-632): returns conc(1,1,knum,nvar) and the StepInfo."""
+    b = _f64(np.asarray(bdys1d).reshape(-1), (NVAR + 1,), "bdys1d")
+    f = _f64(np.asarray(fluxes1d).reshape(-1), (NVAR,), "fluxes1d")
+    out = np.zeros((1, 1, cfg.knum, NVAR), order="F")
+    info = StepInfo()
+    lib = _abi.load()
+    rc = lib.msed_spinup_column(C.byref(cfg), _ptr(b), _ptr(f), int(nsteps), int(method), _ptr(out),
+                                C.byref(info))
+    if rc:
+        raise MsedError(rc, (lib.msed_last_error(None) or b"").decode())
+    return out, info
+
+
+__all__ = [
+    "SedimentDriver", "ode_solver", "default_config", "spinup_column", "nccl_unique_id",
+    "STATE_NAMES", "VARIABLE_NAMES", "PARTICULATE", "EULER", "RUNGE_KUTTA_4", "ADAPTIVE_EULER",
+    "RUNGE_KUTTA_4_38", "MODEL_OMEXDIA_P", "MODEL_NONE", "MODEL_TEST_SOLVER",
+]

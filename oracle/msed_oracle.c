@@ -1,0 +1,850 @@
+/*
+ * msed_oracle.c -- TEST INFRASTRUCTURE ONLY (see msed_oracle.h).
+ *
+ * Plain-C restatement of the reference's CPU algorithm for the fabm_sediment column
+ * solver.  Every routine follows the reference's loop and operation order, including its
+ * un-fused whole-array pass structure (the structure is what the CPU baseline times).
+ * Paths are relative to /root/reference.
+ *
+ * Compile the parity build with -ffp-contract=off so no FMA contraction changes the
+ * rounding the Fortran source order implies.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "msed_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define I3(s, i, j, k) ((size_t)(i) + (size_t)(s)->base.inum * ((size_t)(j) + (size_t)(s)->base.jnum * (size_t)(k)))
+#define N3(s) ((size_t)(s)->base.inum * (s)->base.jnum * (s)->base.knum)
+#define N2(s) ((size_t)(s)->base.inum * (s)->base.jnum)
+
+static double *dalloc(size_t n, double v)
+{
+    double *p = (double *)malloc((n ? n : 1) * sizeof(double));
+    if (!p) { fprintf(stderr, "msed_oracle: out of memory\n"); abort(); }
+    for (size_t i = 0; i < n; ++i) p[i] = v;
+    return p;
+}
+
+/* ---- defaults ------------------------------------------------------------------------- */
+
+/* src/drivers/fabm_sediment_driver.F90:217-231 */
+void osed_sed_nml_defaults(osed_sed_nml *nml)
+{
+    nml->bioturbation_profile = 1;
+    nml->diffusivity = 0.9;
+    nml->bioturbation = 0.9;
+    nml->bioturbation_depth = 5.0;
+    nml->bioturbation_min = 0.2;
+    nml->porosity_max = 0.7;
+    nml->porosity_fac = 0.9;
+    nml->k_par = 2.0e-3;
+    nml->pom_flux_max = 2.0e4;
+    nml->bioturb_k_l = 0.11;
+    nml->bioturb_L1 = 0.2;
+    nml->bioturb_L2 = 0.6;
+    nml->bioturb_beta = 0.22;
+    nml->bioturb_b = 1.334;
+    nml->bioturb_dry_density = 1000.;
+    nml->distributed_pom_flux = 0;
+}
+
+/* examples/standalone/omexdia_p/fabm_sed.nml:51-77; state order from
+ * examples/standalone/omexdia_p/plotbulknutrients.py:57-62 */
+void osed_omexdia_defaults(osed_omexdia_params *p)
+{
+    p->rLabile = 0.043;  p->rSemilabile = 0.001;
+    p->NCrLdet = 0.22;   p->NCrSdet = 0.005;
+    p->PAds = 0.01;      p->PAdsODU = 70.;
+    p->NH3Ads = 0.0;     p->CprodMax = 9600.0;
+    p->rnit = 200.;      p->ksO2nitri = 20.;
+    p->rODUox = 20.;     p->ksO2oduox = 1.;
+    p->ksO2oxic = 3.;    p->ksNO3denit = 1.;
+    p->kinO2denit = 70.; p->kinNO3anox = 1.;
+    p->kinO2anox = 1.;
+    const double init[8] = {4.e3, 4.e3, 4.e1, 10., 20., 40., 100., 100.};
+    for (int n = 0; n < 8; ++n) { p->init[n] = init[n]; p->minimum[n] = 0.0; }
+}
+
+/* ---- grid ----------------------------------------------------------------------------- */
+
+/* fabm_sed_grid%init_grid, src/drivers/fabm_sediment_driver.F90:127-177 */
+int osed_init_grid(osed_sed *s, int inum, int jnum, int knum, double dzmin)
+{
+    memset(s, 0, sizeof(*s));
+    if (inum < 0 || jnum < 0) return 1; /* :139-142 */
+    s->base.inum = inum; s->base.jnum = jnum; s->base.knum = knum;
+    s->dzmin = dzmin;
+    /* :147 */
+    double self_fac = 0.18 / ((knum + 1) / 2.0 * dzmin) - 1.0;
+    size_t n2 = (size_t)inum * jnum;
+    s->dz = dalloc(n2 * knum, 0.0);
+    s->zc = dalloc(n2 * knum, 0.0);
+    s->zi = dalloc(n2 * (knum + 1), 0.0);
+    s->dzc = dalloc(n2 * (knum > 1 ? knum - 1 : 0), 0.0);
+    /* :159-166 (k is 1-based in the Fortran expression) */
+    for (int k = 1; k <= knum; ++k)
+        for (int j = 0; j < jnum; ++j)
+            for (int i = 0; i < inum; ++i) {
+                size_t c = I3(s, i, j, k - 1), cn = I3(s, i, j, k);
+                s->dz[c] = (1.0 + (self_fac - 1.0) * (double)(k - 1) / (double)(knum - 1)) * dzmin;
+                s->zc[c] = s->zi[c] + 0.5 * s->dz[c];
+                s->zi[cn] = s->zi[c] + s->dz[c];
+            }
+    /* :168 */
+    for (int k = 0; k < knum - 1; ++k)
+        for (size_t c = 0; c < n2; ++c)
+            s->dzc[c + n2 * k] = s->zc[c + n2 * (k + 1)] - s->zc[c + n2 * k];
+    return 0;
+}
+
+/* update_porosity, src/drivers/fabm_sediment_driver.F90:393-442 */
+void osed_update_porosity(osed_sed *s, int from_surface)
+{
+    const int K = s->base.knum;
+    const size_t n2 = N2(s);
+    if (from_surface) {
+        for (int k = 1; k < K; ++k) /* :409-413 */
+            for (size_t c = 0; c < n2; ++c)
+                s->porosity[c + n2 * k] = s->porosity[c] *
+                    (1.0 - s->porosity_fac * (s->zc[c + n2 * k] - s->zc[c]));
+        for (int k = 0; k < K; ++k) { /* :415-427 */
+            for (size_t c = 0; c < n2; ++c)
+                s->flux_cap[c + n2 * k] = s->pom_flux_max / 86400.0 *
+                    (1.0 - s->porosity[c + n2 * k]) * s->dz[c + n2 * k];
+            if (k + 1 > 2)
+                for (size_t c = 0; c < n2; ++c)
+                    if (s->flux_cap[c + n2 * k] > s->flux_cap[c + n2 * (k - 1)])
+                        s->flux_cap[c + n2 * k] = s->flux_cap[c + n2 * (k - 1)];
+        }
+    }
+    /* :431 */
+    for (size_t c = 0; c < N3(s); ++c)
+        if (s->base.mask[c] > 0) s->porosity[c] = 1.0;
+    /* :434-435 */
+    for (size_t c = 0; c < n2; ++c) s->intf_porosity[c] = s->porosity[c];
+    for (int k = 1; k < K; ++k)
+        for (size_t c = 0; c < n2; ++c)
+            s->intf_porosity[c + n2 * k] = 0.5 * (s->porosity[c + n2 * (k - 1)] + s->porosity[c + n2 * k]);
+}
+
+/* type_sed%initialize, src/drivers/fabm_sediment_driver.F90:191-388 (numeric parts) */
+int osed_initialize(osed_sed *s, const osed_sed_nml *nml, int model,
+                    const osed_omexdia_params *p, const int *mask)
+{
+    const int K = s->base.knum;
+    const size_t n2 = N2(s), n3 = N3(s);
+    s->bioturbation = nml->bioturbation;                   /* :235-238 */
+    s->bioturbation_profile = nml->bioturbation_profile;
+    s->diffusivity = nml->diffusivity;
+    s->k_par = nml->k_par;
+    s->bcup_particulate_variables = nml->distributed_pom_flux ? 4 : 1; /* :239-243 */
+    s->bcup_dissolved_variables = 2;                       /* :79 */
+    s->missing_value = 1.e20;                              /* :85 */
+    s->base.dt_min = 1.e-9;                                /* solver_library.F90:40 */
+    s->base.relative_change_min = -0.9;
+    s->base.last_min_dt = (double)1.e20f;                  /* :44  real-kind literal 1.e20 */
+    for (int q = 0; q < 4; ++q) s->base.last_min_dt_grid_cell[q] = -99;
+    s->base.adaptive_solver_diagnostics = 0;
+    s->base.get_rhs = osed_get_rhs;
+
+    s->base.mask = (int *)calloc(n3 ? n3 : 1, sizeof(int)); /* :250-253 */
+    s->owns_mask = 1;
+    if (mask) memcpy(s->base.mask, mask, n3 * sizeof(int));
+
+    s->porosity = dalloc(n3, 0.0);                         /* :262-277 */
+    s->intf_porosity = dalloc(n3, 0.0);
+    s->bioturbation_factor = dalloc(n3, 1.0);
+    s->biomass = dalloc(n3, 0.0);
+    s->weighted_toc = dalloc(n3, 0.0);
+    s->par = dalloc(n3, 0.0);
+    s->par_surface = dalloc(n2, 0.0);
+    s->flux_cap = dalloc(n3, 0.0);
+    s->porosity_fac = nml->porosity_fac;
+    s->pom_flux_max = nml->pom_flux_max;
+    for (int k = 0; k < K; ++k) {                          /* :278-304 */
+        for (size_t c = 0; c < n2; ++c) {
+            size_t q = c + n2 * k;
+            s->porosity[q] = nml->porosity_max * (1.0 - nml->porosity_fac * s->zc[q]);
+            s->flux_cap[q] = nml->pom_flux_max / 86400.0 * (1.0 - s->porosity[q]) * s->dz[q];
+        }
+        if (k + 1 > 2)
+            for (size_t c = 0; c < n2; ++c)
+                if (s->flux_cap[c + n2 * k] > s->flux_cap[c + n2 * (k - 1)])
+                    s->flux_cap[c + n2 * k] = s->flux_cap[c + n2 * (k - 1)];
+        for (size_t c = 0; c < n2; ++c) {
+            size_t q = c + n2 * k;
+            switch (nml->bioturbation_profile) {
+            case 1:
+                s->bioturbation_factor[q] = fmax(nml->bioturbation_min / nml->bioturbation,
+                    fmax(nml->bioturbation_depth - 100.0 * s->zi[q], 0.0) / nml->bioturbation_depth);
+                break;
+            case 2:
+                s->bioturbation_factor[q] = exp(-100.0 * s->zi[q] / nml->bioturbation_depth);
+                break;
+            default: break;
+            }
+        }
+    }
+    osed_update_porosity(s, 0);                            /* :313 */
+
+    s->model = model;                                      /* :328-354 */
+    if (p) s->p = *p; else osed_omexdia_defaults(&s->p);
+    s->base.nvar = OSED_NVAR_OMEXDIA;
+    /* particulate property: examples/standalone/omexdia_p/main.F90:92-101 */
+    const int part[8] = {1, 1, 1, 0, 0, 0, 0, 0};
+    for (int n = 0; n < 8; ++n) s->particulate[n] = part[n];
+
+    s->diff = dalloc(n3, nml->diffusivity);                /* :356-370 */
+    s->transport = dalloc(n3 * s->base.nvar, 0.0);
+    s->temp3d = dalloc(n3, -999.0);
+    s->diag_denit = dalloc(n3, 0.0);
+
+    s->k_l = nml->bioturb_k_l; s->L1 = nml->bioturb_L1; s->L2 = nml->bioturb_L2; /* :373-386 */
+    s->beta = nml->bioturb_beta; s->b = nml->bioturb_b;
+    s->poc_factor[0] = 1.0 / 1.2 * 12.01 / nml->bioturb_dry_density / 1000.0;
+    s->poc_factor[1] = 1.0 / 6.0 * 12.01 / nml->bioturb_dry_density / 1000.0;
+    s->poc_data[0] = s->poc_data[1] = NULL;
+    return 0;
+}
+
+/* init_concentrations, src/drivers/fabm_sediment_driver.F90:449-481 */
+void osed_init_concentrations(osed_sed *s)
+{
+    const size_t n3 = N3(s);
+    for (int n = 0; n < s->base.nvar; ++n)                 /* :455-458 */
+        for (size_t c = 0; c < n3; ++c)
+            s->base.conc[c + n3 * n] = s->p.init[n] / s->porosity[c];
+    for (size_t c = 0; c < n3; ++c)                        /* :459-468 */
+        if (s->base.mask[c] > 0)
+            for (int n = 0; n < s->base.nvar; ++n) s->base.conc[c + n3 * n] = s->missing_value;
+    s->poc_data[0] = s->base.conc;                         /* :471-479 */
+    s->poc_data[1] = s->base.conc + n3;
+}
+
+/* fabm_sed_check_domain, src/drivers/fabm_sediment_driver.F90:488-545 */
+int osed_check_domain(osed_sed *s)
+{
+    const size_t n2 = N2(s), n3 = N3(s);
+    const int K = s->base.knum;
+    for (size_t c = 0; c < n3; ++c) {
+        if (!(s->base.mask[c] > 0) && s->porosity[c] <= 0) return 1;   /* :503 */
+        if (!(s->base.mask[c] > 0) && s->porosity[c] > 1) return 2;    /* :508 */
+    }
+    for (int k = 0; k < K - 1; ++k)                                    /* :513 */
+        for (size_t c = 0; c < n2; ++c)
+            if (!(s->base.mask[c + n2 * k] > 0) && !(s->base.mask[c + n2 * (k + 1)] > 0) &&
+                s->dzc[c + n2 * k] <= 0) return 3;
+    for (size_t c = 0; c < n3; ++c)                                    /* :523 */
+        if (!(s->base.mask[c] > 0) && s->dz[c] < s->dzmin) return 4;
+    if (s->base.conc)                                                  /* :532-538 */
+        for (size_t c = 0; c < n3; ++c)
+            if (s->base.mask[c] > 0)
+                for (int n = 0; n < s->base.nvar; ++n) s->base.conc[c + n3 * n] = 1.e20;
+    for (size_t c = 0; c < n3; ++c)                                    /* :541 */
+        if (s->base.mask[c] > 0) s->porosity[c] = 1.0;
+    return 0;
+}
+
+void osed_finalize(osed_sed *s)
+{
+    free(s->zi); free(s->zc); free(s->dz); free(s->dzc);
+    free(s->porosity); free(s->intf_porosity); free(s->bioturbation_factor);
+    free(s->biomass); free(s->weighted_toc); free(s->par); free(s->par_surface);
+    free(s->flux_cap); free(s->diff); free(s->transport); free(s->temp3d); free(s->diag_denit);
+    if (s->owns_mask) free(s->base.mask);
+    memset(s, 0, sizeof(*s));
+}
+
+/* ---- reaction term -------------------------------------------------------------------- */
+
+/* hzg_omexdia_p `do`: source NOT in /root/reference (FABM is cloned at build time,
+ * external/include/fabm.mk:18).  Restates SURVEY.md Appendix B, the project's frozen spec. */
+void osed_omexdia_p_cell(const osed_omexdia_params *p, const double c[8], double temp_celsius,
+                         double rate[8], double *denit)
+{
+    const double ldetC = c[0], sdetC = c[1], detP = c[2], po4 = c[3];
+    const double no3 = c[4], nh3 = c[5], oxy = c[6], odu = c[7];
+    const double relaxO2 = 0.04, T0 = 288.15, Q10b = 1.5;
+    const double rLabile = p->rLabile / 86400.0, rSemilabile = p->rSemilabile / 86400.0;
+    const double rnit = p->rnit / 86400.0, rODUox = p->rODUox / 86400.0;
+
+    double temp_kelvin = temp_celsius + 273.15;
+    double E_a = 0.1 * log(Q10b) * T0 * (T0 + 10.0);
+    double f_T = exp(-E_a * (1.0 / temp_kelvin - 1.0 / T0));
+
+    double Oxicminlim = oxy / (oxy + p->ksO2oxic + relaxO2 * (nh3 + odu));
+    double Denitrilim = (1.0 - oxy / (oxy + p->kinO2denit)) * no3 / (no3 + p->ksNO3denit);
+    double Anoxiclim = (1.0 - oxy / (oxy + p->kinO2anox)) * (1.0 - no3 / (no3 + p->kinNO3anox));
+    double Rescale = 1.0 / (Oxicminlim + Denitrilim + Anoxiclim);
+
+    double CprodL = rLabile * ldetC;
+    double CprodS = rSemilabile * sdetC;
+    double Cprod = CprodL + CprodS;
+    double cmax = p->CprodMax / 86400.0;
+    if (Cprod > cmax) Cprod = cmax;
+    double Nprod = CprodL * p->NCrLdet + CprodS * p->NCrSdet;
+
+    double radsP = p->PAds * rSemilabile * po4 * fmax(odu, p->PAdsODU);
+    double rP = rLabile * (1.0 - Oxicminlim);
+    double Pprod = rP * detP;
+
+    double OxicMin = Cprod * Oxicminlim * Rescale;
+    double Denitrific = Cprod * Denitrilim * Rescale;
+    double AnoxicMin = Cprod * Anoxiclim * Rescale;
+
+    double Nitri = f_T * rnit * nh3 * oxy / (oxy + p->ksO2nitri + relaxO2 * (ldetC + odu));
+    double OduOx = f_T * rODUox * odu * oxy / (oxy + p->ksO2oduox + relaxO2 * (nh3 + ldetC));
+
+    rate[0] = -f_T * CprodL;
+    rate[1] = -f_T * CprodS;
+    rate[2] = f_T * (radsP - Pprod);
+    rate[3] = f_T * (Pprod - radsP);
+    rate[4] = -0.8 * Denitrific + Nitri;
+    rate[5] = (Nprod - Nitri) / (1.0 + p->NH3Ads);
+    rate[6] = -OxicMin - 2.0 * Nitri - OduOx;
+    rate[7] = AnoxicMin - OduOx;
+    if (denit) *denit = 0.8 * Denitrific;
+}
+
+/* ---- transport ------------------------------------------------------------------------ */
+
+/* diff3d, src/drivers/fabm_sediment_driver.F90:739-825.
+ * Flux is (i,j,knum+1); masked columns keep dC = 0 and leave Flux untouched. */
+void osed_diff3d(const osed_sed *s, const double *C, const double *Cup, const double *Cdown,
+                 const double *fluxup, const double *fluxdown, int BcUp, int BcDown,
+                 const double *D, const double *VF, double *Flux, double *dC,
+                 const double *flux_cap)
+{
+    const int inum = s->base.inum, jnum = s->base.jnum, K = s->base.knum;
+    const size_t n2 = N2(s), n3 = N3(s);
+    for (size_t c = 0; c < n3; ++c) dC[c] = 0.0;                        /* :769 */
+    for (int j = 0; j < jnum; ++j)
+        for (int i = 0; i < inum; ++i) {
+            const size_t c = (size_t)i + (size_t)inum * j;
+            if (s->base.mask[c] > 0) continue;                          /* :775 */
+            for (int k = 1; k < K; ++k)                                 /* :776-778 */
+                Flux[c + n2 * k] = -D[c + n2 * k] * (C[c + n2 * k] - C[c + n2 * (k - 1)]) /
+                                   s->dzc[c + n2 * (k - 1)];
+            if (BcUp == 1) {                                            /* :782-803 */
+                Flux[c] = fluxup[c];
+            } else if (BcUp == 2) {
+                Flux[c] = -D[c] * (C[c] - Cup[c]) / s->dz[c];
+            } else if (BcUp == 3) {
+                Flux[c] = 0.0;
+            } else if (BcUp == 4) {
+                Flux[c] = fluxup[c];
+                int k = 2; /* 1-based */
+                double restflux = Flux[c] - flux_cap[c];
+                while (restflux > 0 && k <= K) {
+                    Flux[c + n2 * (k - 1)] = Flux[c + n2 * (k - 1)] + restflux;
+                    restflux = restflux - flux_cap[c + n2 * (k - 1)];
+                    k = k + 1;
+                }
+                if (k > K) Flux[c + n2 * (K - 1)] = Flux[c + n2 * (K - 1)] + restflux;
+            }
+            if (BcDown == 1) {                                          /* :806-816 */
+                Flux[c + n2 * K] = fluxdown[c];
+            } else if (BcDown == 2) {
+                Flux[c + n2 * K] = -D[c + n2 * (K - 1)] * (Cdown[c] - C[c + n2 * (K - 1)]) /
+                                   s->dz[c + n2 * (K - 1)];
+            } else if (BcDown == 3) {
+                Flux[c + n2 * K] = 0.0;
+            }
+            for (int k = 0; k < K; ++k)                                 /* :818-820 */
+                dC[c + n2 * k] = (Flux[c + n2 * k] - Flux[c + n2 * (k + 1)]) /
+                                 (VF[c + n2 * k] * s->dz[c + n2 * k]);
+        }
+}
+
+/* ---- right-hand side ------------------------------------------------------------------- */
+
+/* type_sed%get_rhs, src/drivers/fabm_sediment_driver.F90:575-717 */
+void osed_get_rhs(osed_rhs_driver *self, double *rhs)
+{
+    osed_sed *s = (osed_sed *)self;
+    const int K = s->base.knum, nvar = s->base.nvar;
+    const size_t n2 = N2(s), n3 = N3(s);
+    const int bcdown = 3;                                               /* :590 */
+    double *conc_insitu = dalloc(n3, 0.0), *f_T = dalloc(n3, 0.0);      /* :584-588 */
+    double *weighted_toc = dalloc(n3, 0.0), *intFlux = dalloc(n2 * (K + 1), 0.0);
+    double *cumdepth = dalloc(n2, 0.0), *avg_wtoc = dalloc(n2, 0.0);
+    double *volumeFraction = dalloc(n3, 0.0), *zeros2d = dalloc(n2, 0.0);
+
+    /* environmental properties :593-605 */
+    for (int k = 0; k < K; ++k) {
+        for (size_t c = 0; c < n2; ++c) {
+            double sum = 0.0;               /* sum(dz(:,:,1:k-1),dim=3) ; 0 for k==1 */
+            for (int m = 0; m < k; ++m) sum += s->dz[c + n2 * m];
+            cumdepth[c] = sum;
+        }
+        for (size_t c = 0; c < n2; ++c)
+            if (!(s->base.mask[c + n2 * k] > 0)) {
+                s->temp3d[c + n2 * k] = s->bdys[c];
+                s->par[c + n2 * k] = s->par_surface[c] * exp(-cumdepth[c] / s->k_par);
+            }
+    }
+
+    if (s->bioturbation_profile == 3) {                                 /* :618-645 */
+        for (size_t c = 0; c < n3; ++c) f_T[c] = 1.0;
+        s->bioturbation = 1.0;
+        for (size_t c = 0; c < n3; ++c) weighted_toc[c] = 0.0;
+        for (int q = 0; q < 2; ++q)
+            for (size_t c = 0; c < n3; ++c) {
+                if (s->base.mask[c] > 0) continue; /* porosity==1 there: skip the 1/0 */
+                weighted_toc[c] = weighted_toc[c] +
+                    s->poc_factor[q] * s->porosity[c] / (1.0 - s->porosity[c]) * s->poc_data[q][c];
+            }
+        for (size_t c = 0; c < n2; ++c) {
+            double sum = 0.0;
+            for (int k = 0; k < K; ++k) sum += s->dz[c + n2 * k] * weighted_toc[c + n2 * k];
+            avg_wtoc[c] = sum / cumdepth[c];   /* cumdepth left over from k==K: excludes bottom layer */
+        }
+        for (size_t c = 0; c < n3; ++c) s->weighted_toc[c] = weighted_toc[c];
+        for (int k = 0; k < K; ++k)
+            for (size_t c = 0; c < n2; ++c) {
+                size_t q = c + n2 * k;
+                s->biomass[q] = weighted_toc[q] * exp(s->zc[q] * 100.0 * s->k_l) * avg_wtoc[c] /
+                                (s->L1 + s->L2 * exp(s->zc[q] * 200.0 * s->k_l));
+            }
+        for (size_t c = 0; c < n3; ++c) {
+            if (s->base.mask[c] > 0) continue;
+            s->bioturbation_factor[c] = s->beta * pow(s->biomass[c], s->b) / weighted_toc[c];
+        }
+    } else {                                                            /* :648 */
+        for (size_t c = 0; c < n3; ++c)
+            f_T[c] = 1.0 * exp(-4500.0 * (1.0 / (s->temp3d[c] + 273.0) - (1.0 / 288.0)));
+    }
+
+    for (int n = 0; n < nvar; ++n) {                                    /* :651-694 */
+        for (size_t c = 0; c < n3; ++c)                                 /* :652-653 */
+            s->diff[c] = s->bioturbation * f_T[c] / 86400.0 / 10000.0 *
+                         (1.0 - s->intf_porosity[c]) * s->bioturbation_factor[c];
+        double *tr = s->transport + n3 * n;
+        if (s->particulate[n]) {                                        /* :658-678 */
+            int bcup = s->bcup_particulate_variables;
+            for (size_t c = 0; c < n3; ++c) conc_insitu[c] = s->base.conc[c + n3 * n] * s->porosity[c];
+            for (size_t c = 0; c < n3; ++c) volumeFraction[c] = 1.0 - s->porosity[c];
+            osed_diff3d(s, conc_insitu, s->bdys + n2 * (n + 1), zeros2d, s->fluxes + n2 * n, zeros2d,
+                        bcup, bcdown, s->diff, volumeFraction, intFlux, tr, s->flux_cap);
+            for (size_t c = 0; c < n3; ++c)
+                tr[c] = tr[c] * (1.0 - s->porosity[c]) / s->porosity[c];
+        } else {                                                        /* :679-693 */
+            int bcup = s->bcup_dissolved_variables;
+            for (size_t c = 0; c < n3; ++c)
+                s->diff[c] = s->diff[c] + (s->diffusivity + s->temp3d[c] * 0.035) *
+                                          s->intf_porosity[c] / 86400.0 / 10000.0;
+            for (size_t c = 0; c < n3; ++c) conc_insitu[c] = s->base.conc[c + n3 * n];
+            osed_diff3d(s, conc_insitu, s->bdys + n2 * (n + 1), zeros2d, s->fluxes + n2 * n, zeros2d,
+                        bcup, bcdown, s->diff, s->porosity, intFlux, tr, NULL);
+            /* :692 -- masked columns hold undefined Flux in the reference; defined as 0 here */
+            for (size_t c = 0; c < n2; ++c)
+                s->fluxes[c + n2 * n] = (s->base.mask[c] > 0) ? 0.0 : intFlux[c];
+        }
+    }
+
+    for (size_t c = 0; c < n3 * nvar; ++c) rhs[c] = 0.0;                /* :696 */
+    for (int k = 0; k < K; ++k)                                         /* :697-712 */
+        for (int j = 0; j < s->base.jnum; ++j)
+            for (int i = 0; i < s->base.inum; ++i) {
+                size_t q = I3(s, i, j, k);
+                if (!(s->base.mask[q] > 0)) {
+                    if (s->model == OSED_MODEL_OMEXDIA_P) {             /* fabm_do :700 */
+                        double c8[8], r8[8], denit;
+                        for (int n = 0; n < 8; ++n) c8[n] = s->base.conc[q + n3 * n];
+                        osed_omexdia_p_cell(&s->p, c8, s->temp3d[q], r8, &denit);
+                        for (int n = 0; n < 8; ++n) rhs[q + n3 * n] = r8[n];
+                        s->diag_denit[q] = denit;
+                    }
+                } else {
+                    for (int n = 0; n < nvar; ++n) {
+                        rhs[q + n3 * n] = 0.0;
+                        s->transport[q + n3 * n] = 0.0;
+                    }
+                }
+            }
+    for (size_t c = 0; c < n3 * nvar; ++c) rhs[c] = rhs[c] + s->transport[c]; /* :715 */
+
+    free(conc_insitu); free(f_T); free(weighted_toc); free(intFlux);
+    free(cumdepth); free(avg_wtoc); free(volumeFraction); free(zeros2d);
+}
+
+/* ---- ode_solver ------------------------------------------------------------------------ */
+
+/* Fortran minloc over (c1-c)/c in array order, NaNs skipped as gfortran does */
+static void minloc_relchange(const osed_rhs_driver *d, const double *c1, const double *c, int out[4])
+{
+    size_t n = (size_t)d->inum * d->jnum * d->knum * d->nvar, best = 0;
+    int found = 0;
+    double bv = 0.0;
+    for (size_t q = 0; q < n; ++q) {
+        double v = (c1[q] - c[q]) / c[q];
+        if (v != v) continue;
+        if (!found || v < bv) { bv = v; best = q; found = 1; }
+    }
+    out[0] = (int)(best % d->inum) + 1; best /= d->inum;
+    out[1] = (int)(best % d->jnum) + 1; best /= d->jnum;
+    out[2] = (int)(best % d->knum) + 1; best /= d->knum;
+    out[3] = (int)best + 1;
+}
+
+/* ode_solver, src/utilities/solver_library.F90:80-189 */
+void osed_ode_solver(osed_rhs_driver *d, double dt, int method)
+{
+    const size_t n = (size_t)d->inum * d->jnum * d->knum * d->nvar;
+    double *rhs0 = dalloc(n, 0.0), *rhs1 = NULL, *rhs2 = NULL, *rhs3 = NULL;   /* :89-90 */
+    double *c1 = dalloc(n, 0.0);
+    const double third = 1.0 / 3.0;                                            /* :96 */
+
+    switch (method) {
+    case OSED_EULER:                                                           /* :99-102 */
+        d->get_rhs(d, rhs0);
+        for (size_t q = 0; q < n; ++q) d->conc[q] = d->conc[q] + dt * rhs0[q];
+        break;
+
+    case OSED_ADAPTIVE_EULER: {                                                /* :104-140 */
+        double dt_int = 0.0, dt_red = dt;
+        while (dt_int < dt) {
+            double *c_pointer = d->conc;
+            d->get_rhs(d, rhs0);
+            for (size_t q = 0; q < n; ++q) c1[q] = d->conc[q] + dt_red * rhs0[q];
+            int viol = 0;                                                      /* :121 */
+            for (size_t q = 0; q < n; ++q)
+                if ((c1[q] - (1.0 + d->relative_change_min) * c_pointer[q]) < 0.0) { viol = 1; break; }
+            if (viol && (dt_red > d->dt_min)) {                                /* :126-128 */
+                dt_red = dt_red * 0.25;
+                d->n_subcycle_warnings++;
+                if (d->verbose) fprintf(stderr, " Warning: solver subcycles with dt = %g\n", dt_red);
+            } else {
+                if (d->adaptive_solver_diagnostics && dt_red < d->last_min_dt) { /* :130-136 */
+                    d->last_min_dt = dt_red;
+                    minloc_relchange(d, c1, c_pointer, d->last_min_dt_grid_cell);
+                }
+                for (size_t q = 0; q < n; ++q) d->conc[q] = c1[q];            /* :137-138 */
+                dt_int = dt_int + dt_red;
+            }
+        }
+        break;
+    }
+
+    case OSED_RK4: {                                                           /* :142-163 */
+        double *c_pointer = d->conc;
+        rhs1 = dalloc(n, 0.0); rhs2 = dalloc(n, 0.0); rhs3 = dalloc(n, 0.0);
+        d->get_rhs(d, rhs0);
+        for (size_t q = 0; q < n; ++q) c1[q] = c_pointer[q] + 0.5 * dt * rhs0[q];
+        d->conc = c1;
+        d->get_rhs(d, rhs1);
+        for (size_t q = 0; q < n; ++q) c1[q] = c_pointer[q] + 0.5 * dt * rhs1[q];
+        d->get_rhs(d, rhs2);
+        for (size_t q = 0; q < n; ++q) c1[q] = c_pointer[q] + dt * rhs2[q];
+        d->get_rhs(d, rhs3);
+        for (size_t q = 0; q < n; ++q)
+            c_pointer[q] = c_pointer[q] + dt * third * (0.5 * rhs0[q] + rhs1[q] + rhs2[q] + 0.5 * rhs3[q]);
+        d->conc = c_pointer;
+        break;
+    }
+
+    case OSED_RK4_38: {                                                        /* :164-185 */
+        double *c_pointer = d->conc;
+        rhs1 = dalloc(n, 0.0); rhs2 = dalloc(n, 0.0); rhs3 = dalloc(n, 0.0);
+        d->get_rhs(d, rhs0);
+        for (size_t q = 0; q < n; ++q) c1[q] = c_pointer[q] + third * dt * rhs0[q];
+        d->conc = c1;
+        d->get_rhs(d, rhs1);
+        for (size_t q = 0; q < n; ++q) c1[q] = c_pointer[q] + dt * (rhs1[q] - third * rhs0[q]);
+        d->get_rhs(d, rhs2);
+        for (size_t q = 0; q < n; ++q) c1[q] = c_pointer[q] + dt * (rhs0[q] - rhs1[q] + rhs2[q]);
+        d->get_rhs(d, rhs3);
+        for (size_t q = 0; q < n; ++q)
+            c_pointer[q] = c_pointer[q] +
+                dt * 1.0 / 8.0 * (rhs0[q] + 3.0 * rhs1[q] + 3.0 * rhs2[q] + rhs3[q]);
+        d->conc = c_pointer;
+        break;
+    }
+    default: break;
+    }
+    free(rhs0); free(rhs1); free(rhs2); free(rhs3); free(c1);
+}
+
+/* ---- component wrapper ------------------------------------------------------------------ */
+
+/* check_NaN, src/components/fabm_sediment_component.F90:2377-2421 */
+int osed_check_nan(const osed_sed *s)
+{
+    const size_t n3 = N3(s);
+    for (size_t c = 0; c < n3; ++c) {
+        if (s->base.mask[c] > 0) continue;
+        for (int n = 0; n < s->base.nvar; ++n) {
+            double v = s->base.conc[c + n3 * n];
+            if (v != v) return 1;
+        }
+    }
+    return 0;
+}
+
+/* one iteration of the Run loop, src/components/fabm_sediment_component.F90:1715-1732 */
+int osed_component_step(osed_sed *s, double dt, int method)
+{
+    const size_t n3 = N3(s);
+    osed_ode_solver(&s->base, dt, method);
+    if (osed_check_nan(s)) return 1;
+    for (int n = 0; n < s->base.nvar; ++n)                              /* :1726-1732 */
+        for (size_t c = 0; c < n3; ++c)
+            if (s->base.conc[c + n3 * n] < s->p.minimum[n]) s->base.conc[c + n3 * n] = s->p.minimum[n];
+    return 0;
+}
+
+/* get_boundary_conditions, src/components/fabm_sediment_component.F90:1865-2030 */
+void osed_get_boundary_conditions(osed_sed *s, const double *temperature,
+                                  const double *const *csurf, const double *const *wz)
+{
+    const size_t n2 = N2(s), n3 = N3(s);
+    if (temperature)                                                    /* :1930-1935 */
+        for (size_t c = 0; c < n2; ++c) s->bdys[c] = temperature[c];
+    if (!(s->bcup_dissolved_variables > 0)) return;                     /* :1939 */
+    for (int n = 0; n < s->base.nvar; ++n) {
+        if (!csurf || !csurf[n]) continue;                              /* :1952-1957 */
+        if (s->particulate[n]) {                                        /* :1986 */
+            for (size_t c = 0; c < n2; ++c) s->fluxes[c + n2 * n] = -csurf[n][c] * wz[n][c];
+        } else {
+            for (size_t c = 0; c < n2; ++c) s->bdys[c + n2 * (n + 1)] = csurf[n][c]; /* :2002 */
+            if (s->bcup_dissolved_variables == 1) {                     /* :2012-2014 */
+                for (size_t c = 0; c < n2; ++c)
+                    s->fluxes[c + n2 * n] =
+                        -(s->base.conc[c + n3 * n] - s->bdys[c + n2 * (n + 1)]) / s->dz[c] *
+                        (s->bioturbation + s->diffusivity + s->bdys[c] * 0.035) * s->porosity[c] /
+                        86400. / 10000.;
+            } else {
+                for (size_t c = 0; c < n2; ++c) s->fluxes[c + n2 * n] = 0.0; /* :2020 */
+            }
+        }
+    }
+}
+
+/* 1-D pre-simulation, src/components/fabm_sediment_component.F90:557-632 */
+void osed_spinup_column(const osed_sed_nml *nml, const osed_omexdia_params *p, int knum,
+                        double dzmin, double dt_min, double relative_change_min,
+                        const double *bdys1d, const double *fluxes1d, long nsteps,
+                        int method, double *conc1d)
+{
+    osed_sed s;
+    osed_init_grid(&s, 1, 1, knum, dzmin);
+    osed_initialize(&s, nml, OSED_MODEL_OMEXDIA_P, p, NULL);
+    s.base.conc = conc1d;
+    osed_check_domain(&s);
+    osed_init_concentrations(&s);
+    double bd[OSED_NVAR_OMEXDIA + 1], fl[OSED_NVAR_OMEXDIA];
+    memcpy(bd, bdys1d, sizeof(bd)); memcpy(fl, fluxes1d, sizeof(fl));
+    s.bdys = bd; s.fluxes = fl;
+    s.base.dt_min = dt_min; s.base.relative_change_min = relative_change_min;
+    s.bcup_dissolved_variables = 2;                                     /* :608-609 */
+    s.base.adaptive_solver_diagnostics = 1;                             /* :610 */
+    s.bioturbation_profile = 0;                                         /* :611 */
+    for (long t = 0; t < nsteps; ++t) osed_ode_solver(&s.base, 3600.0, method); /* :614-618 */
+    osed_finalize(&s);
+}
+
+/* ---- CPU baseline harness ---------------------------------------------------------------- */
+
+static double wall_seconds(void)
+{
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+#endif
+}
+
+double osed_bench_tiled(int inum, int jnum, int knum, double dzmin, const osed_sed_nml *nml,
+                        const osed_omexdia_params *p, const int *mask2d, double *conc,
+                        const double *bdys, const double *fluxes_in, double dt, int method,
+                        int nsteps, double dt_min, double relative_change_min,
+                        int bcup_dissolved, int nthreads, long *subcycles)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > jnum) nthreads = jnum;
+    const int nvar = OSED_NVAR_OMEXDIA;
+    osed_sed *tiles = (osed_sed *)calloc(nthreads, sizeof(osed_sed));
+    double **tconc = (double **)calloc(nthreads, sizeof(double *));
+    int *j0 = (int *)calloc(nthreads + 1, sizeof(int));
+    for (int t = 0; t <= nthreads; ++t) j0[t] = (int)((long)jnum * t / nthreads);
+    int err = 0;
+    /* scatter: one tile per thread, like one PET per DE tile (component :350-387) */
+    for (int t = 0; t < nthreads; ++t) {
+        osed_sed *s = &tiles[t];
+        int jl = j0[t + 1] - j0[t];
+        size_t n2l = (size_t)inum * jl, n3l = n2l * knum;
+        osed_init_grid(s, inum, jl, knum, dzmin);
+        int *mask3 = (int *)calloc(n3l ? n3l : 1, sizeof(int));
+        if (mask2d)
+            for (int k = 0; k < knum; ++k)
+                for (size_t c = 0; c < n2l; ++c) mask3[c + n2l * k] = mask2d[c + (size_t)inum * j0[t]];
+        osed_initialize(s, nml, OSED_MODEL_OMEXDIA_P, p, mask3);
+        free(mask3);
+        s->base.dt_min = dt_min; s->base.relative_change_min = relative_change_min;
+        s->bcup_dissolved_variables = bcup_dissolved;
+        tconc[t] = dalloc(n3l * nvar, 0.0);
+        s->base.conc = tconc[t];
+        s->bdys = dalloc(n2l * (nvar + 1), 0.0);
+        s->fluxes = dalloc(n2l * nvar, 0.0);
+        size_t n2 = (size_t)inum * jnum;
+        for (int n = 0; n < nvar; ++n)
+            for (int k = 0; k < knum; ++k)
+                memcpy(tconc[t] + n2l * (k + (size_t)knum * n),
+                       conc + (size_t)inum * j0[t] + n2 * (k + (size_t)knum * n), n2l * sizeof(double));
+        for (int n = 0; n < nvar + 1; ++n)
+            memcpy(s->bdys + n2l * n, bdys + (size_t)inum * j0[t] + n2 * n, n2l * sizeof(double));
+        for (int n = 0; n < nvar; ++n)
+            memcpy(s->fluxes + n2l * n, fluxes_in + (size_t)inum * j0[t] + n2 * n, n2l * sizeof(double));
+        if (osed_check_domain(s)) err = 1;
+        s->poc_data[0] = tconc[t]; s->poc_data[1] = tconc[t] + n3l;
+    }
+    double t0 = wall_seconds();
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+    for (int t = 0; t < nthreads; ++t)
+        for (int st = 0; st < nsteps; ++st)
+            if (osed_component_step(&tiles[t], dt, method)) {
+#pragma omp atomic write
+                err = 2;
+            }
+    double t1 = wall_seconds();
+    long sub = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        osed_sed *s = &tiles[t];
+        int jl = j0[t + 1] - j0[t];
+        size_t n2l = (size_t)inum * jl, n2 = (size_t)inum * jnum;
+        for (int n = 0; n < nvar; ++n)
+            for (int k = 0; k < knum; ++k)
+                memcpy(conc + (size_t)inum * j0[t] + n2 * (k + (size_t)knum * n),
+                       tconc[t] + n2l * (k + (size_t)knum * n), n2l * sizeof(double));
+        sub += s->base.n_subcycle_warnings;
+        free(s->bdys); free(s->fluxes); free(tconc[t]);
+        osed_finalize(s);
+    }
+    if (subcycles) *subcycles = sub;
+    free(tiles); free(tconc); free(j0);
+    return err ? -1.0 : (t1 - t0);
+}
+
+/* ---- flat handle API for the Python test harness ------------------------------------------ */
+
+typedef struct {
+    osed_sed s;
+    double *conc, *bdys, *fluxes;
+} osedpy;
+
+void *osedpy_create(int inum, int jnum, int knum, double dzmin, const osed_sed_nml *nml, int model,
+                    const osed_omexdia_params *p, const int *mask2d)
+{
+    osedpy *h = (osedpy *)calloc(1, sizeof(osedpy));
+    if (osed_init_grid(&h->s, inum, jnum, knum, dzmin)) { free(h); return NULL; }
+    size_t n2 = (size_t)inum * jnum, n3 = n2 * knum;
+    int *mask3 = (int *)calloc(n3 ? n3 : 1, sizeof(int));
+    if (mask2d)   /* sed%mask(i,j,:) = (gridmask(i,j).le.0), component :497-501 */
+        for (int k = 0; k < knum; ++k)
+            for (size_t c = 0; c < n2; ++c) mask3[c + n2 * k] = mask2d[c] > 0;
+    osed_initialize(&h->s, nml, model, p, mask3);
+    free(mask3);
+    h->conc = dalloc(n3 * h->s.base.nvar, 0.0);   /* conc = 0.0_rk, component :531 */
+    h->bdys = dalloc(n2 * (h->s.base.nvar + 1), 0.0);
+    h->fluxes = dalloc(n2 * h->s.base.nvar, 0.0);
+    h->s.base.conc = h->conc;
+    h->s.bdys = h->bdys;
+    h->s.fluxes = h->fluxes;
+    h->s.poc_data[0] = h->conc;
+    h->s.poc_data[1] = h->conc + n3;
+    return h;
+}
+
+void osedpy_destroy(void *hh)
+{
+    osedpy *h = (osedpy *)hh;
+    if (!h) return;
+    free(h->conc); free(h->bdys); free(h->fluxes);
+    osed_finalize(&h->s);
+    free(h);
+}
+
+osed_sed *osedpy_sed(void *hh) { return &((osedpy *)hh)->s; }
+
+double *osedpy_ptr(void *hh, int which)
+{
+    osedpy *h = (osedpy *)hh;
+    switch (which) {
+    case OSEDPY_CONC: return h->conc;
+    case OSEDPY_BDYS: return h->bdys;
+    case OSEDPY_FLUXES: return h->fluxes;
+    case OSEDPY_POROSITY: return h->s.porosity;
+    case OSEDPY_INTF_POROSITY: return h->s.intf_porosity;
+    case OSEDPY_BIOTURBATION_FACTOR: return h->s.bioturbation_factor;
+    case OSEDPY_PAR: return h->s.par;
+    case OSEDPY_PAR_SURFACE: return h->s.par_surface;
+    case OSEDPY_TEMP3D: return h->s.temp3d;
+    case OSEDPY_FLUX_CAP: return h->s.flux_cap;
+    case OSEDPY_BIOMASS: return h->s.biomass;
+    case OSEDPY_WEIGHTED_TOC: return h->s.weighted_toc;
+    case OSEDPY_DENIT: return h->s.diag_denit;
+    case OSEDPY_ZI: return h->s.zi;
+    case OSEDPY_ZC: return h->s.zc;
+    case OSEDPY_DZ: return h->s.dz;
+    case OSEDPY_DZC: return h->s.dzc;
+    case OSEDPY_TRANSPORT: return h->s.transport;
+    default: return NULL;
+    }
+}
+
+void osedpy_set_solver(void *hh, double dt_min, double relative_change_min, int bcup_dissolved,
+                       int diagnostics, int verbose)
+{
+    osed_sed *s = osedpy_sed(hh);
+    s->base.dt_min = dt_min;
+    s->base.relative_change_min = relative_change_min;
+    s->bcup_dissolved_variables = bcup_dissolved;
+    s->base.adaptive_solver_diagnostics = diagnostics;
+    s->base.verbose = verbose;
+}
+
+void osedpy_get_solver_diag(void *hh, double *last_min_dt, int cell[4], long *subcycles,
+                            double *bioturbation)
+{
+    osed_sed *s = osedpy_sed(hh);
+    *last_min_dt = s->base.last_min_dt;
+    for (int q = 0; q < 4; ++q) cell[q] = s->base.last_min_dt_grid_cell[q];
+    *subcycles = s->base.n_subcycle_warnings;
+    *bioturbation = s->bioturbation;
+}
+
+/* src/test/test_Solver.F90:30-44 */
+static void test_solver_rhs(osed_rhs_driver *d, double *rhs)
+{
+    size_t n3 = (size_t)d->inum * d->jnum * d->knum;
+    for (size_t q = 0; q < n3 * d->nvar; ++q) rhs[q] = 0.0;
+    for (int k = 1; k <= d->knum; ++k)
+        for (int j = 1; j <= d->jnum; ++j)
+            for (int i = 1; i <= d->inum; ++i)
+                for (int v = 0; v < d->nvar; ++v)
+                    rhs[(size_t)(i - 1) + (size_t)d->inum * ((j - 1) + (size_t)d->jnum * (k - 1)) + n3 * v] =
+                        (i + j + k) * 1.0e-8;
+}
+
+void osedpy_test_solver(int inum, int jnum, int knum, int nvar, double *conc, double dt, int method,
+                        long nsteps)
+{
+    osed_rhs_driver d;
+    memset(&d, 0, sizeof(d));
+    d.inum = inum; d.jnum = jnum; d.knum = knum; d.nvar = nvar;
+    d.dt_min = 1.e-9; d.relative_change_min = -0.9;
+    d.conc = conc;
+    d.last_min_dt = (double)1.e20f;
+    d.get_rhs = test_solver_rhs;
+    for (long t = 0; t < nsteps; ++t) osed_ode_solver(&d, dt, method);   /* test_Solver.F90:80-82 */
+}

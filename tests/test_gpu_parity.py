@@ -1,0 +1,280 @@
+"""GPU parity: the CUDA path (through the C ABI, via ctypes) against the CPU oracle on identical
+seeded inputs.  Bars from BASELINE.json's north_star: fp64 relative error <= 1e-12 after one step,
+<= 1e-8 on the state after 10 simulated days (unmasked cells)."""
+import numpy as np
+import pytest
+
+from tests.cases import config_case, make_case, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-12     # north_star: one step
+TOL_10D = 1e-8       # north_star: 10 simulated days
+DT = 360.0           # examples/esmf/sediment/run_sed.nml
+
+
+def _pair(oracle, case, **cfgkw):
+    from mossco_code_b200 import SedimentDriver, default_config
+    kw = dict(inum=case.inum, jnum=case.jnum, knum=case.knum, dzmin=case.dzmin, dt_min=1.0)
+    kw.update(cfgkw)
+    cfg = default_config(**kw)
+    sed = SedimentDriver(cfg)
+    ref = oracle.OracleSediment.from_config(cfg, mask2d=case.mask)
+    sed.set_mask(case.mask)
+    sed.init_concentrations()
+    ref.init_concentrations()
+    sed.set_boundary(case.bdys, case.fluxes)
+    ref.set_boundary(case.bdys, case.fluxes)
+    sed.set_par_surface(case.par_surface)
+    ref.par_surface[...] = case.par_surface
+    return cfg, sed, ref
+
+
+def _perturb_state(sed, ref, seed=3):
+    """Make the columns differ in state too (not only in forcing)."""
+    rng = np.random.default_rng(seed)
+    c = ref.conc.copy()
+    wet = c < 1e19
+    c[wet] *= 1.0 + 0.2 * rng.uniform(-1, 1, size=c.shape)[wet]
+    ref.conc[...] = c
+    sed.conc = c
+
+
+@pytest.mark.parametrize("which", ["C1", "C1b"])
+def test_initial_state_and_grid(gpu, oracle, which):
+    case = config_case(which)
+    cfg, sed, ref = _pair(oracle, case)
+    zi, zc, dz, dzc = sed.grid()
+    assert np.array_equal(zi, ref.field3d("zi")[0, 0])
+    assert np.array_equal(zc, ref.field3d("zc")[0, 0])
+    assert np.array_equal(dz, ref.field3d("dz")[0, 0])
+    assert np.array_equal(dzc, ref.field3d("dzc")[0, 0])
+    assert np.array_equal(sed.field("porosity"), ref.field3d("porosity"))
+    assert np.array_equal(sed.conc, ref.conc)          # initial_value/porosity: one IEEE division
+    assert sed.check_domain() == 0
+    sed.finalize()
+
+
+@pytest.mark.parametrize("profile", [0, 1, 2, 3])
+@pytest.mark.parametrize("bcup", [1, 2, 3])
+def test_get_rhs_matches_oracle(gpu, oracle, profile, bcup):
+    case = make_case("rhs", 19, 7, 30, 0.002, seed=11, land_fraction=0.25, smooth_temperature=True)
+    cfg, sed, ref = _pair(oracle, case, bioturbation_profile=profile, bcup_dissolved_variables=bcup)
+    _perturb_state(sed, ref)
+    if bcup == 1:  # dissolved boundary fluxes given: put something non-trivial there
+        fl = case.fluxes.copy()
+        fl[:, :, 3:] = 1e-6 * (1 + np.arange(5))
+        sed.set_boundary(None, fl)
+        ref.set_boundary(None, fl)
+    got = sed.get_rhs()
+    want = ref.get_rhs()
+    wet = case.mask == 0
+    assert scaled_err(got[wet], want[wet]) < 2e-13
+    assert np.all(got[~wet] == 0.0)
+    # side effect: fluxes(dissolved) = intFlux(:,:,1)   (driver :692)
+    assert scaled_err(sed.fluxes[wet], ref.fluxes[wet]) < 2e-13
+    sed.finalize()
+
+
+def test_get_rhs_distributed_pom_flux(gpu, oracle):
+    """BcUp=4 cascade (diff3d :791-803) incl. caps small enough to reach the bottom interface."""
+    case = make_case("pom", 9, 5, 12, 0.004, seed=5)
+    for pom in (2.0e4, 3.0e-1, 2.0e-2):
+        cfg, sed, ref = _pair(oracle, case, distributed_pom_flux=1, pom_flux_max=pom)
+        got, want = sed.get_rhs(), ref.get_rhs()
+        assert scaled_err(got, want) < 2e-13, pom
+        sed.finalize()
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3])
+@pytest.mark.parametrize("which", ["C1", "C1b", "C2s", "C3s"])
+def test_one_step_parity(gpu, oracle, which, method):
+    case = {"C1": lambda: config_case("C1"), "C1b": lambda: config_case("C1b"),
+            "C2s": lambda: config_case("C2", 0.2), "C3s": lambda: config_case("C3", 0.03)}[which]()
+    cfg, sed, ref = _pair(oracle, case)
+    rc = sed.step(DT, method, 1)
+    assert rc == 0
+    assert ref.step(DT, method, 1) == 0
+    wet = case.mask == 0
+    assert rel_err(sed.conc[wet], ref.conc[wet]) <= TOL_STEP
+    assert np.all(sed.conc[~wet] == 1e20)
+    assert scaled_err(sed.fluxes[wet], ref.fluxes[wet]) <= TOL_STEP
+    assert sed.info.steps_done == 1
+    sed.finalize()
+
+
+@pytest.mark.parametrize("method", [2, 1])
+def test_c1_ten_days(gpu, oracle, method):
+    case = config_case("C1")
+    cfg, sed, ref = _pair(oracle, case)
+    n = 2400  # 10 d / 360 s
+    assert sed.step(DT, method, n) == 0
+    assert ref.step(DT, method, n) == 0
+    assert sed.info.steps_done == n
+    assert scaled_err(sed.conc, ref.conc) <= TOL_10D
+    assert rel_err(sed.conc, ref.conc) <= 1e-6  # element-wise, incl. near-zero oxygen at depth
+    if method == 2:
+        assert sed.info.subcycle_warnings == ref.solver_diag()["subcycles"]
+    sed.finalize()
+
+
+def test_c2_ten_days_reduced(gpu, oracle):
+    """C2 forcing on a 24x24x30 tile, 10 simulated days, coupling-interval chunks of 10 steps."""
+    case = config_case("C2", 0.24)
+    cfg, sed, ref = _pair(oracle, case)
+    for _ in range(240):
+        assert sed.run(DT, 2, 3600.0) == 0
+    assert ref.step(DT, 2, 2400) == 0
+    assert scaled_err(sed.conc, ref.conc) <= TOL_10D
+    assert scaled_err(sed.fluxes, ref.fluxes) <= TOL_10D
+    sed.finalize()
+
+
+def test_masked_columns_untouched(gpu, oracle):
+    case = config_case("C3", 0.02)
+    cfg, sed, ref = _pair(oracle, case)
+    land = case.mask > 0
+    assert land.any() and (~land).any()
+    for method in (2, 1, 3, 0):
+        assert sed.step(DT, method, 3) == 0
+        assert np.all(sed.conc[land] == 1e20)
+    assert np.all(sed.field("porosity")[land] == 1.0)
+    assert np.all(sed.field("temperature")[land] == -999.0)
+    sed.finalize()
+
+
+def test_adaptive_subcycling_control_flow(gpu, oracle):
+    """A column that violates relative_change_min forces dt/4 sub-steps for the WHOLE tile
+    (solver_library.F90:121-138)."""
+    case = make_case("sub", 6, 4, 15, 0.004, seed=2)
+    # a huge nitrification/oxidation sink: oxygen would drop by >90 % in one 360 s step
+    kw = dict(rnit=2.0e3, rODUox=2.0e3)
+    cfg, sed, ref = _pair(oracle, case, **kw)
+    assert sed.step(DT, 2, 5) == 0
+    assert ref.step(DT, 2, 5) == 0
+    d = ref.solver_diag()
+    assert d["subcycles"] > 0
+    assert sed.info.subcycle_warnings == d["subcycles"]
+    assert sed.info.rhs_evaluations > 5 + d["subcycles"]
+    assert scaled_err(sed.conc, ref.conc) <= 1e-11
+    assert rel_err(sed.conc, ref.conc) <= 1e-7   # entries that decayed by many orders of magnitude
+    # dt_min >= dt: the violating step is accepted as is (:126)
+    cfg2, sed2, ref2 = _pair(oracle, case, dt_min=1000.0, **kw)
+    assert sed2.step(DT, 2, 1) == 0 and ref2.step(DT, 2, 1) == 0
+    assert sed2.info.subcycle_warnings == 0 and sed2.info.rhs_evaluations == 1
+    assert scaled_err(sed2.conc, ref2.conc) <= 1e-12
+    sed.finalize(); sed2.finalize()
+
+
+def test_ode_solver_has_no_clip_but_step_clips(gpu, oracle):
+    case = make_case("clip", 5, 3, 15, 0.004, seed=9)
+    kw = dict(rnit=2.0e5, rODUox=2.0e5, dt_min=1000.0)   # accept the overshooting Euler step
+    cfg, sed, ref = _pair(oracle, case, **kw)
+    sed.ode_solver(DT, 2)
+    ref.ode_solver(DT, 2)
+    assert ref.conc.min() < 0.0                          # overshoot below zero
+    assert scaled_err(sed.conc, ref.conc) <= 1e-12
+    cfg, sed2, ref2 = _pair(oracle, case, **kw)
+    assert sed2.step(DT, 2, 1) == 0 and ref2.step(DT, 2, 1) == 0
+    assert sed2.conc.min() == 0.0 and ref2.conc.min() == 0.0
+    assert scaled_err(sed2.conc, ref2.conc) <= 1e-12
+    sed.finalize(); sed2.finalize()
+
+
+def test_nan_detected(gpu):
+    from mossco_code_b200 import SedimentDriver, default_config
+    cfg = default_config(inum=4, jnum=3, knum=10, dzmin=0.005)
+    with SedimentDriver(cfg) as sed:
+        sed.init_concentrations()
+        c = sed.conc
+        c[2, 1, 4, 6] = np.nan
+        sed.conc = c
+        assert sed.step(DT, 2, 3) == 1            # MSED_NAN_DETECTED, stops at the first step
+        assert sed.info.nan_detected == 1 and sed.info.steps_done == 1
+
+
+def test_solver_kat_test_solver_f90(gpu, oracle):
+    """src/test/test_Solver.F90: conc = 1+0.1k (default-real arithmetic), rhs=(i+j+k)*1e-8, Euler dt=1."""
+    from mossco_code_b200 import MODEL_TEST_SOLVER, SedimentDriver, default_config
+    inum, jnum, knum, n = 100, 1, 24, 2000
+    conc = np.zeros((inum, jnum, knum, 8), order="F")
+    for k in range(1, knum + 1):
+        conc[:, :, k - 1, :] = np.float64(np.float32(1.0) + np.float32(k) * np.float32(0.1))
+    want = oracle.test_solver_kat(inum, jnum, knum, 8, conc.copy(order="F"), 1.0, 0, n)
+    cfg = default_config(inum=inum, jnum=jnum, knum=knum, model=MODEL_TEST_SOLVER)
+    with SedimentDriver(cfg) as sed:
+        sed.conc = conc
+        # ode_solver n times (no clipping wrapper), as test_Solver.F90:80-82
+        import ctypes as C
+        for _ in range(n):
+            assert sed._lib.msed_ode_solver(sed._h, 1.0, 0, C.byref(sed.info)) == 0
+        got = sed.conc
+    assert np.array_equal(got, want)                      # bit exact: same rounding sequence
+    i = np.arange(1, inum + 1)[:, None, None, None]
+    k = np.arange(1, knum + 1)[None, None, :, None]
+    closed = conc + n * (i + 1 + k) * 1e-8
+    assert np.max(np.abs(got - closed)) < 1e-11
+
+
+def test_boundary_conditions_and_export(gpu, oracle):
+    case = make_case("bc", 11, 6, 15, 0.004, seed=21, land_fraction=0.2, par_max=50.0)
+    rng = np.random.default_rng(4)
+    for bcup in (2, 1):
+        cfg, sed, ref = _pair(oracle, case, bcup_dissolved_variables=bcup)
+        temp = 4.0 + 10.0 * rng.random((11, 6))
+        cs = [rng.random((11, 6)) * s for s in (1e-4, 1e-4, 1e-6, 1.0, 10.0, 5.0, 250.0, 1.0)]
+        wz = [-rng.random((11, 6)) * 1e-3 for _ in range(3)] + [None] * 5
+        cs[4] = None  # nitrate field absent from the import state
+        sed.get_boundary_conditions(temp, cs, wz)
+        ref.get_boundary_conditions(temp, cs, wz)
+        assert np.array_equal(sed.bdys, ref.bdys)
+        assert np.array_equal(sed.fluxes, ref.fluxes)      # same IEEE operation sequence
+        assert sed.step(DT, 2, 2) == 0 and ref.step(DT, 2, 2) == 0
+        wet = case.mask == 0
+        assert np.array_equal(sed.upward_fluxes(), -sed.fluxes)
+        assert scaled_err(sed.fluxes[wet], ref.fluxes[wet]) <= 1e-11
+        assert scaled_err(sed.field("photosynthetically_active_radiation")[wet], ref.field3d("par")[wet]) < 1e-14
+        assert np.array_equal(sed.field("temperature")[wet], ref.field3d("temp3d")[wet])
+        assert scaled_err(sed.field("denit")[wet][..., None], ref.field3d("denit")[wet][..., None]) < 1e-11
+        assert np.array_equal(sed.field("intf_porosity")[wet], ref.field3d("intf_porosity")[wet])
+        sed.finalize()
+
+
+def test_update_porosity_from_surface(gpu, oracle):
+    case = make_case("por", 8, 5, 15, 0.004, seed=31, land_fraction=0.2)
+    cfg, sed, ref = _pair(oracle, case, distributed_pom_flux=1)
+    surf = 0.5 + 0.3 * np.random.default_rng(8).random((8, 5))
+    sed.update_porosity(surf)
+    ref.update_porosity(surf)
+    wet = case.mask == 0
+    assert np.array_equal(sed.field("porosity"), ref.field3d("porosity"))
+    assert scaled_err(sed.field("flux_cap")[wet][..., None], ref.field3d("flux_cap")[wet][..., None]) < 1e-15
+    assert sed.step(DT, 2, 1) == 0 and ref.step(DT, 2, 1) == 0
+    assert rel_err(sed.conc[wet], ref.conc[wet]) <= TOL_STEP
+    sed.finalize()
+
+
+def test_profile3_fields_and_rk(gpu, oracle):
+    """Zhang & Wirtz bioturbation (driver :618-645) incl. the RK quirk that POC stays the original conc."""
+    case = make_case("p3", 7, 4, 15, 0.004, seed=41)
+    cfg, sed, ref = _pair(oracle, case, bioturbation_profile=3)
+    for method in (2, 1, 3):
+        assert sed.step(DT, method, 2) == 0 and ref.step(DT, method, 2) == 0
+        assert rel_err(sed.conc, ref.conc) <= 1e-11
+    ref.get_rhs(); sed.get_rhs()
+    for name in ("weighted_toc", "biomass"):
+        assert scaled_err(sed.field(name)[..., None], ref.field3d(name)[..., None]) < 1e-12
+    assert scaled_err(sed.field("bioturbation")[..., None], ref.field3d("bioturbation_factor")[..., None]) < 1e-12
+    sed.finalize()
+
+
+def test_spinup_column(gpu, oracle):
+    from mossco_code_b200 import default_config, spinup_column
+    from tests.cases import C1_BDYS, C1_FLUXES
+    cfg = default_config(knum=15, dzmin=0.004, dt_min=1.0, bioturbation_profile=1)
+    nsteps = 24 * 20  # 20 days of dt_spinup = 3600 s
+    got, info = spinup_column(cfg, C1_BDYS, C1_FLUXES, nsteps)
+    nml, par = oracle.from_config(cfg)
+    want = oracle.spinup_column(nml, par, 15, 0.004, 1.0, -0.9, C1_BDYS, C1_FLUXES, nsteps)
+    assert info.steps_done == nsteps
+    assert scaled_err(got, want) <= TOL_10D
