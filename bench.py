@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- sediment cell-updates/s of the fused fabm_sediment RHS + adaptive-Euler integrator.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c4slab|c3|c2] [--impl reference]
+
+One "step" is one ``ode_solver(sed, dt=360 s, ode_method=2)`` call + check_NaN + clip over the whole
+grid (one iteration of src/components/fabm_sediment_component.F90:1700-1769).  The default workload
+is BASELINE.json's metric config: the 4096x4096x40 grid (C4), j-slab sharded over N ranks (strong
+scaling: the total grid is fixed).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DT = 360.0                 # examples/esmf/sediment/run_sed.nml
+COUPLING_SECONDS = 3600.0  # examples/esmf/sediment/toplevel_component.F90:71 (1 h coupling)
+METHOD = 2                 # ADAPTIVE_EULER, component default (:62)
+NVAR = 8
+ROW_BLOCK = 512            # forcing is seeded per block of 512 rows so the field is independent of N
+
+WORKLOADS = {
+    # name: (inum, jnum, knum, dzmin, seed, land_fraction, description)
+    "c4": (4096, 4096, 40, 0.0015, 4096, 0.0, "C4 4096x4096x40, no mask, C2-style forcing seed 4096"),
+    "c4slab": (4096, 512, 40, 0.0015, 4096, 0.0, "one 4096x512x40 slab of C4 (its 8-GPU tile)"),
+    "c3": (1000, 1000, 30, 0.002, 2024, 0.45, "C3 1000x1000x30, 45% land mask, smooth T, PAR"),
+    "c2": (100, 100, 30, 0.002, 1234, 0.0, "C2 100x100x30 (L2-resident, launch-latency regime)"),
+}
+
+
+def b_alg(knum: int) -> float:
+    """Algorithmic bytes per cell-update, SURVEY.md 8(d) / BASELINE.md 2: 136 + 216/K."""
+    return 2 * NVAR * 8 + 8 + 8.0 * (3 * NVAR + 3) / knum
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_per_cell():
+    """DRAM bytes per cell-update of the column kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_cell_update"])
+    except Exception:
+        return None
+
+
+def slab_forcing(wl, j0, j1):
+    """Forcing rows [j0,j1) of the workload; seeded per ROW_BLOCK so every N sees the same field."""
+    from tests.cases import make_case
+    inum, jnum, knum, dzmin, seed, land, _ = wl
+    parts = []
+    for b0 in range((j0 // ROW_BLOCK) * ROW_BLOCK, j1, ROW_BLOCK):
+        b1 = min(b0 + ROW_BLOCK, jnum)
+        c = make_case("blk", inum, b1 - b0, knum, dzmin, seed=seed + b0 // ROW_BLOCK, land_fraction=land,
+                      smooth_temperature=land > 0, par_max=50.0 if land > 0 else 0.0)
+        lo, hi = max(j0, b0) - b0, min(j1, b1) - b0
+        parts.append((c.bdys[:, lo:hi], c.fluxes[:, lo:hi], c.mask[:, lo:hi], c.par_surface[:, lo:hi]))
+    cat = lambda i: np.asfortranarray(np.concatenate([p[i] for p in parts], axis=1))  # noqa: E731
+    return cat(0), cat(1), cat(2), cat(3)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.idx), "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), r[5:9]):
+                    if val.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+def pinned_fortran(shape):
+    """Pinned host buffer viewed as a Fortran-ordered numpy array of ``shape``."""
+    import torch
+    t = torch.empty(tuple(reversed(shape)), dtype=torch.float64).pin_memory()
+    return t, t.numpy().T
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(wl, steps, warmup, target_seconds=None, as_arm=False):
+    """The restated reference CPU path (oracle, OpenMP j-slab tiles on all host cores) timed on a
+    bounded sample of the same workload.  Returns (cell_updates_per_s, cores, sample_text, ms/step)."""
+    from mossco_code_b200 import _abi
+    from oracle import msed_oracle as orc
+    inum, jnum, knum, dzmin, seed, land, _ = wl
+    cores = os.cpu_count() or 1
+    cfg = _abi.Config()
+    # msed_config_defaults is pure host code; it runs without a GPU
+    _abi.load().msed_config_defaults(cfg)
+    cfg.inum, cfg.knum, cfg.dzmin, cfg.dt_min = inum, knum, dzmin, 1.0
+
+    def run(rows, nsteps):
+        rows = max(cores, (rows // cores) * cores)
+        cfg.jnum = rows
+        bd, fl, mask, _par = slab_forcing((inum, max(rows, 1), knum, dzmin, seed, land, ""), 0, rows)
+        o = orc.OracleSediment.from_config(cfg, mask2d=mask)
+        o.init_concentrations()
+        conc = o.conc.copy(order="F")
+        o.finalize()
+        secs, sub, _ = orc.bench_tiled(cfg, mask, conc, bd, fl, DT, METHOD, nsteps, cores, native=True)
+        if secs <= 0:
+            raise RuntimeError("oracle bench failed")
+        return secs, rows, sub
+
+    # probe, then size the sample: ~1 s per step, at most 16 M cell-layers (the un-fused reference
+    # structure needs ~400 B of temporaries per cell-layer), 3..100 steps for ~15 s in total
+    secs, rows, _ = run(2 * cores, 3)
+    rate = 3 * inum * rows * knum / secs
+    rows_cap = max(cores, int(16e6 / (inum * knum)))
+    want_rows = int(min(max(int(rate * 1.0 / (inum * knum)), cores), rows_cap, jnum))
+    if as_arm:
+        nsteps = steps
+        if warmup:
+            run(want_rows, warmup)
+    else:
+        step_s = inum * want_rows * knum / rate
+        nsteps = int(min(max((target_seconds or 15.0) / step_s, 3), 100))
+    secs, rows, sub = run(want_rows, nsteps)
+    n = nsteps
+    cells = inum * rows * knum
+    sample = (f"{inum}x{rows}x{knum} slab of the workload, {n} steps, {cores} OpenMP threads "
+              f"(one j-slab tile per thread), oracle -O3 -march=native, subcycles={sub}")
+    return cells * n / secs, cores, sample, secs / n * 1e3
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, cores, sample, ms = cpu_reference(wl, args.steps, args.warmup, as_arm=True)
+    line = {
+        "impl": "reference", "metric": "sediment cell-updates/sec", "value": value,
+        "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][6], "dt_s": DT, "ode_method": METHOD,
+                   "note": "reference = C restatement of the Fortran CPU path (gfortran/ESMF/FABM absent)"},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from mossco_code_b200 import SedimentDriver, default_config
+    from mossco_code_b200.component import FabmSedimentComponent
+    from mossco_code_b200.sediment import PARTICULATE, VARIABLE_NAMES
+    from mossco_code_b200.sharding import init_flag_collective, slab_bounds
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    inum, jnum, knum, dzmin, seed, land, desc = wl
+    j0, j1 = slab_bounds(jnum, world, rank)
+    rows = j1 - j0
+    bdys, fluxes, mask, par = slab_forcing(wl, j0, j1)
+    cfg = default_config(inum=inum, jnum=rows, knum=knum, dzmin=dzmin, dt_min=1.0, device=local_rank,
+                         j_offset=j0)
+    sed = SedimentDriver(cfg)
+    stream = torch.cuda.Stream()
+    sed.set_stream(stream.cuda_stream)
+    if land > 0:
+        sed.set_mask(mask)
+        sed.set_par_surface(par)
+    sed.init_concentrations()
+    sed.set_boundary(bdys, fluxes)
+    init_flag_collective(sed)
+    cells_local = inum * rows * knum * (1.0 if land == 0 else float((mask == 0).mean()))
+    cells_total = torch.tensor([cells_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cells_total)
+    cells_total = float(cells_total.item())
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------
+    sed.step(DT, METHOD, args.warmup)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        rc = sed.step(DT, METHOD, args.steps)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+    if rc != 0:
+        raise SystemExit(f"msed_step returned {rc}")
+    info = sed.info
+    ms = torch.tensor([e0.elapsed_time(e1), info.kernel_ms], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([info.kernel_launches, info.subcycle_warnings, info.rhs_evaluations,
+                           info.steps_done], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(ms[0]), float(ms[1])
+    launches, subcycles, rhs_evals, steps_done = (int(x) for x in counts.tolist())
+    assert steps_done == args.steps
+    value = cells_total * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the component's Run with HOST buffers ("e2e") -------------------------
+    # Run(3600 s): H2D of the import fields (temperature + 8 surface concentrations + 3 sinking
+    # velocities), get_boundary_conditions, 10 ode_solver steps, D2H of the 8 upward bed fluxes.
+    comp = FabmSedimentComponent()
+    comp.sed, comp.cfg = sed, cfg
+    comp.run_nml.update(dt=DT, ode_method=METHOD, numlayers=knum, dzmin=dzmin, dt_min=1.0)
+    comp.export_3d_every_run = False   # <name>_in_soil 3-D fields are read on demand (output/restart)
+    keep, imp, exp = [], {}, {}
+    t_, a_ = pinned_fortran((inum, rows)); a_[...] = bdys[:, :, 0]; keep.append(t_)
+    imp["temperature_at_soil_surface"] = a_
+    h2d = a_.nbytes
+    for n, v in enumerate(VARIABLE_NAMES):
+        t_, a_ = pinned_fortran((inum, rows)); keep.append(t_)
+        if PARTICULATE[n]:
+            a_[...] = -fluxes[:, :, n]                      # C_surface with w_z = 1: flux = -C*w (:1986)
+            tw, aw = pinned_fortran((inum, rows)); aw[...] = 1.0; keep.append(tw)
+            imp[f"{v}_z_velocity_at_soil_surface"] = aw
+            h2d += aw.nbytes
+        else:
+            a_[...] = bdys[:, :, n + 1]
+        imp[f"{v}_at_soil_surface"] = a_
+        h2d += a_.nbytes
+    tf_, comp.flux_buffer = pinned_fortran((inum, rows, NVAR)); keep.append(tf_)
+    steps_per_run = int(round(COUPLING_SECONDS / DT))
+    nruns = max(1, args.steps // steps_per_run)
+    comp.run(imp, exp, run_seconds=COUPLING_SECONDS)        # warm-up Run
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(nruns):
+        comp.run(imp, exp, run_seconds=COUPLING_SECONDS)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    d2h = sum(exp[f"{v}_upward_flux_at_soil_surface"].nbytes for v in VARIABLE_NAMES)
+    e2e_value = cells_total * nruns * steps_per_run / float(e2e_s.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        balg = b_alg(knum)
+        cells_per_launch = cells_total / world              # per GPU, per column-kernel launch
+        avg_launch_s = kernel_ms * 1e-3 / max(rhs_evals, 1)
+        achieved = balg * cells_per_launch / avg_launch_s / 1e9
+        tpc = traffic_per_cell()
+        line = {
+            "metric": "sediment cell-updates/sec", "value": value, "unit": "cell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "grid": [inum, jnum, knum], "rows_per_gpu": rows, "dt_s": DT,
+                       "ode_method": METHOD, "sharding": f"j-slabs x{world}, no halo",
+                       "l2": "per-GPU state >= 5.4 GB >> 126 MB L2 (inputs larger than L2)"
+                       if cells_per_launch * 128 > 1e9 else "state fits L2 (launch-latency regime)",
+                       "subcycles_in_timed_region": subcycles, "rhs_evaluations": rhs_evals,
+                       "e2e_call": f"Run({int(COUPLING_SECONDS)} s) = H2D 12 import fields + get_boundary_conditions "
+                                   f"+ {steps_per_run} ode_solver steps + D2H 8 upward-flux fields; "
+                                   f"{nruns} timed Run(s); 3-D <name>_in_soil export on demand"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "cell-updates/s",
+                    "h2d_bytes_per_step": h2d / steps_per_run, "d2h_bytes_per_step": d2h / steps_per_run,
+                    "h2d_bytes_per_run": h2d, "d2h_bytes_per_run": d2h, "steps_per_run": steps_per_run},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None if tpc is None else tpc * cells_per_launch,
+                         "kernel": "msed::column_kernel<OMEXDIA_P, OP_ADAPTIVE>",
+                         "algorithmic_bytes_per_cell_update": balg, "peak_source": peak_src,
+                         "avg_launch_ms": avg_launch_s * 1e3},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample, _ = cpu_reference(wl, 0, 0, target_seconds=15.0)
+            line["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                                    "sample": sample}
+        print(json.dumps(line))
+    sed.finalize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,9 @@ int msed_destroy(msed_handle *h);
 const char *msed_last_error(const msed_handle *h);
 /* library identification: "msed_b200 <abi> sm_100a" */
 const char *msed_version(void);
+/* sizeof(msed_config) for what==0, sizeof(msed_step_info) for what==1: lets FFI bindings verify
+ * their struct layout at load time */
+size_t msed_sizeof(int what);
 
 /* ---- static fields ------------------------------------------------------------------------ */
 /* grid%zi(knum+1), zc(knum), dz(knum), dzc(knum-1) of init_grid (horizontally uniform); any may be NULL */

@@ -82,6 +82,7 @@ SYMBOLS = {
     "msed_destroy": (C.c_int, [_h]),
     "msed_last_error": (C.c_char_p, [_h]),
     "msed_version": (C.c_char_p, []),
+    "msed_sizeof": (C.c_size_t, [C.c_int]),
     "msed_get_grid": (C.c_int, [_h, _dp, _dp, _dp, _dp]),
     "msed_set_mask": (C.c_int, [_h, C.POINTER(C.c_int32)]),
     "msed_set_porosity": (C.c_int, [_h, _dp]),
@@ -137,6 +138,10 @@ def load(path: str | None = None):
             raise MsedLibraryError(f"{p} does not export {name}") from exc
         fn.restype = res
         fn.argtypes = args
+    if lib.msed_sizeof(0) != C.sizeof(Config) or lib.msed_sizeof(1) != C.sizeof(StepInfo):
+        raise MsedLibraryError(
+            f"struct layout mismatch: msed_config {lib.msed_sizeof(0)} vs {C.sizeof(Config)}, "
+            f"msed_step_info {lib.msed_sizeof(1)} vs {C.sizeof(StepInfo)}")
     if path is None:
         _lib = lib
     return lib

@@ -1,0 +1,250 @@
+"""Host-side mirror of the ``fabm_sediment_component`` ESMF interface
+(src/components/fabm_sediment_component.F90): the same phases (InitializeP0/P1/P2, ReadRestart, Run,
+Finalize, :99-131), the same import/export field names (:943-1192) and the same per-Run sequence
+(PAR/porosity import -> get_boundary_conditions -> step loop -> export write-back, :1493-1829),
+with the body replaced by C-ABI calls into libmsed_b200.so.
+
+ESMF itself is not available here, so an ``ESMF_State`` is represented by a plain ``dict`` mapping
+field names to numpy fp64 arrays in Fortran order (rank 2 ``(inum,jnum)`` for surface fields, rank 3
+``(inum,jnum,knum)`` for ``*_in_soil``).  The Fortran shim in ``fortran/msed_b200.F90`` is the
+production equivalent of this file.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _abi
+from .sediment import (ADAPTIVE_EULER, NVAR, PARTICULATE, STATE_NAMES, VARIABLE_NAMES, SedimentDriver,
+                       default_config, spinup_column)
+
+State = Dict[str, np.ndarray]
+
+# legacy aliases still accepted on import (component :602-605; examples/esmf/sediment/default.dat)
+LEGACY_ALIASES = {
+    "detritus_labile_carbon": ("fast_detritus_C",),
+    "detritus_semilabile_carbon": ("slow_detritus_C",),
+    "detritus_labile_phosphorus": ("detritus-P", "detritus_phosphorus"),
+}
+
+# export_states catalogue, fabm_sediment_driver.F90:877-924
+STATIC_EXPORTS = ("porosity", "layer_height", "layer_center_depth", "temperature",
+                  "photosynthetically_active_radiation")
+PROFILE3_EXPORTS = ("biomass", "bioturbation", "weighted_toc")
+
+# run_nml defaults, component :59-67
+RUN_NML_DEFAULTS = dict(
+    numyears=1, dt=360.0, output=-1, numlayers=10, dzmin=0.005, ode_method=ADAPTIVE_EULER,
+    dt_min=1.0e-8, relative_change_min=-0.9, bcup_dissolved_variables=2, presimulation_years=-1,
+    pel_Temp=5.0, pel_NO3=5.0, pel_NH4=5.0, pel_PO4=0.5, pel_O2=250.0,
+    pflux_lDetC=10.0, pflux_sDetC=10.0, pflux_lDetN=1.5, pflux_sDetN=1.5, pflux_lDetP=0.2,
+)
+
+ESMF_SUCCESS = 0
+ESMF_RC_VAL_OUTOFRANGE = 547  # value ESMF assigns; only identity matters here
+
+
+class ComponentError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(msg)
+        self.rc = rc
+
+
+class FabmSedimentComponent:
+    """One instance per process, like the module-level ``sed`` of the reference (:80)."""
+
+    def __init__(self, name: str = "fabm_sediment"):
+        self.name = name
+        self.sed: Optional[SedimentDriver] = None
+        self.run_nml = dict(RUN_NML_DEFAULTS)
+        self.phase_map = None
+        self.clock_seconds = 0.0
+        self.last_info = None
+        self.export_3d_every_run = True
+        self.flux_buffer = None   # optional caller-owned (pinned) (inum,jnum,nvar) export buffer
+
+    # ---- SetServices -----------------------------------------------------------------------
+    def set_services(self):
+        """Entry points as registered at :108-128."""
+        return {
+            ("initialize", 0): self.initialize_p0, ("initialize", 1): self.initialize_p1,
+            ("initialize", 2): self.initialize_p2, ("readrestart", 1): self.read_restart,
+            ("run", 1): self.run, ("finalize", 1): self.finalize,
+        }
+
+    # ---- InitializeP0 (:135-173) -------------------------------------------------------------
+    def initialize_p0(self, import_state: State, export_state: State, clock=None):
+        self.phase_map = ["IPDv00p1=1", "IPDv00p2=2"]  # NUOPC InitializePhaseMap, :156-164
+        return ESMF_SUCCESS
+
+    # ---- InitializeP1 (:177-1201) -------------------------------------------------------------
+    def initialize_p1(self, import_state: State, export_state: State, clock=None, *, grid_shape,
+                      run_nml: Optional[dict] = None, sed_nml: Optional[dict] = None,
+                      fabm_nml: Optional[dict] = None, grid_mask: Optional[np.ndarray] = None,
+                      device: int = -1, j_offset: int = 0):
+        """``grid_shape`` = (inum, jnum) of the foreign grid tile (:314-448); ``grid_mask`` is the
+        ESMF_GRIDITEM_MASK item: columns with grid_mask <= 0 are masked (:497-501)."""
+        if run_nml:
+            unknown = set(run_nml) - set(RUN_NML_DEFAULTS)
+            if unknown:
+                raise ComponentError(1, f"unknown run_nml entries {sorted(unknown)}")
+            self.run_nml.update(run_nml)
+        r = self.run_nml
+        kw = dict(inum=int(grid_shape[0]), jnum=int(grid_shape[1]), knum=int(r["numlayers"]),
+                  dzmin=float(r["dzmin"]), dt_min=float(r["dt_min"]),
+                  relative_change_min=float(r["relative_change_min"]),
+                  bcup_dissolved_variables=int(r["bcup_dissolved_variables"]), device=device,
+                  j_offset=int(j_offset))
+        kw.update(sed_nml or {})
+        kw.update(fabm_nml or {})
+        cfg = default_config(**kw)
+        self.cfg = cfg
+        self.sed = SedimentDriver(cfg)                      # init_grid (:512) + initialize (:517)
+        sed = self.sed
+        if grid_mask is not None:
+            sed.set_mask((np.asarray(grid_mask) <= 0).astype(np.int32))
+            self.mask = np.asfortranarray((np.asarray(grid_mask) <= 0))
+        else:
+            self.mask = np.zeros(sed.shape2d, dtype=bool, order="F")
+        rc = sed.check_domain()                             # :529
+        if rc:
+            raise ComponentError(rc, "check_domain failed")
+        sed.init_concentrations()                           # :536
+
+        # boundary defaults for the pre-simulation (:588-606)
+        bd = np.zeros(NVAR + 1)
+        fl = np.zeros(NVAR)
+        bd[0] = r["pel_Temp"]
+        bd[1 + STATE_NAMES.index("no3")] = r["pel_NO3"]
+        bd[1 + STATE_NAMES.index("nh3")] = r["pel_NH4"]
+        bd[1 + STATE_NAMES.index("po4")] = r["pel_PO4"]
+        bd[1 + STATE_NAMES.index("oxy")] = r["pel_O2"]
+        bd[1 + STATE_NAMES.index("odu")] = r["pel_O2"]      # reference quirk, :595
+        fl[STATE_NAMES.index("ldetC")] = r["pflux_lDetC"] / 86400.0
+        fl[STATE_NAMES.index("sdetC")] = r["pflux_sDetC"] / 86400.0
+        fl[STATE_NAMES.index("detP")] = r["pflux_lDetP"] / 86400.0
+        bdys = np.empty(sed.shape2d + (NVAR + 1,), order="F")
+        fluxes = np.empty(sed.shape2d + (NVAR,), order="F")
+        bdys[...] = bd
+        fluxes[...] = fl
+        sed.set_boundary(bdys, fluxes)
+
+        if r["presimulation_years"] > 0:                    # :614-632
+            nsteps = int(r["presimulation_years"] * 365 * 24)
+            col, info = spinup_column(cfg, bd, fl, nsteps, int(r["ode_method"]))
+            sed.set_state_from_column(col)
+            self.spinup_info = info
+        sed.get_rhs()                                       # fills diagnostics, :638-645
+
+        # export fields (:943-1040) and import fields (:1045-1192)
+        self._fill_exports(export_state, with_3d=True)
+        for name in self.import_field_names():
+            import_state.setdefault(name, None)
+        self.clock_seconds = 0.0
+        return ESMF_SUCCESS
+
+    def initialize_p2(self, import_state: State, export_state: State, clock=None):
+        return ESMF_SUCCESS                                 # :1206-1324: field completion only
+
+    # ---- names ---------------------------------------------------------------------------------
+    def import_field_names(self):
+        names = ["temperature_at_soil_surface", "porosity_at_soil_surface",
+                 "photosynthetically_active_radiation_at_soil_surface"]
+        for n, v in enumerate(VARIABLE_NAMES):
+            names.append(f"{v}_at_soil_surface")
+            if PARTICULATE[n]:
+                names.append(f"{v}_z_velocity_at_soil_surface")
+        return names
+
+    def export_field_names(self):
+        names = [f"{s}_in_soil" for s in STATIC_EXPORTS]
+        names += [f"{v}_in_soil" for v in VARIABLE_NAMES]
+        names += [f"{v}_upward_flux_at_soil_surface" for v in VARIABLE_NAMES]
+        if self.cfg.bioturbation_profile == 3:
+            names += [f"{s}_in_soil" for s in PROFILE3_EXPORTS]
+        names.append("denit_in_soil")                       # FABM diagnostic, :1012-1040
+        return names
+
+    @staticmethod
+    def _lookup(state: State, base: str, suffix: str):
+        key = base + suffix
+        if state.get(key) is not None:
+            return state[key]
+        for alias in LEGACY_ALIASES.get(base, ()):
+            if state.get(alias + suffix) is not None:
+                return state[alias + suffix]
+        return None
+
+    # ---- ReadRestart (:1328-1489) -----------------------------------------------------------------
+    def read_restart(self, import_state: State, export_state: State, clock=None):
+        sed = self.sed
+        conc = None
+        for n, v in enumerate(VARIABLE_NAMES):
+            f = import_state.get(f"{v}_in_soil")
+            if f is None:
+                continue
+            if tuple(f.shape) != sed.shape3d:               # bounds must match (:1440-1460)
+                continue
+            if conc is None:
+                conc = sed.conc
+            conc[:, :, :, n] = f
+        if conc is not None:
+            sed.conc = conc
+        por = import_state.get("porosity_in_soil")
+        if por is not None and tuple(por.shape) == sed.shape3d:
+            sed.set_porosity(por)
+        rc = sed.check_domain()                              # :1485
+        if rc:
+            raise ComponentError(rc, "check_domain failed after restart")
+        return ESMF_SUCCESS
+
+    # ---- Run (:1493-1829) -------------------------------------------------------------------------
+    def run(self, import_state: State, export_state: State, clock=None, *, run_seconds: float = None):
+        """One coupling interval.  ``clock`` may be a dict with 'currTime'/'stopTime' in seconds."""
+        sed = self.sed
+        r = self.run_nml
+        if run_seconds is None:
+            run_seconds = float(clock["stopTime"] - clock["currTime"])
+        par = import_state.get("photosynthetically_active_radiation_at_soil_surface")
+        if par is not None:                                  # :1568-1596
+            sed.set_par_surface(par)
+        por = import_state.get("porosity_at_soil_surface")
+        if por is not None:                                  # :1619-1643
+            sed.update_porosity(por, from_surface=True)
+        temp = import_state.get("temperature_at_soil_surface")
+        cs = [self._lookup(import_state, v, "_at_soil_surface") for v in VARIABLE_NAMES]
+        wz = [self._lookup(import_state, v, "_z_velocity_at_soil_surface") if PARTICULATE[n] else None
+              for n, v in enumerate(VARIABLE_NAMES)]
+        sed.get_boundary_conditions(temp, cs, wz)            # :1665
+        rc = sed.run(float(r["dt"]), int(r["ode_method"]), float(run_seconds))   # :1700-1769
+        self.last_info = sed.info
+        self.clock_seconds += float(run_seconds)
+        if rc == _abi.NAN_DETECTED:                          # :1718-1723
+            raise ComponentError(ESMF_RC_VAL_OUTOFRANGE, "NaN detected applying ode_solver")
+        self._fill_exports(export_state, with_3d=self.export_3d_every_run)       # :1773-1822
+        return ESMF_SUCCESS
+
+    def _fill_exports(self, export_state: State, with_3d: bool):
+        sed = self.sed
+        up = sed.upward_fluxes(self.flux_buffer)
+        for n, v in enumerate(VARIABLE_NAMES):
+            export_state[f"{v}_upward_flux_at_soil_surface"] = up[:, :, n]
+        if not with_3d:
+            return
+        conc = sed.conc
+        for n, v in enumerate(VARIABLE_NAMES):
+            export_state[f"{v}_in_soil"] = conc[:, :, :, n]
+        for s in STATIC_EXPORTS:
+            export_state[f"{s}_in_soil"] = sed.field(s)
+        if self.cfg.bioturbation_profile == 3:
+            for s in PROFILE3_EXPORTS:
+                export_state[f"{s}_in_soil"] = sed.field(s)
+        export_state["denit_in_soil"] = sed.field("denit")
+
+    # ---- Finalize (:1833-1861) ------------------------------------------------------------------------
+    def finalize(self, import_state: State = None, export_state: State = None, clock=None):
+        if self.sed is not None:
+            self.sed.finalize()
+            self.sed = None
+        return ESMF_SUCCESS

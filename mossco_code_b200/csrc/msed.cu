@@ -387,6 +387,11 @@ extern "C" {
 
 const char *msed_version(void) { return "msed_b200 abi1 sm_100a"; }
 
+size_t msed_sizeof(int what)
+{
+    return what == 0 ? sizeof(msed_config) : what == 1 ? sizeof(msed_step_info) : 0;
+}
+
 const char *msed_last_error(const msed_handle *h) { return h ? h->err.c_str() : g_err.c_str(); }
 
 int msed_config_defaults(msed_config *c)

@@ -196,9 +196,13 @@ class SedimentDriver:
         self._check(self._lib.msed_get_fluxes(self._h, _ptr(out)))
         return out
 
-    def upward_fluxes(self) -> np.ndarray:
-        """``<var>_upward_flux_at_soil_surface`` = -fluxes (component :1819)."""
-        out = np.zeros(self.shape2d + (self.nvar,), order="F")
+    def upward_fluxes(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``<var>_upward_flux_at_soil_surface`` = -fluxes (component :1819).  ``out`` may be a
+        caller-owned (e.g. pinned) Fortran-ordered buffer."""
+        if out is None:
+            out = np.zeros(self.shape2d + (self.nvar,), order="F")
+        elif out.shape != self.shape2d + (self.nvar,) or not out.flags.f_contiguous or out.dtype != np.float64:
+            raise ValueError("upward_fluxes: out must be fp64, Fortran order, shape (inum,jnum,nvar)")
         self._check(self._lib.msed_get_upward_fluxes(self._h, _ptr(out)))
         return out
 

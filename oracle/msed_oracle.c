@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <malloc.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -672,6 +673,12 @@ double osed_bench_tiled(int inum, int jnum, int knum, double dzmin, const osed_s
 {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > jnum) nthreads = jnum;
+    /* The reference's temporaries are automatic (stack) arrays: touched once, then reused.  Keep
+     * freed heap blocks mapped so the per-call malloc/free here does not page-fault every step,
+     * which would understate the CPU baseline. */
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 64 << 20);
     const int nvar = OSED_NVAR_OMEXDIA;
     osed_sed *tiles = (osed_sed *)calloc(nthreads, sizeof(osed_sed));
     double **tconc = (double **)calloc(nthreads, sizeof(double *));
