@@ -193,7 +193,7 @@ cudaError_t launch_op(int op, const KParams &p, cudaStream_t s)
     const dim3 grid(nblocks(p.ncol, COL_BLOCK)), block(COL_BLOCK);
     switch (op) {
 #define MSED_CASE(OPV) \
-    case OPV: column_kernel<MODEL, OPV, P3><<<grid, block, 0, s>>>(p); break;
+    case OPV: column_kernel<MODEL, OPV, P3><<<grid, block, COLUMN_SMEM_BYTES, s>>>(p); break;
         MSED_CASE(OP_RHS)
         MSED_CASE(OP_EULER)
         MSED_CASE(OP_ADAPTIVE)

@@ -1,0 +1,436 @@
+// msed_column.cuh -- included inside namespace msed by msed_kernels.cuh.
+//
+// The fused column kernel.  One thread owns one sediment column (lanes of a warp own adjacent
+// columns -> every global access of the [nvar][knum][ld] state is a coalesced 256-byte warp access)
+// and walks it top -> bottom.  Global reads never stall the math: each thread streams its column
+// through a private STAGES-deep ring in shared memory with cp.async (LDGSTS), STAGES-1 layers ahead
+// of the layer it is computing, so the loads in flight per SM are set by the ring depth, not by the
+// register file.  Per layer the thread reads layer k and k+1 back from its ring slots, evaluates
+//   - the diff3d interface flux (fabm_sediment_driver.F90:776-778) with the layer-k+1 diffusivities,
+//   - the omexdia_p reaction rates of layer k,
+//   - dC (:819), the integrator update (solver_library.F90:102/:111/:147-182), the relative-change
+//     test (:121), check_NaN (component :2392) and the minimum clip (component :1728),
+// and stores layer k.  Per ode_solver attempt the state is read once and written once.
+
+// ---- small device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ double ld_ro(const double *p) { return __ldg(p); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ double lds64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// 1/x to within ~1 ulp: MUFU.RCP64H seed (>= 20 bits) + two Newton steps.  No IEEE slow path:
+// every denominator on this path is a positive, normal number (half-saturation sums, porosity*dz).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+// hzg_omexdia_p local rates for one cell: SURVEY.md Appendix B (frozen project spec; the FABM
+// source is not part of the reference tree).  fT is the per-column Arrhenius factor; every a/b of
+// the spec is evaluated as a*fast_rcp(b).
+__device__ __forceinline__ void omexdia_rates(const OmexDev &m, const double (&c)[NV], double fT,
+                                              double (&r)[NV], double *denit)
+{
+    const double ldetC = c[0], sdetC = c[1], detP = c[2], po4 = c[3];
+    const double no3 = c[4], nh3 = c[5], oxy = c[6], odu = c[7];
+    const double relaxO2 = 0.04;
+
+    const double r1 = fast_rcp(oxy + m.ksO2oxic + relaxO2 * (nh3 + odu));
+    const double r2 = fast_rcp(oxy + m.kinO2denit);
+    const double r3 = fast_rcp(no3 + m.ksNO3denit);
+    const double r4 = fast_rcp(oxy + m.kinO2anox);
+    const double r5 = fast_rcp(no3 + m.kinNO3anox);
+    const double r7 = fast_rcp(oxy + m.ksO2nitri + relaxO2 * (ldetC + odu));
+    const double r8 = fast_rcp(oxy + m.ksO2oduox + relaxO2 * (nh3 + ldetC));
+
+    const double Oxicminlim = oxy * r1;
+    const double Denitrilim = (1.0 - oxy * r2) * no3 * r3;
+    const double Anoxiclim = (1.0 - oxy * r4) * (1.0 - no3 * r5);
+    const double Rescale = fast_rcp(Oxicminlim + Denitrilim + Anoxiclim);
+
+    const double CprodL = m.rLabile * ldetC;
+    const double CprodS = m.rSemilabile * sdetC;
+    const double Csum = CprodL + CprodS;
+    const double Cprod = (Csum > m.CprodMax) ? m.CprodMax : Csum;
+    const double Nprod = CprodL * m.NCrLdet + CprodS * m.NCrSdet;
+
+    const double radsP = m.PAds_rS * po4 * ((odu > m.PAdsODU) ? odu : m.PAdsODU);
+    const double rP = m.rLabile * (1.0 - Oxicminlim);
+    const double Pprod = rP * detP;
+
+    const double OxicMin = Cprod * Oxicminlim * Rescale;
+    const double Denitrific = Cprod * Denitrilim * Rescale;
+    const double AnoxicMin = Cprod * Anoxiclim * Rescale;
+
+    const double Nitri = fT * m.rnit * nh3 * oxy * r7;
+    const double OduOx = fT * m.rODUox * odu * oxy * r8;
+
+    r[0] = -fT * CprodL;
+    r[1] = -fT * CprodS;
+    r[2] = fT * (radsP - Pprod);
+    r[3] = fT * (Pprod - radsP);
+    r[4] = -0.8 * Denitrific + Nitri;
+    r[5] = (Nprod - Nitri) * m.rNH3Ads;
+    r[6] = -OxicMin - 2.0 * Nitri - OduOx;
+    r[7] = AnoxicMin - OduOx;
+    if (denit) *denit = 0.8 * Denitrific;
+}
+
+// Zhang & Wirtz bioturbation factor of one cell, fabm_sediment_driver.F90:627-644
+__device__ __forceinline__ double wtoc_cell(const KParams &p, double por, double poc0, double poc1)
+{
+    // weighted_toc + factor*porosity/(ones3d-porosity)*data, evaluated left to right (:627)
+    double wt = 0.0;
+    wt = wt + p.poc_factor[0] * por / (1.0 - por) * poc0;
+    wt = wt + p.poc_factor[1] * por / (1.0 - por) * poc1;
+    return wt;
+}
+__device__ __forceinline__ double bf3_cell(const KParams &p, int k, double wt, double avg)
+{
+    const double biomass = wt * p.e1[k] * avg / (p.L1 + p.L2 * p.e2[k]);
+    return p.beta * pow(biomass, p.b) / wt;
+}
+
+template <int OP> struct OpTraits {
+    static constexpr bool stepping = (OP != OP_RHS);
+    static constexpr bool reads_base = (OP == OP_RK4_S2 || OP == OP_RK4_S3 || OP == OP_RK4_S4 ||
+                                        OP == OP_RK38_S2 || OP == OP_RK38_S3 || OP == OP_RK38_S4);
+    static constexpr bool final_stage = (OP == OP_EULER || OP == OP_ADAPTIVE || OP == OP_RK4_S4 ||
+                                         OP == OP_RK38_S4);
+    // stage evaluates the RHS on the scratch state c1 (buf[1-cur]) rather than on conc
+    static constexpr bool in_is_c1 = reads_base;
+    static constexpr bool reads_a1 = (OP == OP_RK4_S2 || OP == OP_RK4_S3 || OP == OP_RK4_S4 ||
+                                      OP == OP_RK38_S2 || OP == OP_RK38_S3);
+    static constexpr bool reads_a2 = (OP == OP_RK38_S3 || OP == OP_RK38_S4);
+};
+
+constexpr int ROWS = NV + 1;                 // 8 state rows + porosity per layer
+constexpr int RING_STAGES = 4;               // layers resident in the shared-memory ring (power of 2)
+constexpr uint32_t ROW_BYTES = COL_BLOCK * 8;
+constexpr uint32_t STAGE_BYTES = ROWS * ROW_BYTES;
+constexpr size_t COLUMN_SMEM_BYTES = (size_t)RING_STAGES * STAGE_BYTES;
+
+// ---------------------------------------------------------------------------------------------
+// the column kernel
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int OP, bool PROFILE3>
+__global__ void __launch_bounds__(COL_BLOCK, COL_MIN_BLOCKS)
+column_kernel(const __grid_constant__ KParams p)
+{
+    using T = OpTraits<OP>;
+    extern __shared__ __align__(16) double ring[];
+    int cur = 0;
+    double dt = p.dt;
+    bool final_sub = true, do_clip = false;
+    if (T::stepping && p.use_ctl) {
+        const Ctl *ctl = p.ctl;
+        if (ctl->stop || ctl->steps_done >= ctl->steps_target) return;
+        cur = ctl->cur;
+        do_clip = ctl->do_clip != 0;
+        if (OP == OP_ADAPTIVE) {
+            dt = ctl->dt_red;
+            final_sub = !(ctl->dt_int + dt < ctl->dt);
+        } else {
+            dt = ctl->dt;
+        }
+    }
+    const int col = blockIdx.x * COL_BLOCK + threadIdx.x;
+    if (col >= p.ncol) return;
+
+    const int K = p.K;
+    const size_t ld = p.ld;
+    const size_t plane = (size_t)K * ld;  // distance between two state variables
+    const bool masked = p.mask[col] != 0;
+
+    if (OP == OP_RHS) {
+        if (masked) {  // driver :703-709 ; dissolved fluxes of masked columns are defined as 0
+            for (int n = 0; n < NV; ++n)
+                for (int k = 0; k < K; ++k) p.rhs_out[(size_t)(n * K + k) * ld + col] = 0.0;
+            for (int n = NPART; n < NV; ++n) p.fluxes[(size_t)n * ld + col] = 0.0;
+            return;
+        }
+    } else if (masked) {
+        return;  // conc stays missing_value in both buffers; rhs == 0 there
+    }
+
+    const double *in = (T::in_is_c1 ? p.buf[1 - cur] : p.buf[cur]) + col;
+    const double *base = p.buf[cur] + col;
+    double *out = ((OP == OP_RK4_S4 || OP == OP_RK38_S4) ? p.buf[cur] : p.buf[1 - cur]) + col;
+    const double *poc = p.buf[cur] + col;  // poc_classes%data => original conc (driver :476)
+    double *aux1 = p.aux1 + col, *aux2 = p.aux2 + col;
+    const double *por = p.por + col;
+
+    if (MODEL == MSED_MODEL_TEST_SOLVER) {
+        // rhs(i,j,k,:) = (i+j+k)*1.0d-8, src/test/test_Solver.F90:40
+        const int i1 = col % p.inum + 1 + p.i_offset, j1 = col / p.inum + 1 + p.j_offset;
+        for (int k = 0; k < K; ++k) {
+            const double rhs = (double)(i1 + j1 + k + 1) * 1.0e-8;
+            for (int n = 0; n < NV; ++n) {
+                const size_t q = (size_t)(n * K + k) * ld;
+                if (OP == OP_RHS) p.rhs_out[q + col] = rhs;
+                else out[q] = __dadd_rn(in[q], __dmul_rn(dt, rhs));
+            }
+        }
+        return;
+    }
+
+    // ---- thread-private prefetch ring: layer kk lives in slot kk % RING_STAGES --------------------
+    const uint32_t sbase = smem_u32(ring) + threadIdx.x * 8u;
+    const double *g_in = in, *g_por = por;  // running source pointers of the next layer to fetch
+    int k_fetch = 0;
+    auto fetch_next = [&]() {
+        if (k_fetch < K) {
+            const uint32_t sa = sbase + (uint32_t)(k_fetch & (RING_STAGES - 1)) * STAGE_BYTES;
+            const double *g = g_in;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                cp_async8(sa + n * ROW_BYTES, g);
+                g += plane;
+            }
+            cp_async8(sa + NV * ROW_BYTES, g_por);
+            g_in += ld;
+            g_por += ld;
+        }
+        ++k_fetch;
+        cp_async_commit();  // committed even when empty so the group accounting stays uniform
+    };
+#pragma unroll
+    for (int s = 0; s < RING_STAGES - 1; ++s) fetch_next();
+
+    // ---- per-column constants -----------------------------------------------------------
+    const double temp = ld_ro(p.bdys + col);  // temp3d(:,:,k) = bdys(:,:,1), driver :602
+    double cpart, fT = 1.0;
+    if (PROFILE3) {
+        cpart = 1.0 / 86400.0 / 10000.0;  // f_T = 1, bioturbation = 1, driver :622-623
+    } else {
+        const double f_T = exp(-4500.0 * (1.0 / (temp + 273.0) - (1.0 / 288.0)));  // :648
+        cpart = p.bioturbation * f_T / 86400.0 / 10000.0;                          // :652
+    }
+    const double cdiss = (p.diffusivity + temp * 0.035) / 86400.0 / 10000.0;       // :682-683
+    if (MODEL == MSED_MODEL_OMEXDIA_P)
+        fT = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
+
+    double avg_wt = 0.0;
+    if (PROFILE3) {  // column integral of the weighted TOC, driver :629-633
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double pk = ld_ro(por + (size_t)k * ld);
+            s += p.dz[k] * wtoc_cell(p, pk, poc[(size_t)k * ld], poc[(size_t)(K + k) * ld]);
+        }
+        avg_wt = s / p.cumdepth_last;
+    }
+
+    // ---- layer 1 and the upper boundary ---------------------------------------------------
+    cp_async_wait<RING_STAGES - 2>();  // layer 0 has landed
+    double F[NV];                      // flux through the upper interface of the current layer
+    double rest[NPART];
+    bool casc[NPART];
+    double cap_prev = 0.0;
+    {
+        const double por0 = lds64(sbase + NV * ROW_BYTES);
+        double bf0 = p.bf[0];
+        if (PROFILE3) bf0 = bf3_cell(p, 0, wtoc_cell(p, por0, poc[0], poc[plane]), avg_wt);
+        const double Dp = cpart * (1.0 - por0) * bf0;  // intf_porosity(:,:,1) = porosity(:,:,1), :434
+        const double Dd = Dp + cdiss * por0;
+        const double rdz0 = 1.0 / p.dz[0];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const bool part = n < NPART;
+            const int bc = part ? p.bcup_part : p.bcup_diss;
+            double f = 0.0;
+            if (bc == 1 || bc == 4) {
+                f = ld_ro(p.fluxes + (size_t)n * ld + col);  // driver :783,:792
+            } else if (bc == 2) {                             // :786
+                const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
+                const double c1 = lds64(sbase + n * ROW_BYTES);
+                const double C1 = part ? c1 * por0 : c1;
+                f = -(part ? Dp : Dd) * (C1 - Cup) * rdz0;
+            }
+            F[n] = f;
+            if (!part) p.fluxes[(size_t)n * ld + col] = f;   // fluxes(:,:,n) = intFlux(:,:,1), :692
+        }
+        if (p.bcup_part == 4) {  // :792-794
+            cap_prev = p.pom_flux_rate * (1.0 - por0) * p.dz[0];
+#pragma unroll
+            for (int n = 0; n < NPART; ++n) {
+                rest[n] = F[n] - cap_prev;
+                casc[n] = true;
+                if (K == 1) F[n] += rest[n];  // k=2 > knum: :800-802
+            }
+        }
+    }
+
+    bool viol = false, nanf = false;
+    const bool clip_now = T::final_stage && do_clip && final_sub;
+    double *g_out = out;                                   // running pointers of layer k
+    const double *g_base = base;
+    double *g_a1 = aux1, *g_a2 = aux2;
+    double *g_rhs = p.rhs_out + col;
+
+    for (int k = 0; k < K; ++k) {
+        const bool has_next = (k + 1 < K);
+        fetch_next();                          // layer k+RING_STAGES-1 -> the slot layer k-1 just left
+        cp_async_wait<RING_STAGES - 2>();      // layer k+1 has landed
+        const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * STAGE_BYTES;
+        const uint32_t sn = sbase + (uint32_t)((k + 1) & (RING_STAGES - 1)) * STAGE_BYTES;
+
+        double cc[NV];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
+        const double porc = lds64(sc + NV * ROW_BYTES);
+
+        double basev[NV], a1[NV], a2[NV];
+        if (T::reads_base) {
+            const double *g = g_base;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) { basev[n] = *g; g += plane; }
+        }
+        if (T::reads_a1) {
+            const double *g = g_a1;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) { a1[n] = *g; g += plane; }
+        }
+        if (T::reads_a2) {
+            const double *g = g_a2;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) { a2[n] = *g; g += plane; }
+        }
+
+        // flux through the lower interface (diff3d :776-778; BcDown = 3, :590,:813)
+        double Fn[NV];
+        if (has_next) {
+            const double porn = lds64(sn + NV * ROW_BYTES);
+            const double intf = 0.5 * (porc + porn);  // :435
+            double bfk = p.bf[k + 1];
+            if (PROFILE3)
+                bfk = bf3_cell(p, k + 1,
+                               wtoc_cell(p, porn, poc[(size_t)(k + 1) * ld], poc[plane + (size_t)(k + 1) * ld]),
+                               avg_wt);
+            const double Dp = cpart * (1.0 - intf) * bfk;
+            const double Dd = Dp + cdiss * intf;
+            const double rdzc = p.rdzc[k];
+            const double mDp = -Dp * rdzc, mDd = -Dd * rdzc;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double cn = lds64(sn + n * ROW_BYTES);
+                if (n < NPART) Fn[n] = mDp * (cn * porn - cc[n] * porc);
+                else Fn[n] = mDd * (cn - cc[n]);
+            }
+            if (p.bcup_part == 4) {  // distributed POM flux cascade, :795-802 (kk = k+2, 1-based)
+                double cap = p.pom_flux_rate * (1.0 - porn) * p.dz[k + 1];
+                if (k + 2 > 2 && cap > cap_prev) cap = cap_prev;  // driver :285-291
+                cap_prev = cap;
+#pragma unroll
+                for (int n = 0; n < NPART; ++n) {
+                    if (casc[n] && rest[n] > 0.0) {
+                        Fn[n] += rest[n];
+                        rest[n] -= cap;
+                        if (k + 2 == K) Fn[n] += rest[n];
+                    } else {
+                        casc[n] = false;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) Fn[n] = 0.0;
+        }
+
+        // local reaction rates (fabm_do, driver :700)
+        double r[NV];
+        if (MODEL == MSED_MODEL_OMEXDIA_P) {
+            omexdia_rates(p.om, cc, fT, r, nullptr);
+        } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) r[n] = 0.0;
+        }
+
+        // dC (:819) with the particulate rescaling (:677-678) folded: both reduce to
+        // (Flux(k)-Flux(k+1)) / (porosity*dz)
+        const double rpd = fast_rcp(porc * p.dz[k]);
+        auto finish_layer = [&](auto clip_tag) {
+            constexpr bool CLIP = decltype(clip_tag)::value;
+            double *go = g_out, *ga1 = g_a1, *ga2 = g_a2, *gr = g_rhs;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double rhs = fma(F[n] - Fn[n], rpd, r[n]);  // driver :715
+                F[n] = Fn[n];
+                const double c0 = cc[n];
+                double newc = 0.0;
+                if (OP == OP_RHS) {
+                    *gr = rhs;
+                } else if (OP == OP_EULER || OP == OP_ADAPTIVE) {
+                    newc = fma(dt, rhs, c0);                               // :102,:111
+                    if (OP == OP_ADAPTIVE)                                  // :121
+                        viol |= (fma(-p.fac, c0, newc) < 0.0);
+                } else if (OP == OP_RK4_S1) {                               // :147
+                    newc = fma(0.5 * dt, rhs, c0);
+                    *ga1 = 0.5 * rhs;
+                } else if (OP == OP_RK4_S2) {                               // :152
+                    newc = fma(0.5 * dt, rhs, basev[n]);
+                    *ga1 = a1[n] + rhs;
+                } else if (OP == OP_RK4_S3) {                               // :156
+                    newc = fma(dt, rhs, basev[n]);
+                    *ga1 = a1[n] + rhs;
+                } else if (OP == OP_RK4_S4) {                               // :160
+                    const double third = 1.0 / 3.0;
+                    newc = fma(dt * third, fma(0.5, rhs, a1[n]), basev[n]);
+                } else if (OP == OP_RK38_S1) {                              // :169
+                    const double third = 1.0 / 3.0;
+                    newc = fma(third * dt, rhs, c0);
+                    *ga1 = rhs;
+                } else if (OP == OP_RK38_S2) {                              // :174
+                    const double third = 1.0 / 3.0;
+                    const double r0 = a1[n];
+                    newc = fma(dt, fma(-third, r0, rhs), basev[n]);
+                    *ga1 = r0 - rhs;
+                    *ga2 = fma(3.0, rhs, r0);
+                } else if (OP == OP_RK38_S3) {                              // :178
+                    newc = fma(dt, a1[n] + rhs, basev[n]);
+                    *ga2 = fma(3.0, rhs, a2[n]);
+                } else if (OP == OP_RK38_S4) {                              // :182
+                    newc = fma(dt * 1.0 / 8.0, a2[n] + rhs, basev[n]);
+                }
+                if (OP != OP_RHS) {
+                    if (CLIP) {
+                        nanf |= (newc != newc);                             // component :2392
+                        const double mn = p.om.minimum[n];                  // :1728-1730
+                        newc = (newc < mn) ? mn : newc;
+                    }
+                    *go = newc;
+                }
+                go += plane; ga1 += plane; ga2 += plane; gr += plane;
+            }
+        };
+        if (T::final_stage && clip_now) finish_layer(std::true_type{});
+        else finish_layer(std::false_type{});
+        g_out += ld; g_base += ld; g_a1 += ld; g_a2 += ld; g_rhs += ld;
+    }
+    cp_async_wait<0>();
+
+    if (OP == OP_ADAPTIVE && viol) atomicOr(&p.ctl->flags[0], 1);
+    if (T::final_stage && nanf) atomicOr(&p.ctl->flags[1], 1);
+}
