@@ -1,0 +1,73 @@
+"""Worker for tests/test_gpu_multi.py, launched by torch.distributed.run with one rank per GPU.
+Each rank owns a j-slab; the adaptive accept flag is MAX-reduced over NCCL inside libmsed_b200.
+Rank 0 also integrates the whole tile on its own GPU and compares bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mossco_code_b200 import SedimentDriver, default_config  # noqa: E402
+from mossco_code_b200.sharding import gather_slabs, init_flag_collective, local_slab, slab_bounds  # noqa: E402
+from tests.cases import make_case  # noqa: E402
+
+DT, NSTEPS = 360.0, 4
+
+
+def prepared(case, j0, j1, device, bump_row):
+    cfg = default_config(inum=case.inum, jnum=j1 - j0, knum=case.knum, dzmin=case.dzmin, dt_min=1.0,
+                         device=device, j_offset=j0)
+    sed = SedimentDriver(cfg)
+    sed.init_concentrations()
+    sed.set_boundary(np.asfortranarray(case.bdys[:, j0:j1]), np.asfortranarray(case.fluxes[:, j0:j1]))
+    if j0 <= bump_row < j1:     # one column that violates relative_change_min on a full step
+        c = sed.conc
+        c[2, bump_row - j0, :, 5] *= 50.0
+        c[2, bump_row - j0, :, 6] *= 0.02
+        sed.conc = c
+    return sed
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    case = make_case("mgpu", 40, 8 * world, 20, 0.003, seed=77)
+    bump_row = case.jnum - 2                      # lives in the LAST rank's slab
+    j0, j1 = slab_bounds(case.jnum, world, rank)
+    sed = prepared(case, j0, j1, local, bump_row)
+    init_flag_collective(sed)
+    rc = sed.step(DT, 2, NSTEPS)
+    mine = torch.from_numpy(np.ascontiguousarray(sed.conc)).cuda()
+    sub = torch.tensor([sed.info.subcycle_warnings, sed.info.rhs_evaluations, rc], device="cuda")
+    subs = [torch.zeros_like(sub) for _ in range(world)]
+    dist.all_gather(subs, sub)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)                  # equal slab sizes by construction
+    ok = True
+    if rank == 0:
+        whole = prepared(case, 0, case.jnum, local, bump_row)
+        rc0 = whole.step(DT, 2, NSTEPS)
+        got = gather_slabs([np.asfortranarray(p.cpu().numpy()) for p in parts])
+        info = whole.info
+        same_sub = all(int(s[0]) == info.subcycle_warnings and int(s[1]) == info.rhs_evaluations and
+                       int(s[2]) == 0 for s in subs)
+        ok = rc0 == 0 and info.subcycle_warnings > 0 and same_sub and np.array_equal(got, whole.conc)
+        print(f"MGPU world={world} subcycles={info.subcycle_warnings} rhs={info.rhs_evaluations} "
+              f"per-rank={[s.tolist() for s in subs]} bit_exact={np.array_equal(got, whole.conc)}")
+        whole.finalize()
+    sed.finalize()
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(int(flag.item()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+"""The ESMF-component mirror (mossco_code_b200/component.py) against the same sequence driven on the
+oracle: phases, import/export field names and one coupling interval of Run
+(src/components/fabm_sediment_component.F90:99-131, :943-1192, :1493-1829)."""
+import numpy as np
+import pytest
+
+from tests.cases import make_case, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _import_state(case, rng):
+    from mossco_code_b200.sediment import PARTICULATE, VARIABLE_NAMES
+    s = {"temperature_at_soil_surface": np.asfortranarray(case.bdys[:, :, 0].copy())}
+    for n, v in enumerate(VARIABLE_NAMES):
+        if PARTICULATE[n]:   # default.dat style: negative "concentration", w = 1 => downward flux
+            s[f"{v}_at_soil_surface"] = np.asfortranarray(-case.fluxes[:, :, n])
+            s[f"{v}_z_velocity_at_soil_surface"] = np.ones(case.mask.shape, order="F")
+        else:
+            s[f"{v}_at_soil_surface"] = np.asfortranarray(case.bdys[:, :, n + 1].copy())
+    s["photosynthetically_active_radiation_at_soil_surface"] = np.asfortranarray(case.par_surface)
+    return s
+
+
+def test_component_run_matches_oracle_sequence(gpu, oracle):
+    from mossco_code_b200.component import FabmSedimentComponent
+    from mossco_code_b200.sediment import PARTICULATE, VARIABLE_NAMES
+    case = make_case("comp", 9, 7, 15, 0.004, seed=17, land_fraction=0.2, par_max=40.0)
+    comp = FabmSedimentComponent()
+    imp, exp = {}, {}
+    assert set(k for k in comp.set_services()) >= {("initialize", 0), ("initialize", 1), ("initialize", 2),
+                                                    ("readrestart", 1), ("run", 1), ("finalize", 1)}
+    comp.initialize_p0(imp, exp)
+    assert comp.phase_map == ["IPDv00p1=1", "IPDv00p2=2"]
+    gridmask = 1 - case.mask                      # ESMF_GRIDITEM_MASK: <=0 is masked (:499)
+    comp.initialize_p1(imp, exp, grid_shape=(9, 7), grid_mask=gridmask,
+                       run_nml=dict(numlayers=15, dzmin=0.004, dt=360.0, dt_min=1.0, ode_method=2))
+    comp.initialize_p2(imp, exp)
+    # import / export catalogue
+    assert "temperature_at_soil_surface" in imp and "porosity_at_soil_surface" in imp
+    for n, v in enumerate(VARIABLE_NAMES):
+        assert f"{v}_at_soil_surface" in imp
+        assert (f"{v}_z_velocity_at_soil_surface" in imp) == PARTICULATE[n]
+        assert exp[f"{v}_in_soil"].shape == (9, 7, 15)
+        assert exp[f"{v}_upward_flux_at_soil_surface"].shape == (9, 7)
+    for s in ("porosity", "layer_height", "layer_center_depth", "temperature",
+              "photosynthetically_active_radiation"):
+        assert exp[f"{s}_in_soil"].shape == (9, 7, 15)
+    assert set(comp.export_field_names()) <= set(exp)
+
+    # the same on the oracle
+    ref = oracle.OracleSediment.from_config(comp.cfg, mask2d=case.mask)
+    ref.init_concentrations()
+    wet = case.mask == 0
+    assert np.array_equal(exp["dissolved_oxygen_in_soil"][wet], ref.conc[:, :, :, 6][wet])
+
+    rng = np.random.default_rng(0)
+    state = _import_state(case, rng)
+    imp.update(state)
+    for it in range(3):                           # three coupling intervals of 1 h
+        comp.run(imp, exp, clock={"currTime": 3600.0 * it, "stopTime": 3600.0 * (it + 1)})
+        ref.par_surface[...] = case.par_surface
+        cs = [state[f"{v}_at_soil_surface"] for v in VARIABLE_NAMES]
+        wz = [state.get(f"{v}_z_velocity_at_soil_surface") for v in VARIABLE_NAMES]
+        ref.get_boundary_conditions(state["temperature_at_soil_surface"], cs, wz)
+        assert ref.step(360.0, 2, 10) == 0
+        assert comp.last_info.steps_done == 10
+    for n, v in enumerate(VARIABLE_NAMES):
+        assert rel_err(exp[f"{v}_in_soil"][wet], ref.conc[:, :, :, n][wet]) <= 1e-10, v
+        assert scaled_err(exp[f"{v}_upward_flux_at_soil_surface"][wet][..., None],
+                          -ref.fluxes[:, :, n][wet][..., None]) <= 1e-10, v
+    assert np.array_equal(exp["temperature_in_soil"][wet], ref.field3d("temp3d")[wet])
+    assert scaled_err(exp["photosynthetically_active_radiation_in_soil"][wet][..., None],
+                      ref.field3d("par")[wet][..., None]) < 1e-14
+    assert np.array_equal(exp["porosity_in_soil"], ref.field3d("porosity"))
+    comp.finalize()
+
+
+def test_component_shortened_last_step(gpu, oracle):
+    """Run stops exactly at stopTime: 1000 s = 2 x 360 s + 280 s (component :1705-1708)."""
+    from mossco_code_b200.component import FabmSedimentComponent
+    case = make_case("short", 4, 3, 12, 0.004, seed=5)
+    comp = FabmSedimentComponent()
+    imp, exp = {}, {}
+    comp.initialize_p1(imp, exp, grid_shape=(4, 3),
+                       run_nml=dict(numlayers=12, dzmin=0.004, dt=360.0, dt_min=1.0, ode_method=2))
+    imp.update(_import_state(case, None))
+    comp.run(imp, exp, run_seconds=1000.0)
+    assert comp.last_info.steps_done == 3
+    ref = oracle.OracleSediment.from_config(comp.cfg)
+    ref.init_concentrations()
+    from mossco_code_b200.sediment import VARIABLE_NAMES
+    cs = [imp[f"{v}_at_soil_surface"] for v in VARIABLE_NAMES]
+    wz = [imp.get(f"{v}_z_velocity_at_soil_surface") for v in VARIABLE_NAMES]
+    ref.get_boundary_conditions(imp["temperature_at_soil_surface"], cs, wz)
+    ref.step(360.0, 2, 2)
+    ref.step(280.0, 2, 1)
+    assert rel_err(comp.sed.conc, ref.conc) <= 1e-11
+    comp.finalize()
+
+
+def test_component_restart_roundtrip(gpu):
+    """ReadRestart (:1328-1489): <name>_in_soil fields of a finished run restart a fresh component."""
+    from mossco_code_b200.component import FabmSedimentComponent
+    case = make_case("rst", 5, 4, 12, 0.004, seed=8, land_fraction=0.2)
+    nml = dict(numlayers=12, dzmin=0.004, dt=360.0, dt_min=1.0, ode_method=2)
+    a, b = FabmSedimentComponent(), FabmSedimentComponent()
+    ia, ea, ib, eb = {}, {}, {}, {}
+    a.initialize_p1(ia, ea, grid_shape=(5, 4), grid_mask=1 - case.mask, run_nml=nml)
+    ia.update(_import_state(case, None))
+    a.run(ia, ea, run_seconds=7200.0)
+    b.initialize_p1(ib, eb, grid_shape=(5, 4), grid_mask=1 - case.mask, run_nml=nml)
+    b.read_restart({k: v for k, v in ea.items() if k.endswith("_in_soil")}, eb)
+    assert np.array_equal(b.sed.conc, a.sed.conc)
+    ib.update(_import_state(case, None))
+    a.run(ia, ea, run_seconds=3600.0)
+    b.run(ib, eb, run_seconds=3600.0)
+    assert np.array_equal(b.sed.conc, a.sed.conc)       # deterministic: bit-identical continuation
+    a.finalize(); b.finalize()
+
+
+def test_component_presimulation(gpu, oracle):
+    """presimulation_years > 0: 1-D spin-up broadcast to every wet column (:557-632)."""
+    from mossco_code_b200.component import FabmSedimentComponent
+    case = make_case("pre", 4, 3, 12, 0.004, seed=3, land_fraction=0.3)
+    comp = FabmSedimentComponent()
+    imp, exp = {}, {}
+    years = 20.0 / 365.0
+    comp.initialize_p1(imp, exp, grid_shape=(4, 3), grid_mask=1 - case.mask,
+                       run_nml=dict(numlayers=12, dzmin=0.004, dt=360.0, dt_min=1.0, ode_method=1,
+                                    presimulation_years=years, pel_Temp=5.0, pel_NO3=14.0, pel_NH4=4.0,
+                                    pel_PO4=0.6, pel_O2=250.0, pflux_lDetC=2.0, pflux_sDetC=24.0,
+                                    pflux_lDetP=0.08))
+    from tests.cases import C1_BDYS, C1_FLUXES
+    nml, par = oracle.from_config(comp.cfg)
+    want = oracle.spinup_column(nml, par, 12, 0.004, 1.0, -0.9, C1_BDYS, C1_FLUXES, 480, method=1)
+    conc = comp.sed.conc
+    wet = case.mask == 0
+    for i, j in zip(*np.nonzero(wet)):
+        assert scaled_err(conc[i, j], want[0, 0]) <= 1e-9
+    assert np.all(conc[~wet] == 1e20)
+    comp.finalize()
