@@ -36,6 +36,8 @@ WORKLOADS = {
     "c4slab": (4096, 512, 40, 0.0015, 4096, 0.0, "one 4096x512x40 slab of C4 (its 8-GPU tile)"),
     "c3": (1000, 1000, 30, 0.002, 2024, 0.45, "C3 1000x1000x30, 45% land mask, smooth T, PAR"),
     "c2": (100, 100, 30, 0.002, 1234, 0.0, "C2 100x100x30 (L2-resident, launch-latency regime)"),
+    "c5": (2048, 2048, 30, 0.002, 2048, 0.0, "C5 2048x2048x30 + one pelagic box per column, bed-flux "
+           "exchange every 3600 s on device (msed_coupled_run)"),
 }
 
 
@@ -258,6 +260,20 @@ def main():
     cells_total = float(cells_total.item())
 
     # ---- device-resident throughput ("value") ---------------------------------------------------
+    coupled = args.workload == "c5"
+    steps_per_coupling = int(round(COUPLING_SECONDS / DT))
+    if coupled:   # pelagic boxes: bottom-water concentrations = the forcing, 10 m boxes, w = -1e-6 m/s
+        pel = np.asfortranarray(np.concatenate([np.abs(fluxes[:, :, :3]) * 1e6, bdys[:, :, 4:]], axis=2))
+        wzp = np.zeros((inum, rows, NVAR), order="F"); wzp[:, :, :3] = -1.0e-6
+        sed.pelagic_init(pel, wzp, np.full((inum, rows), 10.0, order="F"), np.asfortranarray(bdys[:, :, 0]))
+        if args.steps % steps_per_coupling:
+            raise SystemExit(f"--workload c5 needs --steps to be a multiple of {steps_per_coupling}")
+
+    def timed_steps(n):
+        if coupled:
+            return sed.coupled_run(DT, METHOD, COUPLING_SECONDS, n // steps_per_coupling)
+        return sed.step(DT, METHOD, n)
+
     sed.step(DT, METHOD, args.warmup)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -266,7 +282,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
-        rc = sed.step(DT, METHOD, args.steps)
+        rc = timed_steps(args.steps)
         e1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None

@@ -181,6 +181,21 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
 int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const double *fluxes1d,
                        int64_t nsteps, int method, double *conc1d, msed_step_info *info);
 
+/* ---- benthic-pelagic exchange on device (BASELINE config 5) -------------------------------- */
+/* One well-mixed pelagic box per column, resident on the device, so that a coupling step needs no
+ * host<->device traffic.  conc2d(inum,jnum,nvar) are the pelagic concentrations of the sediment's
+ * eight species, wz2d(inum,jnum,nvar) their z-velocities (only the particulate entries are read),
+ * layer_height2d(inum,jnum) the box height, temperature2d(inum,jnum) the bottom-water temperature. */
+int msed_pelagic_init(msed_handle *h, const double *conc2d, const double *wz2d,
+                      const double *layer_height2d, const double *temperature2d);
+int msed_pelagic_get(msed_handle *h, double *conc2d);
+/* ncouplings coupling intervals, each: get_boundary_conditions from the pelagic boxes
+ * (fabm_sediment_component.F90:1930-2020: temperature, dissolved bdys, particulate fluxes=-C*w) ->
+ * msed_run(dt, method, coupling_seconds) -> pelagic conc += upward_flux*coupling_seconds/layer_height
+ * where layer_height>0 (src/components/fabm_pelagic_component.F90:2100-2105). */
+int msed_coupled_run(msed_handle *h, double dt, int method, double coupling_seconds,
+                     int64_t ncouplings, msed_step_info *info);
+
 /* ---- execution control -------------------------------------------------------------------- */
 /* all work is enqueued on this cudaStream_t (default: a private non-blocking stream) */
 int msed_set_stream(msed_handle *h, void *cuda_stream);

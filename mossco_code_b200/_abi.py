@@ -105,6 +105,9 @@ SYMBOLS = {
     "msed_run": (C.c_int, [_h, C.c_double, C.c_int, C.c_double, C.POINTER(StepInfo)]),
     "msed_spinup_column": (C.c_int, [C.POINTER(Config), _dp, _dp, C.c_int64, C.c_int, _dp,
                                      C.POINTER(StepInfo)]),
+    "msed_pelagic_init": (C.c_int, [_h, _dp, _dp, _dp, _dp]),
+    "msed_pelagic_get": (C.c_int, [_h, _dp]),
+    "msed_coupled_run": (C.c_int, [_h, C.c_double, C.c_int, C.c_double, C.c_int64, C.POINTER(StepInfo)]),
     "msed_set_stream": (C.c_int, [_h, C.c_void_p]),
     "msed_synchronize": (C.c_int, [_h]),
     "msed_device_state": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

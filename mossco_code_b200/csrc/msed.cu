@@ -65,6 +65,7 @@ struct msed_handle {
     double *aux[2] = {nullptr, nullptr};
     double *por = nullptr, *bdys = nullptr, *fluxes = nullptr, *par_surface = nullptr;
     double *scratch = nullptr;  // [nvar][K][ld] staging (rhs / fields / packed transfers)
+    double *pel = nullptr;      // pelagic boxes: conc [nvar][ld], wz [nvar][ld], height [ld], temperature [ld]
     double *tables = nullptr;   // device copies of zc[K], cumdepth[K], porosity profile[K]
     unsigned char *mask = nullptr;
     Ctl *ctl = nullptr;         // device
@@ -556,7 +557,7 @@ int msed_destroy(msed_handle *h)
     cudaFree(h->buf[0]); cudaFree(h->buf[1]); cudaFree(h->aux[0]); cudaFree(h->aux[1]);
     cudaFree(h->por); cudaFree(h->bdys); cudaFree(h->fluxes); cudaFree(h->par_surface);
     cudaFree(h->scratch); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->ctl);
-    cudaFree(h->minloc_val); cudaFree(h->minloc_idx);
+    cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->pel);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -922,6 +923,76 @@ int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const doubl
     if (rc == MSED_OK) rc = msed_get_state(h, conc1d);
     if (rc) g_err = h->err;
     msed_destroy(h);
+    return rc;
+}
+
+int msed_pelagic_init(msed_handle *h, const double *conc2d, const double *wz2d, const double *layer_height2d,
+                      const double *temperature2d)
+{
+    if (!h || !conc2d || !wz2d || !layer_height2d || !temperature2d) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t rows = 2 * NV + 2;
+    if (!h->pel) {
+        CUDA_TRY(h, cudaMalloc(&h->pel, rows * h->ld * sizeof(double)));
+        CUDA_TRY(h, cudaMemsetAsync(h->pel, 0, rows * h->ld * sizeof(double), h->stream));
+    }
+    int rc;
+    if ((rc = upload_rows(h, h->pel, conc2d, NV))) return rc;
+    if ((rc = upload_rows(h, h->pel + (size_t)NV * h->ld, wz2d, NV))) return rc;
+    if ((rc = upload_rows(h, h->pel + (size_t)2 * NV * h->ld, layer_height2d, 1))) return rc;
+    if ((rc = upload_rows(h, h->pel + (size_t)(2 * NV + 1) * h->ld, temperature2d, 1))) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_pelagic_get(msed_handle *h, double *conc2d)
+{
+    if (!h || !conc2d) return fail(h, MSED_ERR_ARG, "null argument");
+    if (!h->pel) return fail(h, MSED_ERR_STATE, "msed_pelagic_init has not been called");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return download_rows(h, conc2d, h->pel, NV);
+}
+
+int msed_coupled_run(msed_handle *h, double dt, int method, double coupling_seconds, int64_t ncouplings,
+                     msed_step_info *info)
+{
+    if (!h) return MSED_ERR_ARG;
+    if (!h->pel) return fail(h, MSED_ERR_STATE, "msed_pelagic_init has not been called");
+    if (!(dt > 0.0) || !(coupling_seconds > 0.0) || ncouplings < 0) return fail(h, MSED_ERR_ARG, "bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    msed_step_info acc, one;
+    std::memset(&acc, 0, sizeof(acc));
+    acc.last_min_dt = h->last_min_dt;
+    for (int q = 0; q < 4; ++q) acc.last_min_dt_grid_cell[q] = h->last_min_dt_grid_cell[q];
+    BcPtrs in;
+    std::memset(&in, 0, sizeof(in));
+    in.temperature = h->pel + (size_t)(2 * NV + 1) * h->ld;
+    for (int n = 0; n < NV; ++n) {
+        in.csurf[n] = h->pel + (size_t)n * h->ld;
+        if (n < NPART) in.wz[n] = h->pel + (size_t)(NV + n) * h->ld;
+    }
+    int rc = MSED_OK;
+    for (int64_t c = 0; c < ncouplings && rc == MSED_OK; ++c) {
+        boundary_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
+            h->bdys, h->fluxes, h->buf[h->cur], h->por, in, h->ld, h->ld, h->ncol, h->K,
+            h->cfg.bcup_dissolved_variables, h->bioturbation_eff, h->cfg.diffusivity, h->dz[0]);
+        CUDA_TRY(h, cudaGetLastError());
+        rc = msed_run(h, dt, method, coupling_seconds, &one);
+        if (rc < 0) return rc;
+        pelagic_flux_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
+            h->pel, h->fluxes, h->pel + (size_t)2 * NV * h->ld, h->mask, h->ld, h->ncol, coupling_seconds);
+        CUDA_TRY(h, cudaGetLastError());
+        acc.steps_done += one.steps_done;
+        acc.rhs_evaluations += one.rhs_evaluations;
+        acc.subcycle_warnings += one.subcycle_warnings;
+        acc.last_min_dt = one.last_min_dt;
+        for (int q = 0; q < 4; ++q) acc.last_min_dt_grid_cell[q] = one.last_min_dt_grid_cell[q];
+        acc.nan_detected |= one.nan_detected;
+        acc.kernel_ms += one.kernel_ms;
+        acc.kernel_launches += one.kernel_launches + 2;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (info) *info = acc;
     return rc;
 }
 

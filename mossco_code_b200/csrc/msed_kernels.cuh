@@ -242,6 +242,21 @@ __global__ void boundary_kernel(double *bdys, double *fluxes, const double *conc
     (void)ld_in;
 }
 
+// pelagic boxes take up the bed flux: conc = conc + bfl*dt/layer_height where layer_height > 0
+// (src/components/fabm_pelagic_component.F90:2100-2105); bfl = upward flux = -fluxes (component :1819)
+__global__ void pelagic_flux_kernel(double *pel, const double *fluxes, const double *height,
+                                    const unsigned char *mask, size_t ld, int ncol, double dtc)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol || mask[col]) return;
+    const double hgt = height[col];
+    if (!(hgt > 0.0)) return;
+    for (int n = 0; n < NV; ++n) {
+        const size_t q = (size_t)n * ld + col;
+        pel[q] = __dadd_rn(pel[q], __ddiv_rn(__dmul_rn(-fluxes[q], dtc), hgt));
+    }
+}
+
 // -fluxes(:,:,n) for the export state, component :1819
 __global__ void negate_rows_kernel(double *dst, const double *src, size_t ld, int ncol, int rows)
 {

@@ -234,6 +234,26 @@ class SedimentDriver:
         return self._check(self._lib.msed_run(self._h, float(dt), int(method), float(run_seconds),
                                               C.byref(self.info)), allow=(_abi.NAN_DETECTED,))
 
+    # -- benthic-pelagic exchange on device (BASELINE config 5) --------------------------------
+    def pelagic_init(self, conc2d, wz2d, layer_height2d, temperature2d):
+        c = _f64(conc2d, self.shape2d + (self.nvar,), "pelagic conc")
+        w = _f64(wz2d, self.shape2d + (self.nvar,), "pelagic z_velocity")
+        hgt = _f64(layer_height2d, self.shape2d, "layer_height")
+        t = _f64(temperature2d, self.shape2d, "temperature")
+        self._check(self._lib.msed_pelagic_init(self._h, _ptr(c), _ptr(w), _ptr(hgt), _ptr(t)))
+
+    @property
+    def pelagic_conc(self) -> np.ndarray:
+        out = np.zeros(self.shape2d + (self.nvar,), order="F")
+        self._check(self._lib.msed_pelagic_get(self._h, _ptr(out)))
+        return out
+
+    def coupled_run(self, dt: float, method: int, coupling_seconds: float, ncouplings: int) -> int:
+        """``ncouplings`` x [pelagic -> boundary, Run(coupling_seconds), bed flux -> pelagic], all on device."""
+        return self._check(self._lib.msed_coupled_run(self._h, float(dt), int(method), float(coupling_seconds),
+                                                      int(ncouplings), C.byref(self.info)),
+                           allow=(_abi.NAN_DETECTED,))
+
     # -- execution / multi-GPU ---------------------------------------------------------------
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.msed_set_stream(self._h, C.c_void_p(cuda_stream)))
