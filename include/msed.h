@@ -196,6 +196,41 @@ int msed_pelagic_get(msed_handle *h, double *conc2d);
 int msed_coupled_run(msed_handle *h, double dt, int method, double coupling_seconds,
                      int64_t ncouplings, msed_step_info *info);
 
+/* ---- pelagic <-> soil couplers fused onto the device --------------------- */
+/* pelagic_benthic_coupler Run, src/mediators/pelagic_benthic_coupler.F90:281-492: bottom-layer
+ * pelagic fields (inum,jnum; NULL = field absent from the import state) are converted to the
+ * sediment's *_at_soil_surface / *_z_velocity_at_soil_surface fields and fed straight into
+ * get_boundary_conditions (component :1865-2030) without leaving the device. */
+typedef struct msed_pelagic_state {
+    const double *temperature;        /* temperature_in_water                         (required) */
+    const double *oxygen;             /* dissolved_oxygen_in_water: <0 = reduced subst. (required) */
+    const double *detN;               /* Detritus_Nitrogen_detN_in_water               (required) */
+    const double *detN_z_velocity;    /* ..._z_velocity_in_water                       (required) */
+    const double *detC;               /* Detritus_Carbon_detC_in_water, NULL: C:N = 106/16 */
+    const double *detP;               /* Detritus_Phosphorus_detP_in_water, NULL: detN/16 */
+    const double *detP_z_velocity;    /* NULL: detN_z_velocity */
+    const double *nitrate, *ammonium; /* NULL: 0.5*DIN each */
+    const double *DIN;                /* required when nitrate, ammonium or DIP is NULL */
+    const double *DIP;                /* NULL: DIN/16 */
+} msed_pelagic_state;
+int msed_pelagic_benthic_coupler(msed_handle *h, const msed_pelagic_state *state);
+
+/* benthic_pelagic_coupler Run, src/mediators/benthic_pelagic_coupler.F90:188-287: the sediment's
+ * upward bed fluxes recombined into the pelagic model's flux fields.  Output pointers are host
+ * arrays (inum,jnum); NULL = field not in the export state.  When nitrate/ammonium are NULL the
+ * DIN branch (:228-236) is taken. */
+typedef struct msed_benthic_pelagic_params {
+    double dinflux_const;   /* :39, namelist; constant DIN boundary flux per year */
+    double dipflux_const;   /* <0: dinflux_const/16 (:156 of soil_pelagic_connector, :40 here) */
+    double convertN;        /* :43 */
+    double NC_fdet, NC_sdet;/* :205-206 (0.20, 0.04) */
+} msed_benthic_pelagic_params;
+typedef struct msed_pelagic_fluxes {
+    double *nitrate, *ammonium, *DIN, *DIP, *detN, *detC, *detP, *oxygen;
+} msed_pelagic_fluxes;
+int msed_benthic_pelagic_coupler(msed_handle *h, const msed_benthic_pelagic_params *par,
+                                 const msed_pelagic_fluxes *out);
+
 /* ---- execution control -------------------------------------------------------------------- */
 /* all work is enqueued on this cudaStream_t (default: a private non-blocking stream) */
 int msed_set_stream(msed_handle *h, void *cuda_stream);

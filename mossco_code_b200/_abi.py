@@ -70,6 +70,22 @@ class StepInfo(C.Structure):
     ]
 
 
+class PelagicState(C.Structure):
+    """``msed_pelagic_state`` -- inputs of pelagic_benthic_coupler (NULL = field absent)."""
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in (
+        "temperature", "oxygen", "detN", "detN_z_velocity", "detC", "detP", "detP_z_velocity",
+        "nitrate", "ammonium", "DIN", "DIP")]
+
+
+class BenthicPelagicParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("dinflux_const", "dipflux_const", "convertN", "NC_fdet", "NC_sdet")]
+
+
+class PelagicFluxes(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in (
+        "nitrate", "ammonium", "DIN", "DIP", "detN", "detC", "detP", "oxygen")]
+
+
 ALLREDUCE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 
 _dp = C.POINTER(C.c_double)
@@ -108,6 +124,8 @@ SYMBOLS = {
     "msed_pelagic_init": (C.c_int, [_h, _dp, _dp, _dp, _dp]),
     "msed_pelagic_get": (C.c_int, [_h, _dp]),
     "msed_coupled_run": (C.c_int, [_h, C.c_double, C.c_int, C.c_double, C.c_int64, C.POINTER(StepInfo)]),
+    "msed_pelagic_benthic_coupler": (C.c_int, [_h, C.POINTER(PelagicState)]),
+    "msed_benthic_pelagic_coupler": (C.c_int, [_h, C.POINTER(BenthicPelagicParams), C.POINTER(PelagicFluxes)]),
     "msed_set_stream": (C.c_int, [_h, C.c_void_p]),
     "msed_synchronize": (C.c_int, [_h]),
     "msed_device_state": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

@@ -996,6 +996,75 @@ int msed_coupled_run(msed_handle *h, double dt, int method, double coupling_seco
     return rc;
 }
 
+int msed_pelagic_benthic_coupler(msed_handle *h, const msed_pelagic_state *st)
+{
+    if (!h || !st) return fail(h, MSED_ERR_ARG, "null argument");
+    if (!st->temperature || !st->oxygen || !st->detN || !st->detN_z_velocity)
+        return fail(h, MSED_ERR_ARG, "temperature, oxygen, detN and detN_z_velocity are required");
+    if ((!st->nitrate || !st->ammonium || !st->DIP) && !st->DIN)
+        return fail(h, MSED_ERR_ARG, "DIN is required when nitrate, ammonium or DIP is absent");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    // staging rows (row length ld): [0..10] inputs, [11] temperature, [12..19] csurf, [20..22] wz
+    const size_t ld = h->ld, w = (size_t)h->ncol;
+    double *stage = h->scratch;
+    if ((size_t)NV * h->K < 23) return fail(h, MSED_ERR_STATE, "staging buffer too small");
+    auto up = [&](const double *src, size_t row, const double **dst) -> int {
+        *dst = nullptr;
+        if (!src) return MSED_OK;
+        CUDA_TRY(h, cudaMemcpyAsync(stage + row * ld, src, w * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        *dst = stage + row * ld;
+        return MSED_OK;
+    };
+    P2BIn in;
+    const double *temp = nullptr;
+    if ((rc = up(st->oxygen, 0, &in.oxygen)) || (rc = up(st->detN, 1, &in.detN)) ||
+        (rc = up(st->detN_z_velocity, 2, &in.detN_wz)) || (rc = up(st->detC, 3, &in.detC)) ||
+        (rc = up(st->detP, 4, &in.detP)) || (rc = up(st->detP_z_velocity, 5, &in.detP_wz)) ||
+        (rc = up(st->nitrate, 6, &in.nitrate)) || (rc = up(st->ammonium, 7, &in.ammonium)) ||
+        (rc = up(st->DIN, 8, &in.DIN)) || (rc = up(st->DIP, 9, &in.DIP)) || (rc = up(st->temperature, 11, &temp)))
+        return rc;
+    double *csurf = stage + 12 * ld, *wz = stage + 20 * ld;
+    pelagic_benthic_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(csurf, wz, in, ld, h->ncol);
+    CUDA_TRY(h, cudaGetLastError());
+    BcPtrs bc;
+    std::memset(&bc, 0, sizeof(bc));
+    bc.temperature = temp;
+    for (int n = 0; n < NV; ++n) {
+        bc.csurf[n] = csurf + (size_t)n * ld;
+        if (n < NPART) bc.wz[n] = wz + (size_t)n * ld;
+    }
+    boundary_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
+        h->bdys, h->fluxes, h->buf[h->cur], h->por, bc, h->ld, ld, h->ncol, h->K,
+        h->cfg.bcup_dissolved_variables, h->bioturbation_eff, h->cfg.diffusivity, h->dz[0]);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_benthic_pelagic_coupler(msed_handle *h, const msed_benthic_pelagic_params *par,
+                                 const msed_pelagic_fluxes *out)
+{
+    if (!h || !par || !out) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    const double dip = par->dipflux_const < 0.0 ? par->dinflux_const / 16.0 : par->dipflux_const;
+    benthic_pelagic_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
+        h->scratch, h->fluxes, h->ld, h->ncol, par->dinflux_const, dip, par->convertN, par->NC_fdet,
+        par->NC_sdet);
+    CUDA_TRY(h, cudaGetLastError());
+    double *dst[8] = {out->nitrate, out->ammonium, out->DIN, out->DIP, out->detN, out->detC, out->detP,
+                      out->oxygen};
+    for (int r = 0; r < 8; ++r)
+        if (dst[r])
+            CUDA_TRY(h, cudaMemcpyAsync(dst[r], h->scratch + (size_t)r * h->ld, (size_t)h->ncol * sizeof(double),
+                                        cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
 int msed_set_stream(msed_handle *h, void *cuda_stream)
 {
     if (!h) return MSED_ERR_ARG;

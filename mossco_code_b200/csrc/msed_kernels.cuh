@@ -242,6 +242,59 @@ __global__ void boundary_kernel(double *bdys, double *fluxes, const double *conc
     (void)ld_in;
 }
 
+// pelagic_benthic_coupler Run (src/mediators/pelagic_benthic_coupler.F90:330-480), one thread per
+// column.  Writes the 8 surface concentrations into csurf rows and the 3 sinking velocities into wz
+// rows of a staging area [..][ld_out]; the per-cell intent of the oxygen/odu split is implemented
+// (the reference assigns the whole array inside its i,j loop, :344-349).
+struct P2BIn {
+    const double *oxygen, *detN, *detN_wz, *detC, *detP, *detP_wz, *nitrate, *ammonium, *DIN, *DIP;
+};
+__global__ void pelagic_benthic_kernel(double *csurf, double *wz, P2BIn in, size_t ld_out, int ncol)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    const double NC_fdet = 0.20, NC_sdet = 0.04, sinking_factor = 0.3;   // :298,:301-302
+    const double o2 = in.oxygen[col];
+    const double detN = in.detN[col];
+    const double vN = in.detN_wz[col];
+    const double CN = in.detC ? __ddiv_rn(in.detC[col], detN) : 106.0 / 16.0;           // :379-394
+    const double fac_f = __ddiv_rn(__dsub_rn(1.0, __dmul_rn(NC_sdet, CN)), NC_fdet - NC_sdet);  // :395
+    const double fac_s = __ddiv_rn(__dsub_rn(1.0, __dmul_rn(NC_fdet, CN)), NC_sdet - NC_fdet);  // :396
+    csurf[0 * ld_out + col] = __dmul_rn(fac_f, detN);                                   // :400
+    csurf[1 * ld_out + col] = __dmul_rn(fac_s, detN);                                   // :403
+    csurf[2 * ld_out + col] = in.detP ? in.detP[col] : __dmul_rn(1.0 / 16.0, detN);     // :416-420
+    const double din = in.DIN ? in.DIN[col] : 0.0;
+    csurf[3 * ld_out + col] = in.DIP ? in.DIP[col] : __dmul_rn(1.0 / 16.0, din);        // :466-480
+    csurf[4 * ld_out + col] = in.nitrate ? in.nitrate[col] : __dmul_rn(0.5, din);       // :455-459
+    csurf[5 * ld_out + col] = in.ammonium ? in.ammonium[col] : __dmul_rn(0.5, din);     // :446-450
+    csurf[6 * ld_out + col] = o2 > 0.0 ? o2 : 0.0;                                      // max(0, o2)  :346
+    csurf[7 * ld_out + col] = -o2 > 0.0 ? -o2 : 0.0;                                    // max(0,-o2)  :347
+    wz[0 * ld_out + col] = __dmul_rn(sinking_factor, vN);                               // :406
+    wz[1 * ld_out + col] = __dmul_rn(sinking_factor, vN);                               // :408
+    wz[2 * ld_out + col] = __dmul_rn(sinking_factor, in.detP_wz ? in.detP_wz[col] : vN);  // :427-431
+}
+
+// benthic_pelagic_coupler Run (src/mediators/benthic_pelagic_coupler.F90:211-282).
+// out rows: 0 nitrate 1 ammonium 2 DIN 3 DIP 4 detN 5 detC 6 detP 7 oxygen
+__global__ void benthic_pelagic_kernel(double *out, const double *fluxes, size_t ld, int ncol,
+                                       double dinflux_const, double dipflux_const, double convertN,
+                                       double NC_fdet, double NC_sdet)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    double up[NV];
+    for (int n = 0; n < NV; ++n) up[n] = -fluxes[(size_t)n * ld + col];                 // component :1819
+    const double year = 86400.0 * 365.0;
+    out[0 * ld + col] = __dmul_rn(convertN, __dadd_rn(up[4], __ddiv_rn(__ddiv_rn(dinflux_const, 86400.), 365.)));  // :220
+    out[1 * ld + col] = __dmul_rn(convertN, up[5]);                                      // :222
+    out[2 * ld + col] = __dadd_rn(__dadd_rn(up[4], up[5]), __ddiv_rn(dinflux_const, year));  // :232-234
+    out[3 * ld + col] = __dadd_rn(up[3], __ddiv_rn(dipflux_const, year));                // :245
+    out[4 * ld + col] = __dmul_rn(convertN, __dadd_rn(__dmul_rn(NC_fdet, up[0]), __dmul_rn(NC_sdet, up[1])));  // :258
+    out[5 * ld + col] = __dadd_rn(up[0], up[1]);                                         // :264
+    out[6 * ld + col] = up[2];                                                           // :274
+    out[7 * ld + col] = __dsub_rn(up[6], up[7]);                                         // :281
+}
+
 // pelagic boxes take up the bed flux: conc = conc + bfl*dt/layer_height where layer_height > 0
 // (src/components/fabm_pelagic_component.F90:2100-2105); bfl = upward flux = -fluxes (component :1819)
 __global__ void pelagic_flux_kernel(double *pel, const double *fluxes, const double *height,

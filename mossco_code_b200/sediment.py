@@ -254,6 +254,37 @@ class SedimentDriver:
                                                       int(ncouplings), C.byref(self.info)),
                            allow=(_abi.NAN_DETECTED,))
 
+    # -- pelagic <-> soil couplers on device -----------------------------------
+    def pelagic_benthic_coupler(self, **fields):
+        """``pelagic_benthic_coupler`` Run (src/mediators/pelagic_benthic_coupler.F90:281-492) fused with
+        ``get_boundary_conditions``.  Keyword arguments are the bottom-layer pelagic fields
+        (temperature, oxygen, detN, detN_z_velocity required; detC, detP, detP_z_velocity, nitrate,
+        ammonium, DIN, DIP optional)."""
+        st, keep = _abi.PelagicState(), []
+        for name, arr in fields.items():
+            if not hasattr(st, name):
+                raise AttributeError(f"msed_pelagic_state has no field {name!r}")
+            if arr is not None:
+                a = _f64(arr, self.shape2d, name)
+                keep.append(a)
+                setattr(st, name, _ptr(a))
+        self._check(self._lib.msed_pelagic_benthic_coupler(self._h, C.byref(st)))
+
+    def benthic_pelagic_coupler(self, want=("DIN", "DIP", "detN", "detC", "detP", "oxygen"),
+                                dinflux_const=0.0, dipflux_const=-1.0, convertN=1.0, NC_fdet=0.20,
+                                NC_sdet=0.04):
+        """``benthic_pelagic_coupler`` Run (src/mediators/benthic_pelagic_coupler.F90:188-287): returns
+        a dict of the requested pelagic flux fields."""
+        par = _abi.BenthicPelagicParams(dinflux_const, dipflux_const, convertN, NC_fdet, NC_sdet)
+        out, res = _abi.PelagicFluxes(), {}
+        for name in want:
+            if not hasattr(out, name):
+                raise AttributeError(f"msed_pelagic_fluxes has no field {name!r}")
+            res[name] = np.zeros(self.shape2d, order="F")
+            setattr(out, name, _ptr(res[name]))
+        self._check(self._lib.msed_benthic_pelagic_coupler(self._h, C.byref(par), C.byref(out)))
+        return res
+
     # -- execution / multi-GPU ---------------------------------------------------------------
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.msed_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -855,3 +855,52 @@ void osedpy_test_solver(int inum, int jnum, int knum, int nvar, double *conc, do
     d.get_rhs = test_solver_rhs;
     for (long t = 0; t < nsteps; ++t) osed_ode_solver(&d, dt, method);   /* test_Solver.F90:80-82 */
 }
+
+/* ---- pelagic <-> soil couplers ------------------------------------------- */
+
+/* pelagic_benthic_coupler Run, src/mediators/pelagic_benthic_coupler.F90:330-480.
+ * in[]: 0 oxygen 1 detN 2 detN_wz 3 detC 4 detP 5 detP_wz 6 nitrate 7 ammonium 8 DIN 9 DIP (NULL = absent)
+ * csurf(n2,8), wz(n2,3) out.  The oxygen/odu split follows the per-cell intent of :344-349 (the
+ * reference assigns the whole arrays inside the i,j loop). */
+void osed_pelagic_benthic_coupler(size_t n2, const double *const in[10], double *csurf, double *wz)
+{
+    const double NC_fdet = 0.20, NC_sdet = 0.04, sinking_factor = 0.3;   /* :298,:301-302 */
+    for (size_t c = 0; c < n2; ++c) {
+        double o2 = in[0][c], detN = in[1][c], vN = in[2][c];
+        double CN_det = in[3] ? in[3][c] / detN : 106.0 / 16.0;                     /* :379-394 */
+        double fac_fdet = (1.0 - NC_sdet * CN_det) / (NC_fdet - NC_sdet);           /* :395 */
+        double fac_sdet = (1.0 - NC_fdet * CN_det) / (NC_sdet - NC_fdet);           /* :396 */
+        double din = in[8] ? in[8][c] : 0.0;
+        csurf[c + n2 * 0] = fac_fdet * detN;                                        /* :400 */
+        csurf[c + n2 * 1] = fac_sdet * detN;                                        /* :403 */
+        csurf[c + n2 * 2] = in[4] ? in[4][c] : 1.0 / 16.0 * detN;                   /* :416-420 */
+        csurf[c + n2 * 3] = in[9] ? in[9][c] : 1.0 / 16.0 * din;                    /* :466-480 */
+        csurf[c + n2 * 4] = in[6] ? in[6][c] : 0.5 * din;                           /* :455-459 */
+        csurf[c + n2 * 5] = in[7] ? in[7][c] : 0.5 * din;                           /* :446-450 */
+        csurf[c + n2 * 6] = fmax(0.0, o2);                                          /* :346 */
+        csurf[c + n2 * 7] = fmax(0.0, -o2);                                         /* :347 */
+        wz[c + n2 * 0] = sinking_factor * vN;                                       /* :406 */
+        wz[c + n2 * 1] = sinking_factor * vN;                                       /* :408 */
+        wz[c + n2 * 2] = sinking_factor * (in[5] ? in[5][c] : vN);                  /* :427-431 */
+    }
+}
+
+/* benthic_pelagic_coupler Run, src/mediators/benthic_pelagic_coupler.F90:211-282.
+ * up(n2,8) = <var>_upward_flux_at_soil_surface; out(n2,8): nitrate ammonium DIN DIP detN detC detP oxygen */
+void osed_benthic_pelagic_coupler(size_t n2, const double *up, double dinflux_const, double dipflux_const,
+                                  double convertN, double NC_fdet, double NC_sdet, double *out)
+{
+    if (dipflux_const < 0.0) dipflux_const = dinflux_const / 16.0;
+    for (size_t c = 0; c < n2; ++c) {
+        const double ldetC = up[c], sdetC = up[c + n2], detP = up[c + n2 * 2], po4 = up[c + n2 * 3];
+        const double no3 = up[c + n2 * 4], nh3 = up[c + n2 * 5], oxy = up[c + n2 * 6], odu = up[c + n2 * 7];
+        out[c + n2 * 0] = convertN * (no3 + dinflux_const / 86400. / 365.);         /* :220 */
+        out[c + n2 * 1] = convertN * nh3;                                           /* :222 */
+        out[c + n2 * 2] = (no3 + nh3) + dinflux_const / (86400.0 * 365.0);          /* :232-234 */
+        out[c + n2 * 3] = po4 + dipflux_const / (86400.0 * 365.0);                  /* :245 */
+        out[c + n2 * 4] = convertN * (NC_fdet * ldetC + NC_sdet * sdetC);           /* :258 */
+        out[c + n2 * 5] = ldetC + sdetC;                                            /* :264 */
+        out[c + n2 * 6] = detP;                                                     /* :274 */
+        out[c + n2 * 7] = oxy - odu;                                                /* :281 */
+    }
+}

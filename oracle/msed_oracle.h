@@ -21,6 +21,8 @@
 #ifndef MSED_ORACLE_H
 #define MSED_ORACLE_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -144,6 +146,11 @@ double osed_bench_tiled(int inum, int jnum, int knum, double dzmin, const osed_s
                         const double *bdys, const double *fluxes_in, double dt, int method,
                         int nsteps, double dt_min, double relative_change_min,
                         int bcup_dissolved, int nthreads, long *subcycles);
+
+/* pelagic <-> soil couplers (src/mediators/pelagic_benthic_coupler.F90, benthic_pelagic_coupler.F90) */
+void osed_pelagic_benthic_coupler(size_t n2, const double *const in[10], double *csurf, double *wz);
+void osed_benthic_pelagic_coupler(size_t n2, const double *up, double dinflux_const, double dipflux_const,
+                                  double convertN, double NC_fdet, double NC_sdet, double *out);
 
 /* ---- flat handle API for the Python test harness (oracle/msed_oracle.py) ------------------- */
 enum { OSEDPY_CONC = 0, OSEDPY_BDYS, OSEDPY_FLUXES, OSEDPY_POROSITY, OSEDPY_INTF_POROSITY,

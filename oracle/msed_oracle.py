@@ -90,6 +90,9 @@ def load(fast: bool = False):
                                      C.POINTER(OmexdiaParams), C.POINTER(C.c_int), dp, dp, dp,
                                      C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                      C.c_int, C.POINTER(C.c_long)]
+    lib.osed_pelagic_benthic_coupler.argtypes = [C.c_size_t, C.POINTER(dp), dp, dp]
+    lib.osed_benthic_pelagic_coupler.argtypes = [C.c_size_t, dp, C.c_double, C.c_double, C.c_double,
+                                                 C.c_double, C.c_double, dp]
     _libs[key] = lib
     return lib
 
@@ -315,3 +318,35 @@ def bench_tiled(cfg, mask2d, conc, bdys, fluxes, dt, method, nsteps, nthreads, n
                                 cfg.dt_min, cfg.relative_change_min, cfg.bcup_dissolved_variables,
                                 int(nthreads), C.byref(sub))
     return secs, sub.value, conc
+
+
+P2B_FIELDS = ("oxygen", "detN", "detN_z_velocity", "detC", "detP", "detP_z_velocity", "nitrate", "ammonium",
+              "DIN", "DIP")
+B2P_FIELDS = ("nitrate", "ammonium", "DIN", "DIP", "detN", "detC", "detP", "oxygen")
+
+
+def pelagic_benthic_coupler(shape2d, **fields):
+    """Restated pelagic_benthic_coupler Run: returns (csurf list of 8, wz list of 3 + 5 None)."""
+    dp = C.POINTER(C.c_double)
+    n2 = int(np.prod(shape2d))
+    arr, keep = (dp * 10)(), []
+    for i, name in enumerate(P2B_FIELDS):
+        a = fields.get(name)
+        if a is not None:
+            a = np.asfortranarray(np.asarray(a, dtype=np.float64))
+            keep.append(a)
+            arr[i] = _p(a)
+    cs = np.zeros(tuple(shape2d) + (8,), order="F")
+    wz = np.zeros(tuple(shape2d) + (3,), order="F")
+    load().osed_pelagic_benthic_coupler(n2, arr, _p(cs), _p(wz))
+    return [cs[..., n] for n in range(8)], [wz[..., n] for n in range(3)] + [None] * 5
+
+
+def benthic_pelagic_coupler(up, dinflux_const=0.0, dipflux_const=-1.0, convertN=1.0, NC_fdet=0.20,
+                            NC_sdet=0.04):
+    up = np.asfortranarray(np.asarray(up, dtype=np.float64))
+    n2 = int(np.prod(up.shape[:-1]))
+    out = np.zeros(up.shape[:-1] + (8,), order="F")
+    load().osed_benthic_pelagic_coupler(n2, _p(up), dinflux_const, dipflux_const, convertN, NC_fdet, NC_sdet,
+                                        _p(out))
+    return {name: out[..., i] for i, name in enumerate(B2P_FIELDS)}

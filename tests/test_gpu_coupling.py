@@ -60,3 +60,37 @@ def test_coupled_run_matches_oracle_sequence(gpu, oracle, bcup):
     # exchange actually happened: oxygen is drawn down, particulates are lost to the bed
     assert np.all(got_pel[wet & (height > 0)][:, 6] < conc[wet & (height > 0)][:, 6])
     assert np.all(got_pel[wet & (height > 0)][:, 0] < conc[wet & (height > 0)][:, 0])
+
+
+@pytest.mark.parametrize("full", [True, False])
+def test_pelagic_soil_couplers(gpu, oracle, full):
+    """pelagic_benthic_coupler fused with get_boundary_conditions, and benthic_pelagic_coupler
+    (src/mediators/pelagic_benthic_coupler.F90:281-492, benthic_pelagic_coupler.F90:188-287)."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    case = make_case("cpl", 9, 7, 15, 0.004, seed=66)
+    rng = np.random.default_rng(3)
+    sh = (9, 7)
+    f = dict(temperature=4 + 8 * rng.random(sh), oxygen=250 * (rng.random(sh) - 0.2),
+             detN=2 + rng.random(sh), detN_z_velocity=-1e-5 * (1 + rng.random(sh)), DIN=10 + 5 * rng.random(sh))
+    if full:
+        f.update(detC=(6 + 2 * rng.random(sh)) * f["detN"], detP=0.1 + 0.1 * rng.random(sh),
+                 detP_z_velocity=-2e-5 * (1 + rng.random(sh)), nitrate=8 + rng.random(sh),
+                 ammonium=3 + rng.random(sh), DIP=0.5 + rng.random(sh))
+    cfg = default_config(inum=9, jnum=7, knum=15, dzmin=0.004, dt_min=1.0)
+    with SedimentDriver(cfg) as sed:
+        sed.init_concentrations()
+        sed.pelagic_benthic_coupler(**f)
+        ref = oracle.OracleSediment.from_config(cfg)
+        ref.init_concentrations()
+        cs, wz = oracle.pelagic_benthic_coupler(sh, **{k: v for k, v in f.items() if k != "temperature"})
+        ref.get_boundary_conditions(f["temperature"], cs, wz)
+        assert np.array_equal(sed.bdys, ref.bdys)            # same IEEE operation sequence
+        assert np.array_equal(sed.fluxes, ref.fluxes)
+        assert np.all(sed.bdys[:, :, 7] >= 0) and np.all(sed.bdys[:, :, 8] >= 0)
+        assert np.any(sed.bdys[:, :, 8] > 0)                  # negative oxygen became reduced substances
+        assert sed.run(360.0, 2, 3600.0) == 0 and ref.step(360.0, 2, 10) == 0
+        got = sed.benthic_pelagic_coupler(want=oracle.B2P_FIELDS, dinflux_const=0.3, convertN=1.0 if full else 2.0)
+        want = oracle.benthic_pelagic_coupler(-sed.fluxes, dinflux_const=0.3, convertN=1.0 if full else 2.0)
+        for k in oracle.B2P_FIELDS:
+            assert np.array_equal(got[k], want[k]), k
+        assert scaled_err(sed.fluxes, ref.fluxes) <= 1e-10
