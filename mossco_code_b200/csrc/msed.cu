@@ -73,6 +73,7 @@ struct msed_handle {
     double *minloc_val = nullptr;
     long long *minloc_idx = nullptr;
     int cur = 0;
+    int por_mode = 1;           // how the column kernel obtains porosity (see KParams::por_mode)
     std::vector<double> zi, zc, dz, dzc, bf, por_profile, cumdepth;
     double bioturbation_eff = 0.0;  // sed%bioturbation (profile 3 overwrites it with 1, driver :623)
     double last_min_dt = (double)1.e20f;  // solver_library.F90:44 (default-real literal)
@@ -147,6 +148,7 @@ void fill_params(const msed_handle *h, KParams &p)
     p.bcup_part = c.distributed_pom_flux ? 4 : 1;  // driver :239-243
     p.profile = c.bioturbation_profile;
     p.use_ctl = 1;
+    p.por_mode = h->por_mode;
     p.dt = 0.0;
     p.fac = 1.0 + c.relative_change_min;           // solver_library.F90:121
     p.bioturbation = h->bioturbation_eff;
@@ -185,6 +187,8 @@ void fill_params(const msed_handle *h, KParams &p)
         p.bf[k] = h->bf[k];
         p.e1[k] = std::exp(h->zc[k] * 100.0 * c.bioturb_k_l);  // driver :639
         p.e2[k] = std::exp(h->zc[k] * 200.0 * c.bioturb_k_l);  // driver :640
+        p.portab[k] = (h->por_mode == 2) ? 1.0 - c.porosity_fac * (h->zc[k] - h->zc[0])  // driver :411-412
+                                         : h->por_profile[k];                                // driver :280
     }
 }
 
@@ -596,6 +600,7 @@ int msed_set_porosity(msed_handle *h, const double *porosity3d)
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc = upload_rows(h, h->por, porosity3d, h->K);
     if (rc) return rc;
+    h->por_mode = 0;  // arbitrary field: stream it
     apply_mask_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->por, h->buf[0], h->buf[1], h->mask, h->ld,
                                                                h->ncol, h->K);
     CUDA_TRY(h, cudaGetLastError());
@@ -613,6 +618,7 @@ int msed_update_porosity_from_surface(msed_handle *h, const double *porosity_sur
                                 cudaMemcpyHostToDevice, h->stream));
     porosity_from_surface_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
         h->por, h->scratch, h->mask, h->ld, h->ncol, h->K, h->cfg.porosity_fac, h->tables);
+    h->por_mode = 2;  // porosity(:,:,k) = porosity(:,:,1) * (1 - porosity_fac*(zc(k)-zc(1)))
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return MSED_OK;

@@ -210,7 +210,7 @@ column_kernel(const __grid_constant__ KParams p)
                 cp_async8(sa + n * ROW_BYTES, g);
                 g += plane;
             }
-            cp_async8(sa + NV * ROW_BYTES, g_por);
+            if (p.por_mode == 0) cp_async8(sa + NV * ROW_BYTES, g_por);
             g_in += ld;
             g_por += ld;
         }
@@ -219,6 +219,15 @@ column_kernel(const __grid_constant__ KParams p)
     };
 #pragma unroll
     for (int s = 0; s < RING_STAGES - 1; ++s) fetch_next();
+
+    // porosity of layer kk: the 3-D field (mode 0, streamed through the ring), the uniform profile
+    // of initialize (mode 1, driver :280) or surface value x depth profile (mode 2, driver :411-412) --
+    // the last two reproduce the stored field bit for bit and save its 8 B/cell-update of HBM traffic
+    const double por_surf = (p.por_mode == 2) ? ld_ro(por) : 1.0;
+    auto por_at = [&](int kk, uint32_t slot) -> double {
+        if (p.por_mode == 0) return lds64(slot + NV * ROW_BYTES);
+        return (p.por_mode == 1) ? p.portab[kk] : __dmul_rn(por_surf, p.portab[kk]);
+    };
 
     // ---- per-column constants -----------------------------------------------------------
     const double temp = ld_ro(p.bdys + col);  // temp3d(:,:,k) = bdys(:,:,1), driver :602
@@ -250,7 +259,7 @@ column_kernel(const __grid_constant__ KParams p)
     bool casc[NPART];
     double cap_prev = 0.0;
     {
-        const double por0 = lds64(sbase + NV * ROW_BYTES);
+        const double por0 = por_at(0, sbase);
         double bf0 = p.bf[0];
         if (PROFILE3) bf0 = bf3_cell(p, 0, wtoc_cell(p, por0, poc[0], poc[plane]), avg_wt);
         const double Dp = cpart * (1.0 - por0) * bf0;  // intf_porosity(:,:,1) = porosity(:,:,1), :434
@@ -300,7 +309,7 @@ column_kernel(const __grid_constant__ KParams p)
         double cc[NV];
 #pragma unroll
         for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
-        const double porc = lds64(sc + NV * ROW_BYTES);
+        const double porc = por_at(k, sc);
 
         double basev[NV], a1[NV], a2[NV];
         if (T::reads_base) {
@@ -322,7 +331,7 @@ column_kernel(const __grid_constant__ KParams p)
         // flux through the lower interface (diff3d :776-778; BcDown = 3, :590,:813)
         double Fn[NV];
         if (has_next) {
-            const double porn = lds64(sn + NV * ROW_BYTES);
+            const double porn = por_at(k + 1, sn);
             const double intf = 0.5 * (porc + porn);  // :435
             double bfk = p.bf[k + 1];
             if (PROFILE3)

@@ -72,13 +72,14 @@ struct KParams {
     int i_offset, j_offset;
     int bcup_diss, bcup_part, profile;
     int use_ctl;             // 0: OP_RHS / plain launch with p.dt and buffer 0
+    int por_mode;            // 0: 3-D porosity field, 1: portab[k], 2: por(:,:,1)*portab[k]
     double dt;
     double fac;              // 1 + relative_change_min
     double bioturbation, diffusivity;
     double pom_flux_rate;    // pom_flux_max/86400
     double beta, b, L1, L2, poc_factor[2], cumdepth_last;
     OmexDev om;
-    double dz[MAXK], rdzc[MAXK], bf[MAXK], e1[MAXK], e2[MAXK];
+    double dz[MAXK], rdzc[MAXK], bf[MAXK], e1[MAXK], e2[MAXK], portab[MAXK];
 };
 
 // loaders, reaction term and the fused column kernel
