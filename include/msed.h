@@ -176,6 +176,17 @@ int msed_step(msed_handle *h, double dt, int method, int64_t nsteps, msed_step_i
 /* the whole `do while (.not.stopTime)` loop (component :1700-1769): steps of dt until
  * run_seconds are covered, the last one shortened (:1705-1708) */
 int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_step_info *info);
+/* One whole Run of the component with HOST import/export buffers, component :1493-1829:
+ * get_boundary_conditions(import fields) -> the step loop of msed_run -> upward_fluxes(inum,jnum,nvar)
+ * = -fluxes (:1819).  Same results as msed_get_boundary_conditions + msed_run +
+ * msed_get_upward_fluxes, but the tile is processed in column chunks for the first and the last
+ * attempt so the PCIe transfers overlap the kernels (falls back to the plain sequence for RK methods,
+ * small tiles, or when an attempt was rejected). */
+int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
+                      const double *temperature2d, const double *const *csurf, const double *const *wz,
+                      double *upward_fluxes, msed_step_info *info);
+/* number of column chunks msed_run_exchange uses (0 = choose from the tile size, 1 = no overlap) */
+int msed_set_exchange_chunks(msed_handle *h, int nchunks);
 /* 1-D pre-simulation (component :557-632) for the handle's configuration; conc1d(1,1,knum,nvar) out.
  * bdys1d(nvar+1), fluxes1d(nvar). Runs a 1x1 tile on the same device. */
 int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const double *fluxes1d,

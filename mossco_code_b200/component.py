@@ -216,18 +216,21 @@ class FabmSedimentComponent:
         cs = [self._lookup(import_state, v, "_at_soil_surface") for v in VARIABLE_NAMES]
         wz = [self._lookup(import_state, v, "_z_velocity_at_soil_surface") if PARTICULATE[n] else None
               for n, v in enumerate(VARIABLE_NAMES)]
-        sed.get_boundary_conditions(temp, cs, wz)            # :1665
-        rc = sed.run(float(r["dt"]), int(r["ode_method"]), float(run_seconds))   # :1700-1769
+        # get_boundary_conditions (:1665) + the step loop (:1700-1769) + the flux export (:1819) in
+        # one C-ABI call, so the library can overlap the PCIe transfers with the first/last attempt
+        rc, up = sed.run_exchange(float(r["dt"]), int(r["ode_method"]), float(run_seconds), temp, cs, wz,
+                                  out=self.flux_buffer)
         self.last_info = sed.info
         self.clock_seconds += float(run_seconds)
         if rc == _abi.NAN_DETECTED:                          # :1718-1723
             raise ComponentError(ESMF_RC_VAL_OUTOFRANGE, "NaN detected applying ode_solver")
-        self._fill_exports(export_state, with_3d=self.export_3d_every_run)       # :1773-1822
+        self._fill_exports(export_state, with_3d=self.export_3d_every_run, up=up)   # :1773-1822
         return ESMF_SUCCESS
 
-    def _fill_exports(self, export_state: State, with_3d: bool):
+    def _fill_exports(self, export_state: State, with_3d: bool, up=None):
         sed = self.sed
-        up = sed.upward_fluxes(self.flux_buffer)
+        if up is None:
+            up = sed.upward_fluxes(self.flux_buffer)
         for n, v in enumerate(VARIABLE_NAMES):
             export_state[f"{v}_upward_flux_at_soil_surface"] = up[:, :, n]
         if not with_3d:

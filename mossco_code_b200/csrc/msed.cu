@@ -6,6 +6,7 @@
 // array work.  There is no CPU compute path in this file.
 #include "msed_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -79,6 +80,9 @@ struct msed_handle {
     double last_min_dt = (double)1.e20f;  // solver_library.F90:44 (default-real literal)
     int last_min_dt_grid_cell[4] = {-99, -99, -99, -99};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;           // PCIe traffic of msed_run_exchange
+    cudaEvent_t ev_pool[2 * 16] = {};             // per-chunk H2D-done / compute-done events
+    int exchange_chunks = 0;                      // 0 = choose from the tile size
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     msed_allreduce_hook hook = nullptr;
@@ -140,6 +144,8 @@ void fill_params(const msed_handle *h, KParams &p)
     p.ctl = h->ctl;
     p.ld = h->ld;
     p.ncol = h->ncol;
+    p.col0 = 0;
+    p.col_end = h->ncol;
     p.K = h->K;
     p.inum = c.inum;
     p.i_offset = c.i_offset;
@@ -195,7 +201,7 @@ void fill_params(const msed_handle *h, KParams &p)
 template <int MODEL, bool P3>
 cudaError_t launch_op(int op, const KParams &p, cudaStream_t s)
 {
-    const dim3 grid(nblocks(p.ncol, COL_BLOCK)), block(COL_BLOCK);
+    const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
     switch (op) {
 #define MSED_CASE(OPV) \
     case OPV: column_kernel<MODEL, OPV, P3><<<grid, block, COLUMN_SMEM_BYTES, s>>>(p); break;
@@ -270,8 +276,22 @@ int reduce_flags(msed_handle *h)
     return MSED_OK;
 }
 
-// the step loop shared by msed_ode_solver / msed_step / msed_run
-int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrapper, msed_step_info *info)
+// msed_run_exchange: the tile is cut into column chunks so that the H2D of the import fields overlaps
+// the first attempt and the D2H of the bed fluxes overlaps the last one
+struct ExchangePlan {
+    int nchunks = 0;
+    int c0[16], c1[16];
+    BcPtrs bc;                 // device staging rows of the import fields
+    bool first = false;        // chunk the first attempt: wait for chunk H2D, assemble boundary, compute
+    bool last = false;         // chunk the last attempt: export each chunk as soon as it is computed
+    double *neg = nullptr;     // device rows [nvar][ld] receiving -fluxes
+    double *host_out = nullptr;
+    bool export_done = false;  // out: host_out holds the final upward fluxes
+};
+
+// the step loop shared by msed_ode_solver / msed_step / msed_run / msed_run_exchange
+int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrapper, msed_step_info *info,
+              ExchangePlan *plan = nullptr)
 {
     if (nsteps < 0) return fail(h, MSED_ERR_ARG, "nsteps < 0");
     if (method < 0 || method > 3) return fail(h, MSED_ERR_ARG, "unknown ode_method");
@@ -308,13 +328,49 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     long long launches = 0;
 
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    long long remaining = nsteps;
+    long long remaining = nsteps, issued = 0;
     const long long max_batch = 256;
     int guard = 0;
     while (remaining > 0) {
         const long long batch = remaining < max_batch ? remaining : max_batch;
-        for (long long s = 0; s < batch; ++s) {
-            if (method == MSED_EULER) {
+        for (long long s = 0; s < batch; ++s, ++issued) {
+            const bool chunk_first = plan && plan->first && issued == 0;
+            const bool chunk_last = plan && plan->last && issued == nsteps - 1;
+            if ((chunk_first || chunk_last) && (method == MSED_EULER || method == MSED_ADAPTIVE_EULER)) {
+                for (int c = 0; c < plan->nchunks; ++c) {
+                    const int c0 = plan->c0[c], c1 = plan->c1[c];
+                    if (chunk_first) {  // get_boundary_conditions of this chunk as soon as its fields landed
+                        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_pool[c], 0));
+                        BcPtrs bc = plan->bc;
+                        if (bc.temperature) bc.temperature += c0;
+                        for (int n = 0; n < NV; ++n) {
+                            if (bc.csurf[n]) bc.csurf[n] += c0;
+                            if (bc.wz[n]) bc.wz[n] += c0;
+                        }
+                        boundary_kernel<<<nblocks(c1 - c0), 256, 0, h->stream>>>(
+                            h->bdys + c0, h->fluxes + c0, h->buf[h->cur] + c0, h->por + c0, bc, h->ld, h->ld,
+                            c1 - c0, h->K, h->cfg.bcup_dissolved_variables, h->bioturbation_eff,
+                            h->cfg.diffusivity, h->dz[0]);
+                        launches += 1;
+                    }
+                    KParams pc = p;
+                    pc.col0 = c0;
+                    pc.col_end = c1;
+                    CUDA_TRY(h, launch_column(h, method == MSED_EULER ? OP_EULER : OP_ADAPTIVE, pc));
+                    launches += 1;
+                    if (chunk_last) {  // export this chunk while the next ones are still being computed
+                        CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], h->stream));
+                        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pool[16 + c], 0));
+                        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->copy_stream>>>(
+                            plan->neg + c0, h->fluxes + c0, h->ld, c1 - c0, NV);
+                        launches += 1;
+                        CUDA_TRY(h, cudaMemcpy2DAsync(plan->host_out + c0, (size_t)h->ncol * sizeof(double),
+                                                      plan->neg + c0, h->ld * sizeof(double),
+                                                      (size_t)(c1 - c0) * sizeof(double), NV,
+                                                      cudaMemcpyDeviceToHost, h->copy_stream));
+                    }
+                }
+            } else if (method == MSED_EULER) {
                 CUDA_TRY(h, launch_column(h, OP_EULER, p));
                 launches += 1;
             } else if (method == MSED_ADAPTIVE_EULER) {
@@ -359,6 +415,11 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     }
 
     const Ctl &r = *h->ctl_host;
+    if (plan && plan->last) {  // the chunked export is final only if no attempt was rejected
+        CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+        plan->export_done = (method == MSED_EULER || method == MSED_ADAPTIVE_EULER) && !r.stop &&
+                            r.subcycles == 0 && r.steps_done == nsteps && nsteps > 0;
+    }
     h->cur = r.cur;
     if (diag && r.last_min_dt < h->last_min_dt) {
         long long idx = -1;
@@ -517,6 +578,8 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     CREATE_TRY(cudaSetDevice(h->device));
     CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev_pool) CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreate(&h->ev0));
     CREATE_TRY(cudaEventCreate(&h->ev1));
     const size_t state_bytes = (size_t)NV * K * h->ld * sizeof(double);
@@ -563,6 +626,8 @@ int msed_destroy(msed_handle *h)
     cudaFree(h->scratch); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->ctl);
     cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->pel);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
+    for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -886,6 +951,114 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
     std::memset(&b, 0, sizeof(b));
     int rc = run_steps(h, dt, method, nfull, true, &a);
     if (rc == MSED_OK && rem > 0.0) rc = run_steps(h, rem, method, 1, true, &b);
+    if (info) {
+        *info = a;
+        if (rem > 0.0) {
+            info->steps_done += b.steps_done;
+            info->rhs_evaluations += b.rhs_evaluations;
+            info->subcycle_warnings += b.subcycle_warnings;
+            info->last_min_dt = b.last_min_dt;
+            for (int q = 0; q < 4; ++q) info->last_min_dt_grid_cell[q] = b.last_min_dt_grid_cell[q];
+            info->nan_detected |= b.nan_detected;
+            info->kernel_ms += b.kernel_ms;
+            info->kernel_launches += b.kernel_launches;
+        }
+    }
+    return rc;
+}
+
+int msed_set_exchange_chunks(msed_handle *h, int nchunks)
+{
+    if (!h || nchunks < 0 || nchunks > 16) return fail(h, MSED_ERR_ARG, "nchunks must be in [0,16]");
+    h->exchange_chunks = nchunks;
+    return MSED_OK;
+}
+
+int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds, const double *temperature2d,
+                      const double *const *csurf, const double *const *wz, double *upward_fluxes,
+                      msed_step_info *info)
+{
+    if (!h || !upward_fluxes) return fail(h, MSED_ERR_ARG, "null argument");
+    if (!(dt > 0.0) || run_seconds < 0.0) return fail(h, MSED_ERR_ARG, "dt <= 0 or run_seconds < 0");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    long long nfull = (long long)std::floor(run_seconds / dt * (1.0 + 1e-14));
+    double rem = run_seconds - (double)nfull * dt;
+    if (rem < 1e-9 * dt) rem = 0.0;
+    int nchunks = h->exchange_chunks;
+    if (nchunks == 0) nchunks = h->ncol >= (1 << 20) ? 8 : (h->ncol >= (1 << 17) ? 4 : 1);
+    const bool pipelined = nchunks > 1 && (method == MSED_EULER || method == MSED_ADAPTIVE_EULER) &&
+                           !h->cfg.adaptive_solver_diagnostics && (nfull + (rem > 0.0 ? 1 : 0)) > 0 &&
+                           (size_t)NV * h->K >= 12 + NV;
+    int rc;
+    if (!pipelined) {  // plain sequence: boundary, loop, export
+        if ((rc = msed_get_boundary_conditions(h, temperature2d, csurf, wz))) return rc;
+        rc = msed_run(h, dt, method, run_seconds, info);
+        if (rc < 0) return rc;
+        const int rc2 = msed_get_upward_fluxes(h, upward_fluxes);
+        return rc2 ? rc2 : rc;
+    }
+    if ((rc = ensure_scratch(h))) return rc;
+    ExchangePlan plan;
+    std::memset(&plan.bc, 0, sizeof(plan.bc));
+    plan.nchunks = nchunks;
+    const int per = ((h->ncol + nchunks - 1) / nchunks + COL_BLOCK - 1) / COL_BLOCK * COL_BLOCK;
+    int used = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int c0 = c * per, c1 = std::min(h->ncol, (c + 1) * per);
+        if (c0 >= c1) break;
+        plan.c0[used] = c0;
+        plan.c1[used] = c1;
+        ++used;
+    }
+    plan.nchunks = used;
+    // staging rows: [0..11] import fields, [12..19] negated fluxes
+    double *stage = h->scratch;
+    const double *host[12];
+    const double **dev[12];
+    int nf = 0;
+    if (temperature2d) { host[nf] = temperature2d; dev[nf] = &plan.bc.temperature; ++nf; }
+    for (int n = 0; n < NV; ++n) {
+        if (!csurf || !csurf[n]) continue;
+        if (n < NPART) {
+            if (!wz || !wz[n]) return fail(h, MSED_ERR_ARG, "particulate variable without z_velocity field");
+            host[nf] = wz[n]; dev[nf] = &plan.bc.wz[n]; ++nf;
+        }
+        host[nf] = csurf[n]; dev[nf] = &plan.bc.csurf[n]; ++nf;
+    }
+    for (int f = 0; f < nf; ++f) *dev[f] = stage + (size_t)f * h->ld;
+    plan.neg = stage + (size_t)12 * h->ld;
+    plan.host_out = upward_fluxes;
+    for (int c = 0; c < plan.nchunks; ++c) {  // all H2D traffic on the copy stream, chunk by chunk
+        const int c0 = plan.c0[c], n = plan.c1[c] - plan.c0[c];
+        for (int f = 0; f < nf; ++f)
+            CUDA_TRY(h, cudaMemcpyAsync(stage + (size_t)f * h->ld + c0, host[f] + c0, (size_t)n * sizeof(double),
+                                        cudaMemcpyHostToDevice, h->copy_stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_pool[c], h->copy_stream));
+    }
+    msed_step_info a, b;
+    std::memset(&a, 0, sizeof(a));
+    std::memset(&b, 0, sizeof(b));
+    bool exported = false;
+    rc = MSED_OK;
+    if (nfull > 0) {
+        plan.first = true;
+        plan.last = (rem == 0.0);
+        rc = run_steps(h, dt, method, nfull, true, &a, &plan);
+        exported = plan.export_done;
+    }
+    if (rc == MSED_OK && rem > 0.0) {
+        plan.first = (nfull == 0);
+        plan.last = true;
+        plan.export_done = false;
+        rc = run_steps(h, rem, method, 1, true, &b, &plan);
+        exported = plan.export_done;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    if (rc < 0) return rc;
+    if (!exported) {  // an attempt was rejected (or NaN): export again from the final state
+        const int rc2 = msed_get_upward_fluxes(h, upward_fluxes);
+        if (rc2) return rc2;
+    }
     if (info) {
         *info = a;
         if (rem > 0.0) {

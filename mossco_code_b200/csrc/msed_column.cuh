@@ -157,8 +157,8 @@ column_kernel(const __grid_constant__ KParams p)
             dt = ctl->dt;
         }
     }
-    const int col = blockIdx.x * COL_BLOCK + threadIdx.x;
-    if (col >= p.ncol) return;
+    const int col = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
+    if (col >= p.col_end) return;
 
     const int K = p.K;
     const size_t ld = p.ld;

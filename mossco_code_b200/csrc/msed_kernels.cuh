@@ -69,6 +69,7 @@ struct KParams {
     Ctl *ctl;
     size_t ld;
     int ncol, K, inum;
+    int col0, col_end;       // column range [col0, col_end) of this launch (chunked launches overlap PCIe)
     int i_offset, j_offset;
     int bcup_diss, bcup_part, profile;
     int use_ctl;             // 0: OP_RHS / plain launch with p.dt and buffer 0

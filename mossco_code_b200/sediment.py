@@ -234,6 +234,33 @@ class SedimentDriver:
         return self._check(self._lib.msed_run(self._h, float(dt), int(method), float(run_seconds),
                                               C.byref(self.info)), allow=(_abi.NAN_DETECTED,))
 
+    def run_exchange(self, dt: float, method: int, run_seconds: float, temperature=None, csurf=None,
+                     wz=None, out: Optional[np.ndarray] = None):
+        """One component Run with host buffers (component :1493-1829): boundary assembly from the import
+        fields, the step loop, and the upward bed fluxes into ``out`` -- PCIe transfers overlapped with
+        the first and last attempt.  Returns (rc, upward_fluxes)."""
+        keep = []
+        t = None if temperature is None else _f64(temperature, self.shape2d, "temperature")
+        cs = (C.POINTER(C.c_double) * NVAR)()
+        ws = (C.POINTER(C.c_double) * NVAR)()
+        for n in range(NVAR):
+            for arr, src in ((cs, csurf), (ws, wz)):
+                if src is not None and src[n] is not None:
+                    a = _f64(src[n], self.shape2d, "import field")
+                    keep.append(a)
+                    arr[n] = _ptr(a)
+        if out is None:
+            out = np.zeros(self.shape2d + (self.nvar,), order="F")
+        elif out.shape != self.shape2d + (self.nvar,) or not out.flags.f_contiguous or out.dtype != np.float64:
+            raise ValueError("run_exchange: out must be fp64, Fortran order, shape (inum,jnum,nvar)")
+        rc = self._check(self._lib.msed_run_exchange(self._h, float(dt), int(method), float(run_seconds),
+                                                     _ptr(t), cs, ws, _ptr(out), C.byref(self.info)),
+                         allow=(_abi.NAN_DETECTED,))
+        return rc, out
+
+    def set_exchange_chunks(self, nchunks: int):
+        self._check(self._lib.msed_set_exchange_chunks(self._h, int(nchunks)))
+
     # -- benthic-pelagic exchange on device (BASELINE config 5) --------------------------------
     def pelagic_init(self, conc2d, wz2d, layer_height2d, temperature2d):
         c = _f64(conc2d, self.shape2d + (self.nvar,), "pelagic conc")

@@ -94,3 +94,65 @@ def test_pelagic_soil_couplers(gpu, oracle, full):
         for k in oracle.B2P_FIELDS:
             assert np.array_equal(got[k], want[k]), k
         assert scaled_err(sed.fluxes, ref.fluxes) <= 1e-10
+
+
+@pytest.mark.parametrize("nchunks,seconds", [(4, 3600.0), (3, 1000.0), (5, 360.0), (1, 3600.0)])
+def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds):
+    """msed_run_exchange (chunk-pipelined PCIe/compute overlap) must be bit-identical to
+    get_boundary_conditions + run + upward_fluxes, incl. the shortened last step and a single step."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    from mossco_code_b200.sediment import PARTICULATE
+    case = make_case("xchg", 70, 37, 20, 0.003, seed=91, land_fraction=0.25)
+    rng = np.random.default_rng(5)
+    sh = (70, 37)
+    temp = 4 + 8 * rng.random(sh)
+    cs = [np.asfortranarray((-case.fluxes[:, :, n]) if PARTICULATE[n] else case.bdys[:, :, n + 1]) for n in range(8)]
+    wz = [np.ones(sh, order="F") if PARTICULATE[n] else None for n in range(8)]
+    cs[5] = None                                              # ammonium absent from the import state
+    res = []
+    for fused in (False, True):
+        cfg = default_config(inum=70, jnum=37, knum=20, dzmin=0.003, dt_min=1.0)
+        with SedimentDriver(cfg) as sed:
+            sed.set_mask(case.mask)
+            sed.init_concentrations()
+            sed.set_boundary(case.bdys, case.fluxes)
+            for _ in range(2):
+                if fused:
+                    sed.set_exchange_chunks(nchunks)
+                    rc, up = sed.run_exchange(360.0, 2, seconds, temp, cs, wz)
+                else:
+                    sed.get_boundary_conditions(temp, cs, wz)
+                    rc = sed.run(360.0, 2, seconds)
+                    up = sed.upward_fluxes()
+                assert rc == 0
+                steps = sed.info.steps_done
+            res.append((sed.conc, up.copy(), sed.bdys, steps))
+    assert res[0][3] == res[1][3]
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2])
+
+
+def test_run_exchange_with_rejected_attempt(gpu):
+    """If an attempt is rejected the chunk-wise export is stale and must be redone from the final state."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    case = make_case("xrej", 40, 16, 15, 0.004, seed=2)
+    cs = [np.asfortranarray((-case.fluxes[:, :, n]) if n < 3 else case.bdys[:, :, n + 1]) for n in range(8)]
+    wz = [np.ones((40, 16), order="F") if n < 3 else None for n in range(8)]
+    temp = np.asfortranarray(case.bdys[:, :, 0])
+    out = []
+    for fused in (False, True):
+        cfg = default_config(inum=40, jnum=16, knum=15, dzmin=0.004, dt_min=1.0, rnit=2.0e3, rODUox=2.0e3)
+        with SedimentDriver(cfg) as sed:
+            sed.init_concentrations()
+            if fused:
+                sed.set_exchange_chunks(4)
+                rc, up = sed.run_exchange(360.0, 2, 1800.0, temp, cs, wz)
+            else:
+                sed.get_boundary_conditions(temp, cs, wz)
+                rc = sed.run(360.0, 2, 1800.0)
+                up = sed.upward_fluxes()
+            assert rc == 0 and sed.info.subcycle_warnings > 0
+            out.append((sed.conc, up.copy(), sed.info.subcycle_warnings))
+    assert out[0][2] == out[1][2]
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
