@@ -356,9 +356,10 @@ def main():
                        "l2": "per-GPU state >= 5.4 GB >> 126 MB L2 (inputs larger than L2)"
                        if cells_per_launch * 128 > 1e9 else "state fits L2 (launch-latency regime)",
                        "subcycles_in_timed_region": subcycles, "rhs_evaluations": rhs_evals,
-                       "e2e_call": f"Run({int(COUPLING_SECONDS)} s) = H2D 12 import fields + get_boundary_conditions "
-                                   f"+ {steps_per_run} ode_solver steps + D2H 8 upward-flux fields; "
-                                   f"{nruns} timed Run(s); 3-D <name>_in_soil export on demand"},
+                       "e2e_call": f"FabmSedimentComponent.run({int(COUPLING_SECONDS)} s) -> msed_run_exchange: H2D of 12 "
+                                   f"pinned import fields + get_boundary_conditions + {steps_per_run} ode_solver "
+                                   f"steps + D2H of 8 upward-flux fields (transfers chunk-overlapped with the "
+                                   f"first/last attempt); {nruns} timed Run(s); 3-D <name>_in_soil export on demand"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "cell-updates/s",
                     "h2d_bytes_per_step": h2d / steps_per_run, "d2h_bytes_per_step": d2h / steps_per_run,

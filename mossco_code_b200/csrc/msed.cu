@@ -708,19 +708,17 @@ int msed_check_domain(msed_handle *h)
         if (h->dzc[k] <= 0) return fail(h, MSED_BAD_DOMAIN, "sediment central layer difference <= 0");
     for (int k = 0; k < h->K; ++k)
         if (h->dz[k] < h->cfg.dzmin) return fail(h, MSED_BAD_DOMAIN, "sediment layer height < minimum value");
-    // porosity conditions (driver :503-511) need the field
-    std::vector<double> por((size_t)h->K * h->ncol);
-    std::vector<unsigned char> m(h->ld);
-    int rc = download_rows(h, por.data(), h->por, h->K);
-    if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpy(m.data(), h->mask, h->ld, cudaMemcpyDeviceToHost));
-    for (int k = 0; k < h->K; ++k)
-        for (int c = 0; c < h->ncol; ++c) {
-            if (m[c]) continue;
-            const double v = por[(size_t)k * h->ncol + c];
-            if (v <= 0) return fail(h, MSED_BAD_DOMAIN, "sediment porosity <=0");
-            if (v > 1) return fail(h, MSED_BAD_DOMAIN, "sediment porosity > 1");
-        }
+    // porosity conditions (driver :503-511) are checked where the field lives
+    int *dflags = (int *)h->minloc_idx;  // 8 bytes of device scratch: [0] porosity<=0, [1] porosity>1
+    CUDA_TRY(h, cudaMemsetAsync(dflags, 0, 2 * sizeof(int), h->stream));
+    check_porosity_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->por, h->mask, h->ld, h->ncol, h->K, dflags);
+    CUDA_TRY(h, cudaGetLastError());
+    int hflags[2] = {0, 0};
+    CUDA_TRY(h, cudaMemcpyAsync(hflags, dflags, sizeof(hflags), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->minloc_idx, 0xff, sizeof(long long), h->stream));
+    if (hflags[0]) return fail(h, MSED_BAD_DOMAIN, "sediment porosity <=0");
+    if (hflags[1]) return fail(h, MSED_BAD_DOMAIN, "sediment porosity > 1");
     apply_mask_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->por, h->buf[0], h->buf[1], h->mask, h->ld,
                                                                h->ncol, h->K);  // driver :532-541
     CUDA_TRY(h, cudaGetLastError());

@@ -159,6 +159,22 @@ __global__ void porosity_from_surface_kernel(double *por, const double *surf, co
     }
 }
 
+// fabm_sed_check_domain porosity conditions on unmasked cells (driver :503-511)
+__global__ void check_porosity_kernel(const double *por, const unsigned char *mask, size_t ld, int ncol,
+                                      int K, int *flags)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol || mask[col]) return;
+    bool le0 = false, gt1 = false;
+    for (int k = 0; k < K; ++k) {
+        const double v = por[(size_t)k * ld + col];
+        le0 |= (v <= 0.0);
+        gt1 |= (v > 1.0);
+    }
+    if (le0) atomicOr(&flags[0], 1);
+    if (gt1) atomicOr(&flags[1], 1);
+}
+
 // where(mask>0) porosity = 1 ; conc = 1e20  (driver :431,:535,:541)
 __global__ void apply_mask_kernel(double *por, double *b0, double *b1, const unsigned char *mask, size_t ld,
                                   int ncol, int K)

@@ -156,3 +156,23 @@ def test_run_exchange_with_rejected_attempt(gpu):
             out.append((sed.conc, up.copy(), sed.info.subcycle_warnings))
     assert out[0][2] == out[1][2]
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_check_domain_flags_bad_porosity(gpu):
+    """fabm_sed_check_domain 'stop' conditions (driver :503-511) come back as MSED_BAD_DOMAIN."""
+    from mossco_code_b200 import MsedError, SedimentDriver, default_config
+    cfg = default_config(inum=6, jnum=5, knum=12, dzmin=0.004)
+    mask = np.zeros((6, 5), dtype=np.int32); mask[1, 1] = 1
+    for bad, text in ((1.2, "> 1"), (0.0, "<=0")):
+        with SedimentDriver(cfg) as sed:
+            sed.set_mask(mask)
+            assert sed.check_domain() == 0
+            por = sed.field("porosity")
+            por[1, 1, 3] = bad                       # masked column: ignored (and reset to 1)
+            sed.set_porosity(por)
+            assert sed.check_domain() == 0
+            por[4, 2, 7] = bad
+            sed.set_porosity(por)
+            with pytest.raises(MsedError) as e:
+                sed.check_domain()
+            assert e.value.code == 2 and text in str(e.value)
