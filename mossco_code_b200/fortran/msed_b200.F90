@@ -122,6 +122,12 @@ module msed_b200
       import; type(c_ptr), value :: h; real(c_double), value :: dt, run_seconds
       integer(c_int), value :: method; type(msed_step_info), intent(out) :: info
     end function
+    integer(c_int) function msed_run_exchange(h, dt, method, run_seconds, temperature, csurf, wz, &
+        upward, info) bind(c, name='msed_run_exchange')
+      import; type(c_ptr), value :: h, temperature; real(c_double), value :: dt, run_seconds
+      integer(c_int), value :: method; type(c_ptr), intent(in) :: csurf(*), wz(*)
+      real(c_double), intent(out) :: upward(*); type(msed_step_info), intent(out) :: info
+    end function
     integer(c_int) function msed_nccl_unique_id(id) bind(c, name='msed_nccl_unique_id')
       import; character(kind=c_char) :: id(128)
     end function
