@@ -140,7 +140,8 @@ SYMBOLS = {
     "msed_set_allreduce_hook": (C.c_int, [_h, ALLREDUCE_HOOK, C.c_void_p]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmsed_b200.so")
+LIB_PATH = os.environ.get("MSED_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                    "libmsed_b200.so")
 _lib = None
 
 

@@ -128,7 +128,7 @@ template <int OP> struct OpTraits {
 };
 
 constexpr int ROWS = NV + 1;                 // 8 state rows + porosity per layer
-constexpr int RING_STAGES = 4;               // layers resident in the shared-memory ring (power of 2)
+constexpr int RING_STAGES = MSED_RING_STAGES; // layers resident in the shared-memory ring (power of 2)
 constexpr uint32_t ROW_BYTES = COL_BLOCK * 8;
 constexpr uint32_t STAGE_BYTES = ROWS * ROW_BYTES;
 constexpr size_t COLUMN_SMEM_BYTES = (size_t)RING_STAGES * STAGE_BYTES;

@@ -20,8 +20,18 @@ namespace msed {
 constexpr int NV = MSED_NVAR;
 constexpr int MAXK = MSED_MAX_LAYERS;
 constexpr int NPART = 3;  // ldetC, sdetC, detP are particulate (main.F90:92-101)
-constexpr int COL_BLOCK = 128;      // threads (= columns) per CTA of the column kernel
-constexpr int COL_MIN_BLOCKS = 4;   // 4 CTAs/SM -> <=128 registers/thread, 16 warps/SM
+// tunables of the column kernel (overridable with -D for the sweeps in tools/tune_sweep.sh)
+#ifndef MSED_COL_BLOCK
+#define MSED_COL_BLOCK 128
+#endif
+#ifndef MSED_COL_MIN_BLOCKS
+#define MSED_COL_MIN_BLOCKS 4
+#endif
+#ifndef MSED_RING_STAGES
+#define MSED_RING_STAGES 4
+#endif
+constexpr int COL_BLOCK = MSED_COL_BLOCK;            // threads (= columns) per CTA of the column kernel
+constexpr int COL_MIN_BLOCKS = MSED_COL_MIN_BLOCKS;  // 4 CTAs/SM -> <=128 registers/thread, 16 warps/SM
 
 // integrator stage executed by the column kernel
 enum Op : int {
