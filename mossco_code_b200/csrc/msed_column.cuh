@@ -153,6 +153,10 @@ column_kernel(const __grid_constant__ KParams p)
         if (OP == OP_ADAPTIVE) {
             dt = ctl->dt_red;
             final_sub = !(ctl->dt_int + dt < ctl->dt);
+            // An attempt whose violation flag is already up will be rejected for certain when
+            // dt_red > dt_min (solver_library.F90:126) and its output discarded: CTAs that start
+            // after the first violation skip their work, so a rejected attempt costs about one wave.
+            if (dt > ctl->dt_min && *(const volatile int *)&ctl->flags[0]) return;
         } else {
             dt = ctl->dt;
         }

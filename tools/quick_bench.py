@@ -18,10 +18,12 @@ ap.add_argument("--knum", type=int, default=40)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--method", type=int, default=2)
 ap.add_argument("--spin", type=int, default=10)
+ap.add_argument("--perturb", type=float, default=0.1)
+ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 dzmin = 0.0015 if a.knum == 40 else 0.002
 t0 = time.time()
-case = make_case("qb", a.inum, a.jnum, a.knum, dzmin, seed=4096)
+case = make_case("qb", a.inum, a.jnum, a.knum, dzmin, seed=4096, perturb=a.perturb)
 cfg = default_config(inum=a.inum, jnum=a.jnum, knum=a.knum, dzmin=dzmin, dt_min=1.0)
 sed = SedimentDriver(cfg)
 sed.init_concentrations()
@@ -29,7 +31,7 @@ sed.set_boundary(case.bdys, case.fluxes)
 print(f"setup {time.time()-t0:.1f}s")
 sed.step(360.0, a.method, a.spin)
 print("spin: subcycles", sed.info.subcycle_warnings, "rhs evals", sed.info.rhs_evaluations)
-for rep in range(3):
+for rep in range(a.reps):
     sed.step(360.0, a.method, a.steps)
     i = sed.info
     cells = a.inum * a.jnum * a.knum
@@ -37,4 +39,4 @@ for rep in range(3):
     balg = 136.0 + 216.0 / a.knum
     print(f"rep{rep}: {ms:.3f} ms/step  {cells/ms/1e6:.2f} Gcell-updates/s  alg {cells*balg/ms/1e6:.0f} GB/s "
           f"({cells*balg/ms/1e6/6547.2*100:.1f}% of measured HBM) subcycles={i.subcycle_warnings} "
-          f"rhs={i.rhs_evaluations} launches={i.kernel_launches}")
+          f"rhs={i.rhs_evaluations} launches={i.kernel_launches} ms/rhs={i.kernel_ms/max(i.rhs_evaluations,1):.3f}")
