@@ -198,13 +198,13 @@ void fill_params(const msed_handle *h, KParams &p)
     }
 }
 
-template <int MODEL, bool P3>
+template <int MODEL, bool P3, bool SP>
 cudaError_t launch_op(int op, const KParams &p, cudaStream_t s)
 {
     const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
     switch (op) {
 #define MSED_CASE(OPV) \
-    case OPV: column_kernel<MODEL, OPV, P3><<<grid, block, COLUMN_SMEM_BYTES, s>>>(p); break;
+    case OPV: column_kernel<MODEL, OPV, P3, SP><<<grid, block, COLUMN_SMEM_BYTES, s>>>(p); break;
         MSED_CASE(OP_RHS)
         MSED_CASE(OP_EULER)
         MSED_CASE(OP_ADAPTIVE)
@@ -224,17 +224,22 @@ cudaError_t launch_op(int op, const KParams &p, cudaStream_t s)
 
 cudaError_t launch_column(const msed_handle *h, int op, const KParams &p)
 {
+    // the (rare) Zhang & Wirtz path always streams the 3-D porosity field, which is kept current in
+    // every mode; the closed-form porosity variants exist for the hot profile-0/1/2 kernels only
     const bool p3 = h->cfg.bioturbation_profile == 3;
+    const bool sp = p3 || p.por_mode == 0;
     switch (h->cfg.model) {
     case MSED_MODEL_OMEXDIA_P:
-        return p3 ? launch_op<MSED_MODEL_OMEXDIA_P, true>(op, p, h->stream)
-                  : launch_op<MSED_MODEL_OMEXDIA_P, false>(op, p, h->stream);
+        if (p3) return launch_op<MSED_MODEL_OMEXDIA_P, true, true>(op, p, h->stream);
+        return sp ? launch_op<MSED_MODEL_OMEXDIA_P, false, true>(op, p, h->stream)
+                  : launch_op<MSED_MODEL_OMEXDIA_P, false, false>(op, p, h->stream);
     case MSED_MODEL_NONE:
-        return p3 ? launch_op<MSED_MODEL_NONE, true>(op, p, h->stream)
-                  : launch_op<MSED_MODEL_NONE, false>(op, p, h->stream);
+        if (p3) return launch_op<MSED_MODEL_NONE, true, true>(op, p, h->stream);
+        return sp ? launch_op<MSED_MODEL_NONE, false, true>(op, p, h->stream)
+                  : launch_op<MSED_MODEL_NONE, false, false>(op, p, h->stream);
     case MSED_MODEL_TEST_SOLVER:
         if (op != OP_RHS && op != OP_EULER) return cudaErrorInvalidValue;
-        return launch_op<MSED_MODEL_TEST_SOLVER, false>(op, p, h->stream);
+        return launch_op<MSED_MODEL_TEST_SOLVER, false, true>(op, p, h->stream);
     default: return cudaErrorInvalidValue;
     }
 }

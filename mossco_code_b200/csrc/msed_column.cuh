@@ -136,7 +136,9 @@ constexpr size_t COLUMN_SMEM_BYTES = (size_t)RING_STAGES * STAGE_BYTES;
 // ---------------------------------------------------------------------------------------------
 // the column kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODEL, int OP, bool PROFILE3>
+// STREAM_POR: porosity is an arbitrary 3-D field streamed through the ring (KParams::por_mode 0);
+// otherwise it is por_surf * portab[k] (modes 1 and 2, see below), which costs no HBM traffic.
+template <int MODEL, int OP, bool PROFILE3, bool STREAM_POR>
 __global__ void __launch_bounds__(COL_BLOCK, COL_MIN_BLOCKS)
 column_kernel(const __grid_constant__ KParams p)
 {
@@ -214,7 +216,7 @@ column_kernel(const __grid_constant__ KParams p)
                 cp_async8(sa + n * ROW_BYTES, g);
                 g += plane;
             }
-            if (p.por_mode == 0) cp_async8(sa + NV * ROW_BYTES, g_por);
+            if (STREAM_POR) cp_async8(sa + NV * ROW_BYTES, g_por);
             g_in += ld;
             g_por += ld;
         }
@@ -227,10 +229,11 @@ column_kernel(const __grid_constant__ KParams p)
     // porosity of layer kk: the 3-D field (mode 0, streamed through the ring), the uniform profile
     // of initialize (mode 1, driver :280) or surface value x depth profile (mode 2, driver :411-412) --
     // the last two reproduce the stored field bit for bit and save its 8 B/cell-update of HBM traffic
-    const double por_surf = (p.por_mode == 2) ? ld_ro(por) : 1.0;
+    // (mode 1 is mode 2 with a surface factor of exactly 1.0: x*1.0 is exact)
+    const double por_surf = (!STREAM_POR && p.por_mode == 2) ? ld_ro(por) : 1.0;
     auto por_at = [&](int kk, uint32_t slot) -> double {
-        if (p.por_mode == 0) return lds64(slot + NV * ROW_BYTES);
-        return (p.por_mode == 1) ? p.portab[kk] : __dmul_rn(por_surf, p.portab[kk]);
+        if (STREAM_POR) return lds64(slot + NV * ROW_BYTES);
+        return __dmul_rn(por_surf, p.portab[kk]);
     };
 
     // ---- per-column constants -----------------------------------------------------------
