@@ -63,6 +63,8 @@ class FabmSedimentComponent:
         self.last_info = None
         self.export_3d_every_run = True
         self.flux_buffer = None   # optional caller-owned (pinned) (inum,jnum,nvar) export buffer
+        self._out = None          # output.dat handle (run_nml output > 0, component :266-269)
+        self.advance_count = 0    # ESMF clock advanceCount
 
     # ---- SetServices -----------------------------------------------------------------------
     def set_services(self):
@@ -82,7 +84,7 @@ class FabmSedimentComponent:
     def initialize_p1(self, import_state: State, export_state: State, clock=None, *, grid_shape,
                       run_nml: Optional[dict] = None, sed_nml: Optional[dict] = None,
                       fabm_nml: Optional[dict] = None, grid_mask: Optional[np.ndarray] = None,
-                      device: int = -1, j_offset: int = 0):
+                      device: int = -1, j_offset: int = 0, output_path: str = "output.dat"):
         """``grid_shape`` = (inum, jnum) of the foreign grid tile (:314-448); ``grid_mask`` is the
         ESMF_GRIDITEM_MASK item: columns with grid_mask <= 0 are masked (:497-501)."""
         if run_nml:
@@ -142,6 +144,9 @@ class FabmSedimentComponent:
         for name in self.import_field_names():
             import_state.setdefault(name, None)
         self.clock_seconds = 0.0
+        self.advance_count = 0
+        if int(r["output"]) > 0:                            # sed%do_output = output .gt. 0, :266
+            self._open_output(output_path)
         return ESMF_SUCCESS
 
     def initialize_p2(self, import_state: State, export_state: State, clock=None):
@@ -216,16 +221,78 @@ class FabmSedimentComponent:
         cs = [self._lookup(import_state, v, "_at_soil_surface") for v in VARIABLE_NAMES]
         wz = [self._lookup(import_state, v, "_z_velocity_at_soil_surface") if PARTICULATE[n] else None
               for n, v in enumerate(VARIABLE_NAMES)]
-        # get_boundary_conditions (:1665) + the step loop (:1700-1769) + the flux export (:1819) in
-        # one C-ABI call, so the library can overlap the PCIe transfers with the first/last attempt
-        rc, up = sed.run_exchange(float(r["dt"]), int(r["ode_method"]), float(run_seconds), temp, cs, wz,
-                                  out=self.flux_buffer)
+        if self._out is not None:
+            rc, up = self._run_with_output(temp, cs, wz, float(run_seconds))
+        else:
+            # get_boundary_conditions (:1665) + the step loop (:1700-1769) + the flux export (:1819) in
+            # one C-ABI call, so the library can overlap the PCIe transfers with the first/last attempt
+            rc, up = sed.run_exchange(float(r["dt"]), int(r["ode_method"]), float(run_seconds), temp, cs,
+                                      wz, out=self.flux_buffer)
         self.last_info = sed.info
         self.clock_seconds += float(run_seconds)
         if rc == _abi.NAN_DETECTED:                          # :1718-1723
             raise ComponentError(ESMF_RC_VAL_OUTOFRANGE, "NaN detected applying ode_solver")
         self._fill_exports(export_state, with_3d=self.export_3d_every_run, up=up)   # :1773-1822
         return ESMF_SUCCESS
+
+    # ---- output.dat (:677-685 header, :1734-1759 rows) ---------------------------------------------
+    @staticmethod
+    def _fortran_e(x: float, width: int, digits: int, expw: int = 2) -> str:
+        """Fortran Ew.d / Ew.dEe edit descriptor (0.dddE+ee normalisation)."""
+        if x != x:
+            return "NaN".rjust(width)
+        if x == 0.0:
+            mant, ex = 0.0, 0
+        else:
+            ex = int(np.floor(np.log10(abs(x)))) + 1
+            mant = abs(x) / 10.0 ** ex
+            if round(mant, digits) >= 1.0:
+                mant, ex = mant / 10.0, ex + 1
+        s = f"{mant:.{digits}f}E{'+' if ex >= 0 else '-'}{abs(ex):0{expw}d}"
+        return (("-" if x < 0 else "") + s).rjust(width)
+
+    def _open_output(self, path: str):
+        self._out = open(path, "w")
+        names = [f"hzg_omexdia_p_{s}" for s in STATE_NAMES] + ["hzg_omexdia_p_denit"]
+        self._out.write("time(s) depth(m) layer-height(m) porosity() " + "".join(" " + n for n in names) + "\n")
+
+    def _write_output(self, time_s: float):
+        sed, e = self.sed, self._fortran_e
+        i0, j0 = np.argwhere(~self.mask)[0] if (~self.mask).any() else (0, 0)   # column (lbnd1,lbnd2)
+        conc, por, denit = sed.conc, sed.field("porosity"), sed.field("denit")
+        _, zc, dz, _ = sed.grid()
+        fl = sed.fluxes
+        self._out.write(f" {time_s!r} fluxes " + " ".join(repr(float(v)) for v in fl[0, 0, :]) + "\n")
+        for k in range(sed.knum):
+            row = e(time_s, 15, 3) + " " + e(zc[k], 15, 4, 3) + " " + e(dz[k], 15, 4, 3) + " " + \
+                e(por[i0, j0, k], 15, 4, 3)
+            row += "".join(" " + e(conc[i0, j0, k, n], 15, 4, 3) for n in range(NVAR))
+            row += " " + e(denit[i0, j0, k], 15, 4, 3)
+            self._out.write(row + "\n")
+        self._out.flush()
+
+    def _run_with_output(self, temp, cs, wz, run_seconds: float):
+        """Run loop split at the output steps: row block after every step with
+        mod(advanceCount, output) == 0 (:1737), time label advanceCount*dt."""
+        sed, r = self.sed, self.run_nml
+        dt, method, every = float(r["dt"]), int(r["ode_method"]), int(r["output"])
+        sed.get_boundary_conditions(temp, cs, wz)
+        nfull = int(np.floor(run_seconds / dt * (1.0 + 1e-14)))
+        rem = run_seconds - nfull * dt
+        rc = 0
+        for _ in range(nfull):
+            rc = sed.step(dt, method, 1)
+            if rc:
+                break
+            if self.advance_count % every == 0:
+                self._write_output(self.advance_count * dt)
+            self.advance_count += 1
+        if rc == 0 and rem > 1e-9 * dt:
+            rc = sed.step(rem, method, 1)
+            if rc == 0 and self.advance_count % every == 0:
+                self._write_output(self.advance_count * rem)   # advanceCount*dt with the shortened dt (:1739)
+            self.advance_count += 1
+        return rc, sed.upward_fluxes(self.flux_buffer)
 
     def _fill_exports(self, export_state: State, with_3d: bool, up=None):
         sed = self.sed
@@ -247,6 +314,9 @@ class FabmSedimentComponent:
 
     # ---- Finalize (:1833-1861) ------------------------------------------------------------------------
     def finalize(self, import_state: State = None, export_state: State = None, clock=None):
+        if self._out is not None:                            # close(funit), :1852
+            self._out.close()
+            self._out = None
         if self.sed is not None:
             self.sed.finalize()
             self.sed = None

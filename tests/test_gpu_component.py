@@ -140,3 +140,35 @@ def test_component_presimulation(gpu, oracle):
         assert scaled_err(conc[i, j], want[0, 0]) <= 1e-8
     assert np.all(conc[~wet] == 1e20)
     comp.finalize()
+
+
+def test_component_output_dat(gpu, tmp_path):
+    """output.dat (component :677-685, :1734-1759): header + one block per output step, parseable the way
+    examples/standalone/omexdia_p/plotsed1d.py parses it."""
+    from mossco_code_b200.component import FabmSedimentComponent
+    case = make_case("out", 3, 2, 12, 0.004, seed=4)
+    comp = FabmSedimentComponent()
+    imp, exp = {}, {}
+    path = tmp_path / "output.dat"
+    comp.initialize_p1(imp, exp, grid_shape=(3, 2), output_path=str(path),
+                       run_nml=dict(numlayers=12, dzmin=0.004, dt=360.0, dt_min=1.0, ode_method=2, output=5))
+    imp.update(_import_state(case, None))
+    comp.run(imp, exp, run_seconds=3600.0)          # steps 0..9 -> blocks after steps 0 and 5
+    comp.run(imp, exp, run_seconds=3600.0)          # steps 10..19 -> blocks after steps 10 and 15
+    conc = comp.sed.conc
+    comp.finalize()
+    lines = path.read_text().splitlines()
+    head = lines[0].split()
+    assert head[:4] == ["time(s)", "depth(m)", "layer-height(m)", "porosity()"]
+    assert "hzg_omexdia_p_denit" in head and head[4] == "hzg_omexdia_p_ldetC"
+    blocks = [i for i, l in enumerate(lines) if len(l.split()) > 1 and l.split()[1] == "fluxes"]
+    assert len(blocks) == 4
+    assert [float(lines[i].split()[0]) for i in blocks] == [0.0, 1800.0, 3600.0, 5400.0]
+    first = lines[blocks[0] + 1].split()
+    assert len(first) == 4 + 8 + 1 and len(lines[blocks[0] + 1]) == 13 * 15 + 12
+    assert first[0] == "0.000E+00" and first[1].endswith("E-002")
+    rows = np.array([[float(x) for x in l.split()] for l in lines[blocks[3] + 1: blocks[3] + 13]])
+    assert rows.shape == (12, 13) and np.all(rows[:, 0] == 5400.0)
+    assert np.all(np.diff(rows[:, 1]) > 0)                       # depth increases
+    assert FabmSedimentComponent._fortran_e(-1234.5678, 15, 4, 3).strip() == "-0.1235E+004"
+    assert FabmSedimentComponent._fortran_e(0.99996, 15, 4, 3).strip() == "0.1000E+001"
