@@ -284,6 +284,11 @@ column_kernel(const __grid_constant__ KParams p)
                 const double c1 = lds64(sbase + n * ROW_BYTES);
                 const double C1 = part ? c1 * por0 : c1;
                 f = -(part ? Dp : Dd) * (C1 - Cup) * rdz0;
+            } else if (bc != 3 && n > 0) {
+                // BcUp outside 1..4 (bcup_dissolved_variables = 0): diff3d never assigns Flux(1)
+                // (:782-803), so it keeps what the previous variable's call left in get_rhs's
+                // intFlux array (:586) -- reproduced here; BcUp = 3 is the explicit zero (:789)
+                f = F[n - 1];
             }
             F[n] = f;
             if (!part) p.fluxes[(size_t)n * ld + col] = f;   // fluxes(:,:,n) = intFlux(:,:,1), :692
