@@ -185,6 +185,11 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
 int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
                       const double *temperature2d, const double *const *csurf, const double *const *wz,
                       double *upward_fluxes, msed_step_info *info);
+/* Step fusion (default on): Euler / adaptive-Euler steps are issued in speculative pairs that read and
+ * write the state once for two steps; a pair is committed only if neither step would be rejected
+ * (solver_library.F90:126) or stopped by check_NaN, otherwise the same steps are redone singly from the
+ * untouched state.  Results are bit-identical with fusion on or off; 0 switches it off. */
+int msed_set_step_fusion(msed_handle *h, int enable);
 /* number of column chunks msed_run_exchange uses (0 = choose from the tile size, 1 = no overlap) */
 int msed_set_exchange_chunks(msed_handle *h, int nchunks);
 /* 1-D pre-simulation (component :557-632) for the handle's configuration; conc1d(1,1,knum,nvar) out.

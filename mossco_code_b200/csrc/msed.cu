@@ -83,6 +83,9 @@ struct msed_handle {
     cudaStream_t copy_stream = nullptr;           // PCIe traffic of msed_run_exchange
     cudaEvent_t ev_pool[2 * 16] = {};             // per-chunk H2D-done / compute-done events
     int exchange_chunks = 0;                      // 0 = choose from the tile size
+    int step_fusion = 1;                          // fused pairs of Euler/adaptive steps allowed
+    int pair_cooldown = 0;                        // steps to run singly after a rejection / failed pair
+    long long pairs_committed = 0;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     msed_allreduce_hook hook = nullptr;
@@ -264,16 +267,44 @@ int ensure_scratch(msed_handle *h)
     return MSED_OK;
 }
 
+cudaError_t launch_pair(const msed_handle *h, int method, const KParams &p)
+{
+    const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
+    const bool adaptive = method == MSED_ADAPTIVE_EULER;
+    if (h->cfg.model == MSED_MODEL_OMEXDIA_P) {
+        if (adaptive) pair_kernel<MSED_MODEL_OMEXDIA_P, true><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);
+        else pair_kernel<MSED_MODEL_OMEXDIA_P, false><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);
+    } else {
+        if (adaptive) pair_kernel<MSED_MODEL_NONE, true><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);
+        else pair_kernel<MSED_MODEL_NONE, false><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t enable_pair_smem()
+{
+    cudaError_t e;
+    const int bytes = (int)PAIR_SMEM_BYTES;
+    if ((e = cudaFuncSetAttribute(pair_kernel<MSED_MODEL_OMEXDIA_P, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pair_kernel<MSED_MODEL_OMEXDIA_P, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pair_kernel<MSED_MODEL_NONE, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(pair_kernel<MSED_MODEL_NONE, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 int reduce_flags(msed_handle *h)
 {
     if (h->hook) {
         void *flags = (void *)((char *)h->ctl + offsetof(Ctl, flags));
-        if (h->hook(h->hook_user, flags, 2, (void *)h->stream) != 0)
+        if (h->hook(h->hook_user, flags, 4, (void *)h->stream) != 0)
             return fail(h, MSED_ERR_NCCL, "allreduce hook failed");
     } else if (h->comm) {
         NcclApi &api = nccl_api();
         int *flags = (int *)((char *)h->ctl + offsetof(Ctl, flags));
-        int rc = api.AllReduce(flags, flags, 2, kNcclInt32, kNcclMax, h->comm, h->stream);
+        int rc = api.AllReduce(flags, flags, 4, kNcclInt32, kNcclMax, h->comm, h->stream);
         if (rc != 0)
             return fail(h, MSED_ERR_NCCL, std::string("ncclAllReduce: ") +
                                               (api.GetErrorString ? api.GetErrorString(rc) : "error"));
@@ -333,31 +364,67 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     long long launches = 0;
 
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-    long long remaining = nsteps, issued = 0;
+
+    // get_boundary_conditions of one chunk of msed_run_exchange as soon as its fields have landed
+    auto boundary_chunk = [&](int c) -> int {
+        const int c0 = plan->c0[c], c1 = plan->c1[c];
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_pool[c], 0));
+        BcPtrs bc = plan->bc;
+        if (bc.temperature) bc.temperature += c0;
+        for (int n = 0; n < NV; ++n) {
+            if (bc.csurf[n]) bc.csurf[n] += c0;
+            if (bc.wz[n]) bc.wz[n] += c0;
+        }
+        boundary_kernel<<<nblocks(c1 - c0), 256, 0, h->stream>>>(
+            h->bdys + c0, h->fluxes + c0, h->buf[h->cur] + c0, h->por + c0, bc, h->ld, h->ld, c1 - c0, h->K,
+            h->cfg.bcup_dissolved_variables, h->bioturbation_eff, h->cfg.diffusivity, h->dz[0]);
+        launches += 1;
+        return MSED_OK;
+    };
+
+    // ---- fused pairs of steps first (msed_pair.cuh): speculative, nothing is committed on failure --
+    const bool single_attempt = (method == MSED_EULER || method == MSED_ADAPTIVE_EULER);
+    long long npairs = 0;
+    if (h->step_fusion && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 3 &&
+        (h->cfg.model == MSED_MODEL_OMEXDIA_P || h->cfg.model == MSED_MODEL_NONE) &&
+        h->cfg.bioturbation_profile != 3 && !h->cfg.distributed_pom_flux && h->por_mode != 0)
+        npairs = (nsteps - 1) / 2;  // the last step is always a single one (diagnostics, chunked export)
+    bool first_pending = plan && plan->first && single_attempt;
+    for (long long q = 0; q < npairs; ++q) {
+        if (first_pending) {
+            for (int c = 0; c < plan->nchunks; ++c) {
+                if ((rc = boundary_chunk(c))) return rc;
+                KParams pc = p;
+                pc.col0 = plan->c0[c];
+                pc.col_end = plan->c1[c];
+                CUDA_TRY(h, launch_pair(h, method, pc));
+                launches += 1;
+            }
+            first_pending = false;
+        } else {
+            CUDA_TRY(h, launch_pair(h, method, p));
+            launches += 1;
+        }
+        if (collective)
+            if ((rc = reduce_flags(h))) return rc;
+        pair_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method);
+        launches += 1;
+    }
+    const long long singles_planned = nsteps - 2 * npairs;
+
+    long long remaining = singles_planned, issued = 0;
     const long long max_batch = 256;
     int guard = 0;
     while (remaining > 0) {
         const long long batch = remaining < max_batch ? remaining : max_batch;
         for (long long s = 0; s < batch; ++s, ++issued) {
-            const bool chunk_first = plan && plan->first && issued == 0;
-            const bool chunk_last = plan && plan->last && issued == nsteps - 1;
-            if ((chunk_first || chunk_last) && (method == MSED_EULER || method == MSED_ADAPTIVE_EULER)) {
+            const bool chunk_first = first_pending && issued == 0;
+            const bool chunk_last = plan && plan->last && issued == singles_planned - 1;
+            if ((chunk_first || chunk_last) && single_attempt) {
                 for (int c = 0; c < plan->nchunks; ++c) {
                     const int c0 = plan->c0[c], c1 = plan->c1[c];
-                    if (chunk_first) {  // get_boundary_conditions of this chunk as soon as its fields landed
-                        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_pool[c], 0));
-                        BcPtrs bc = plan->bc;
-                        if (bc.temperature) bc.temperature += c0;
-                        for (int n = 0; n < NV; ++n) {
-                            if (bc.csurf[n]) bc.csurf[n] += c0;
-                            if (bc.wz[n]) bc.wz[n] += c0;
-                        }
-                        boundary_kernel<<<nblocks(c1 - c0), 256, 0, h->stream>>>(
-                            h->bdys + c0, h->fluxes + c0, h->buf[h->cur] + c0, h->por + c0, bc, h->ld, h->ld,
-                            c1 - c0, h->K, h->cfg.bcup_dissolved_variables, h->bioturbation_eff,
-                            h->cfg.diffusivity, h->dz[0]);
-                        launches += 1;
-                    }
+                    if (chunk_first)
+                        if ((rc = boundary_chunk(c))) return rc;
                     KParams pc = p;
                     pc.col0 = c0;
                     pc.col_end = c1;
@@ -422,9 +489,14 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     const Ctl &r = *h->ctl_host;
     if (plan && plan->last) {  // the chunked export is final only if no attempt was rejected
         CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
-        plan->export_done = (method == MSED_EULER || method == MSED_ADAPTIVE_EULER) && !r.stop &&
-                            r.subcycles == 0 && r.steps_done == nsteps && nsteps > 0;
+        plan->export_done = single_attempt && !r.stop && r.subcycles == 0 && r.pair_failures == 0 &&
+                            r.steps_done == nsteps && nsteps > 0;
     }
+    // fused pairs only pay off while steps are accepted first time: after a rejection or a failed
+    // pair run single steps for a while (sub-cycling comes in long episodes)
+    if (r.subcycles > 0 || r.pair_failures > 0) h->pair_cooldown = 64;
+    else if (h->pair_cooldown > 0) h->pair_cooldown -= (int)std::min<long long>(nsteps, h->pair_cooldown);
+    h->pairs_committed += (npairs > 0 && r.pair_failures == 0) ? npairs : 0;
     h->cur = r.cur;
     if (diag && r.last_min_dt < h->last_min_dt) {
         long long idx = -1;
@@ -581,6 +653,7 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     } while (0)
 
     CREATE_TRY(cudaSetDevice(h->device));
+    CREATE_TRY(enable_pair_smem());
     CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -968,6 +1041,14 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
         }
     }
     return rc;
+}
+
+int msed_set_step_fusion(msed_handle *h, int enable)
+{
+    if (!h) return MSED_ERR_ARG;
+    h->step_fusion = enable ? 1 : 0;
+    h->pair_cooldown = 0;
+    return MSED_OK;
 }
 
 int msed_set_exchange_chunks(msed_handle *h, int nchunks)

@@ -114,6 +114,61 @@ __device__ __forceinline__ double bf3_cell(const KParams &p, int k, double wt, d
     return p.beta * pow(biomass, p.b) / wt;
 }
 
+// ---- the transport arithmetic, shared by column_kernel and pair_kernel (msed_pair.cuh) so that a
+// fused pair of steps is bit-identical to two single steps ---------------------------------------
+// diffusivities of the interface between two layers, pre-multiplied by -1/dzc
+// (driver :652-653 bioturbation part, :682-683 molecular part, diff3d :777)
+__device__ __forceinline__ void interface_coeffs(double cpart, double cdiss, double porc, double porn,
+                                                 double bfk, double rdzc, double &mDp, double &mDd)
+{
+    const double intf = 0.5 * (porc + porn);  // intf_porosity, driver :435
+    const double Dp = cpart * (1.0 - intf) * bfk;
+    const double Dd = Dp + cdiss * intf;
+    mDp = -Dp * rdzc;
+    mDd = -Dd * rdzc;
+}
+__device__ __forceinline__ double flux_particulate(double mDp, double cn, double porn, double cc, double porc)
+{
+    return mDp * (cn * porn - cc * porc);  // C = conc*porosity, driver :663
+}
+__device__ __forceinline__ double flux_dissolved(double mDd, double cn, double cc) { return mDd * (cn - cc); }
+// upper-boundary diffusivities: intf_porosity(:,:,1) = porosity(:,:,1), driver :434
+__device__ __forceinline__ void top_coeffs(double cpart, double cdiss, double por0, double bf0, double &Dp,
+                                           double &Dd)
+{
+    Dp = cpart * (1.0 - por0) * bf0;
+    Dd = Dp + cdiss * por0;
+}
+__device__ __forceinline__ double top_flux_dirichlet(double D, double C1, double Cup, double rdz0)
+{
+    return -D * (C1 - Cup) * rdz0;  // diff3d :786
+}
+// dC (:819) with the particulate rescaling (:677-678) folded: (Flux(k)-Flux(k+1))/(porosity*dz) + rate
+__device__ __forceinline__ double layer_rhs(double Fup, double Flow, double rpd, double rate)
+{
+    return fma(Fup - Flow, rpd, rate);  // driver :715
+}
+__device__ __forceinline__ double euler_update(double dt, double rhs, double c0) { return fma(dt, rhs, c0); }
+__device__ __forceinline__ bool violates(double fac, double c0, double newc)  // solver_library.F90:121
+{
+    return fma(-fac, c0, newc) < 0.0;
+}
+// per-column Arrhenius factors and diffusivity prefactors (driver :648,:652,:682; omexdia_p f_T)
+template <int MODEL, bool PROFILE3>
+__device__ __forceinline__ void column_constants(const KParams &p, double temp, double &cpart, double &cdiss,
+                                                 double &fT)
+{
+    fT = 1.0;
+    if (PROFILE3) {
+        cpart = 1.0 / 86400.0 / 10000.0;  // f_T = 1, bioturbation = 1, driver :622-623
+    } else {
+        const double f_T = exp(-4500.0 * (1.0 / (temp + 273.0) - (1.0 / 288.0)));  // :648
+        cpart = p.bioturbation * f_T / 86400.0 / 10000.0;                          // :652
+    }
+    cdiss = (p.diffusivity + temp * 0.035) / 86400.0 / 10000.0;                    // :682-683
+    if (MODEL == MSED_MODEL_OMEXDIA_P) fT = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
+}
+
 template <int OP> struct OpTraits {
     static constexpr bool stepping = (OP != OP_RHS);
     static constexpr bool reads_base = (OP == OP_RK4_S2 || OP == OP_RK4_S3 || OP == OP_RK4_S4 ||
@@ -238,16 +293,8 @@ column_kernel(const __grid_constant__ KParams p)
 
     // ---- per-column constants -----------------------------------------------------------
     const double temp = ld_ro(p.bdys + col);  // temp3d(:,:,k) = bdys(:,:,1), driver :602
-    double cpart, fT = 1.0;
-    if (PROFILE3) {
-        cpart = 1.0 / 86400.0 / 10000.0;  // f_T = 1, bioturbation = 1, driver :622-623
-    } else {
-        const double f_T = exp(-4500.0 * (1.0 / (temp + 273.0) - (1.0 / 288.0)));  // :648
-        cpart = p.bioturbation * f_T / 86400.0 / 10000.0;                          // :652
-    }
-    const double cdiss = (p.diffusivity + temp * 0.035) / 86400.0 / 10000.0;       // :682-683
-    if (MODEL == MSED_MODEL_OMEXDIA_P)
-        fT = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
+    double cpart, cdiss, fT;
+    column_constants<MODEL, PROFILE3>(p, temp, cpart, cdiss, fT);
 
     double avg_wt = 0.0;
     if (PROFILE3) {  // column integral of the weighted TOC, driver :629-633
@@ -269,8 +316,8 @@ column_kernel(const __grid_constant__ KParams p)
         const double por0 = por_at(0, sbase);
         double bf0 = p.bf[0];
         if (PROFILE3) bf0 = bf3_cell(p, 0, wtoc_cell(p, por0, poc[0], poc[plane]), avg_wt);
-        const double Dp = cpart * (1.0 - por0) * bf0;  // intf_porosity(:,:,1) = porosity(:,:,1), :434
-        const double Dd = Dp + cdiss * por0;
+        double Dp, Dd;
+        top_coeffs(cpart, cdiss, por0, bf0, Dp, Dd);
         const double rdz0 = 1.0 / p.dz[0];
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
@@ -283,7 +330,7 @@ column_kernel(const __grid_constant__ KParams p)
                 const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
                 const double c1 = lds64(sbase + n * ROW_BYTES);
                 const double C1 = part ? c1 * por0 : c1;
-                f = -(part ? Dp : Dd) * (C1 - Cup) * rdz0;
+                f = top_flux_dirichlet(part ? Dp : Dd, C1, Cup, rdz0);
             } else if (bc != 3 && n > 0) {
                 // BcUp outside 1..4 (bcup_dissolved_variables = 0): diff3d never assigns Flux(1)
                 // (:782-803), so it keeps what the previous variable's call left in get_rhs's
@@ -344,21 +391,18 @@ column_kernel(const __grid_constant__ KParams p)
         double Fn[NV];
         if (has_next) {
             const double porn = por_at(k + 1, sn);
-            const double intf = 0.5 * (porc + porn);  // :435
             double bfk = p.bf[k + 1];
             if (PROFILE3)
                 bfk = bf3_cell(p, k + 1,
                                wtoc_cell(p, porn, poc[(size_t)(k + 1) * ld], poc[plane + (size_t)(k + 1) * ld]),
                                avg_wt);
-            const double Dp = cpart * (1.0 - intf) * bfk;
-            const double Dd = Dp + cdiss * intf;
-            const double rdzc = p.rdzc[k];
-            const double mDp = -Dp * rdzc, mDd = -Dd * rdzc;
+            double mDp, mDd;
+            interface_coeffs(cpart, cdiss, porc, porn, bfk, p.rdzc[k], mDp, mDd);
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
                 const double cn = lds64(sn + n * ROW_BYTES);
-                if (n < NPART) Fn[n] = mDp * (cn * porn - cc[n] * porc);
-                else Fn[n] = mDd * (cn - cc[n]);
+                if (n < NPART) Fn[n] = flux_particulate(mDp, cn, porn, cc[n], porc);
+                else Fn[n] = flux_dissolved(mDd, cn, cc[n]);
             }
             if (p.bcup_part == 4) {  // distributed POM flux cascade, :795-802 (kk = k+2, 1-based)
                 double cap = p.pom_flux_rate * (1.0 - porn) * p.dz[k + 1];
@@ -397,16 +441,15 @@ column_kernel(const __grid_constant__ KParams p)
             double *go = g_out, *ga1 = g_a1, *ga2 = g_a2, *gr = g_rhs;
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
-                const double rhs = fma(F[n] - Fn[n], rpd, r[n]);  // driver :715
+                const double rhs = layer_rhs(F[n], Fn[n], rpd, r[n]);
                 F[n] = Fn[n];
                 const double c0 = cc[n];
                 double newc = 0.0;
                 if (OP == OP_RHS) {
                     *gr = rhs;
                 } else if (OP == OP_EULER || OP == OP_ADAPTIVE) {
-                    newc = fma(dt, rhs, c0);                               // :102,:111
-                    if (OP == OP_ADAPTIVE)                                  // :121
-                        viol |= (fma(-p.fac, c0, newc) < 0.0);
+                    newc = euler_update(dt, rhs, c0);                      // :102,:111
+                    if (OP == OP_ADAPTIVE) viol |= violates(p.fac, c0, newc);  // :121
                 } else if (OP == OP_RK4_S1) {                               // :147
                     newc = fma(0.5 * dt, rhs, c0);
                     *ga1 = 0.5 * rhs;

@@ -52,7 +52,10 @@ struct Ctl {
     long long steps_done, steps_target;
     long long rhs_evals, subcycles;
     int cur;            // which of buf[0..1] is sed%conc
-    int flags[2];       // [0] relative-change violation (:121)  [1] NaN (component :2392)
+    int flags[4];       // [0] relative-change violation (:121)  [1] NaN (component :2392);
+                        // [2],[3] the same for the second step of a fused pair (msed_pair.cuh)
+    int pairs_disabled; // a fused pair could not be committed: fall back to single steps
+    int pair_failures;
     int nan_detected;
     int stop;
     int do_clip;        // component wrapper (check_NaN + clip) on/off
@@ -95,6 +98,8 @@ struct KParams {
 
 // loaders, reaction term and the fused column kernel
 #include "msed_column.cuh"
+// two Euler / adaptive-Euler steps per pass over HBM (speculative, rollback-free)
+#include "msed_pair.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // step-loop controller: the scalar part of ode_solver (:108,:126-139) and of the component

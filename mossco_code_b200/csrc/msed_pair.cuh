@@ -1,0 +1,222 @@
+// msed_pair.cuh -- included inside namespace msed after msed_column.cuh.
+//
+// Two consecutive Euler / adaptive-Euler steps in one pass over HBM.
+//
+// The single-step kernel is HBM-bound (state read once, written once per step) with the fp64 pipe
+// only half busy.  Columns are independent and the stencil is one layer wide, so the second step can
+// chase the first one down the column with a lag of one layer: when step 1 has produced layer k,
+// step 2 has everything it needs for layer k-1.  The intermediate state c1 never leaves the SM (a
+// thread-private 4-layer window in shared memory), so a pair costs one read and one write of the
+// state instead of two.
+//
+// Semantics are exactly those of two ode_solver calls (solver_library.F90:104-140) with the component's
+// check_NaN / minimum clip after each (fabm_sediment_component.F90:1718-1732): step 1's output is
+// clipped before step 2 reads it, each step raises its own violation / NaN flags, and the pair is
+// committed by pair_controller_kernel only if neither step would have been rejected or stopped.
+// Otherwise nothing is committed (the input buffer is untouched) and the host falls back to single
+// steps from the same state -- so a pair is speculation with a free rollback.  The arithmetic is the
+// shared inline code of msed_column.cuh: a committed pair is bit-identical to two single steps.
+//
+// Restricted to the hot configuration: bcup_particulate = 1 (no distributed POM flux cascade),
+// bioturbation_profile != 3, closed-form porosity (KParams::por_mode 1 or 2).
+
+constexpr int PAIR_WIN = 4;  // c1 window slots (3 live layers: j, j+1 and the one being written)
+constexpr uint32_t PAIR_STAGE_BYTES = NV * ROW_BYTES;                    // input ring: 8 rows per layer
+constexpr uint32_t PAIR_RING_BYTES = RING_STAGES * PAIR_STAGE_BYTES;
+constexpr size_t PAIR_SMEM_BYTES = (size_t)PAIR_RING_BYTES + (size_t)PAIR_WIN * NV * ROW_BYTES;
+constexpr int PAIR_MIN_BLOCKS = 3;
+
+__device__ __forceinline__ void sts64(uint32_t addr, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+template <int MODEL, bool ADAPTIVE>
+__global__ void __launch_bounds__(COL_BLOCK, PAIR_MIN_BLOCKS)
+pair_kernel(const __grid_constant__ KParams p)
+{
+    extern __shared__ __align__(16) double ring[];
+    const Ctl *ctl = p.ctl;
+    if (ctl->stop || ctl->pairs_disabled || ctl->steps_done + 2 > ctl->steps_target || ctl->dt_int != 0.0)
+        return;
+    const int cur = ctl->cur;
+    const bool do_clip = ctl->do_clip != 0;
+    const double dt = ctl->dt;
+    // a pair whose violation flags are already up cannot be committed: later CTAs skip their work
+    const volatile int *flags = ctl->flags;
+    if (ADAPTIVE && dt > ctl->dt_min && (flags[0] | flags[2])) return;
+
+    const int col = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
+    if (col >= p.col_end) return;
+    if (p.mask[col] != 0) return;  // conc stays missing_value in both buffers
+
+    const int K = p.K;
+    const size_t ld = p.ld;
+    const size_t plane = (size_t)K * ld;
+    const double *in = p.buf[cur] + col;
+    double *out = p.buf[1 - cur] + col;
+
+    // ---- input ring (cp.async, as in column_kernel) and the c1 window --------------------------
+    const uint32_t sbase = smem_u32(ring) + threadIdx.x * 8u;
+    const uint32_t wbase = sbase + PAIR_RING_BYTES;
+    const double *g_in = in;
+    int k_fetch = 0;
+    auto fetch_next = [&]() {
+        if (k_fetch < K) {
+            const uint32_t sa = sbase + (uint32_t)(k_fetch & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
+            const double *g = g_in;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                cp_async8(sa + n * ROW_BYTES, g);
+                g += plane;
+            }
+            g_in += ld;
+        }
+        ++k_fetch;
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < RING_STAGES - 1; ++s) fetch_next();
+
+    const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
+    auto por_at = [&](int kk) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
+
+    const double temp = ld_ro(p.bdys + col);
+    double cpart, cdiss, fT;
+    column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
+
+    // upper boundary of one step: F[n] = Flux(1) (diff3d :782-803), c0(n) = state of layer 1
+    auto top_boundary = [&](auto c0, double por0, double (&F)[NV], bool write_fluxes) {
+        double Dp, Dd;
+        top_coeffs(cpart, cdiss, por0, p.bf[0], Dp, Dd);
+        const double rdz0 = 1.0 / p.dz[0];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const bool part = n < NPART;
+            const int bc = part ? p.bcup_part : p.bcup_diss;
+            double f = 0.0;
+            if (bc == 1 || bc == 4) {
+                f = ld_ro(p.fluxes + (size_t)n * ld + col);
+            } else if (bc == 2) {
+                const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
+                const double c1 = c0(n);
+                const double C1 = part ? c1 * por0 : c1;
+                f = top_flux_dirichlet(part ? Dp : Dd, C1, Cup, rdz0);
+            } else if (bc != 3 && n > 0) {
+                f = F[n - 1];
+            }
+            F[n] = f;
+            if (write_fluxes && !part) p.fluxes[(size_t)n * ld + col] = f;  // driver :692
+        }
+    };
+
+    cp_async_wait<RING_STAGES - 2>();  // layer 0 has landed
+    double FA[NV], FB[NV];
+    // Step 1 reads the particulate input fluxes BEFORE step 2 may overwrite the dissolved entries of
+    // the same array; with bcup_dissolved = 1 the dissolved input fluxes are read here as well and
+    // rewritten unchanged by step 2 (:692).
+    top_boundary([&](int n) { return lds64(sbase + n * ROW_BYTES); }, por_at(0), FA, false);
+
+    bool viol1 = false, nan1 = false, viol2 = false, nan2 = false;
+    double *g_out = out;
+
+    // one step of one layer: finishes layer kk given its state cc, the state cn of the layer below,
+    // the flux F through its upper interface; returns the new state through `sink`
+    auto step_layer = [&](int kk, const double (&cc)[NV], auto cn, double (&F)[NV], bool &viol, bool &nanf,
+                          auto sink) {
+        const bool has_next = (kk + 1 < K);
+        const double porc = por_at(kk);
+        double Fn[NV];
+        if (has_next) {
+            const double porn = por_at(kk + 1);
+            double mDp, mDd;
+            interface_coeffs(cpart, cdiss, porc, porn, p.bf[kk + 1], p.rdzc[kk], mDp, mDd);
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double c = cn(n);
+                if (n < NPART) Fn[n] = flux_particulate(mDp, c, porn, cc[n], porc);
+                else Fn[n] = flux_dissolved(mDd, c, cc[n]);
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) Fn[n] = 0.0;
+        }
+        double r[NV];
+        if (MODEL == MSED_MODEL_OMEXDIA_P) {
+            omexdia_rates(p.om, cc, fT, r, nullptr);
+        } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) r[n] = 0.0;
+        }
+        const double rpd = fast_rcp(porc * p.dz[kk]);
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const double rhs = layer_rhs(F[n], Fn[n], rpd, r[n]);
+            F[n] = Fn[n];
+            const double c0 = cc[n];
+            double newc = euler_update(dt, rhs, c0);
+            if (ADAPTIVE) viol |= violates(p.fac, c0, newc);
+            if (do_clip) {
+                nanf |= (newc != newc);
+                const double mn = p.om.minimum[n];
+                newc = (newc < mn) ? mn : newc;
+            }
+            sink(n, newc);
+        }
+    };
+
+    for (int k = 0; k <= K; ++k) {
+        if (k < K) {  // ---- step 1, layer k: state from the ring, result into the c1 window ----------
+            fetch_next();
+            cp_async_wait<RING_STAGES - 2>();
+            const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
+            const uint32_t sn = sbase + (uint32_t)((k + 1) & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
+            const uint32_t wk = wbase + (uint32_t)(k & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+            double cc[NV];
+#pragma unroll
+            for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
+            step_layer(k, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA, viol1, nan1,
+                       [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); });
+        }
+        if (k >= 1) {  // ---- step 2, layer j = k-1: state from the c1 window, result to HBM ---------
+            const int j = k - 1;
+            const uint32_t wj = wbase + (uint32_t)(j & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+            const uint32_t wn = wbase + (uint32_t)((j + 1) & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+            if (j == 0)
+                top_boundary([&](int n) { return lds64(wj + n * ROW_BYTES); }, por_at(0), FB, true);
+            double cc[NV];
+#pragma unroll
+            for (int n = 0; n < NV; ++n) cc[n] = lds64(wj + n * ROW_BYTES);
+            double *go = g_out;
+            step_layer(j, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB, viol2, nan2,
+                       [&](int n, double v) { go[(size_t)n * plane] = v; });
+            g_out += ld;
+        }
+    }
+    cp_async_wait<0>();
+
+    int *wf = p.ctl->flags;
+    if (ADAPTIVE && viol1) atomicOr(&wf[0], 1);
+    if (nan1) atomicOr(&wf[1], 1);
+    if (ADAPTIVE && viol2) atomicOr(&wf[2], 1);
+    if (nan2) atomicOr(&wf[3], 1);
+}
+
+// commits a pair (or disables pairs so the host falls back to single steps from the same state)
+__global__ void pair_controller_kernel(Ctl *c, int method)
+{
+    c->step_completed = 0;
+    if (c->stop || c->pairs_disabled || c->steps_done + 2 > c->steps_target || c->dt_int != 0.0) return;
+    const int v1 = c->flags[0], n1 = c->flags[1], v2 = c->flags[2], n2 = c->flags[3];
+    c->flags[0] = c->flags[1] = c->flags[2] = c->flags[3] = 0;
+    const bool rejectable = (method == MSED_ADAPTIVE_EULER) && (c->dt_red > c->dt_min);
+    if ((rejectable && (v1 || v2)) || (c->do_clip && (n1 || n2))) {
+        c->pairs_disabled = 1;  // a step would be rejected (:126) or stopped (component :1718):
+        c->pair_failures += 1;  // nothing is committed, single steps redo it exactly
+        return;
+    }
+    c->cur ^= 1;
+    c->steps_done += 2;
+    c->rhs_evals += 2;
+    c->step_completed = 1;
+}

@@ -258,6 +258,10 @@ class SedimentDriver:
                          allow=(_abi.NAN_DETECTED,))
         return rc, out
 
+    def set_step_fusion(self, enable: bool):
+        """Speculative two-step kernels on/off (results are bit-identical either way)."""
+        self._check(self._lib.msed_set_step_fusion(self._h, int(bool(enable))))
+
     def set_exchange_chunks(self, nchunks: int):
         self._check(self._lib.msed_set_exchange_chunks(self._h, int(nchunks)))
 

@@ -1,0 +1,111 @@
+"""Step fusion (msed_pair.cuh): speculative two-step kernels must be invisible in the results --
+bit-identical state, bed fluxes, sub-cycle counts and NaN behaviour with fusion on or off -- and must
+actually be used (fewer launches) in the regime they are meant for."""
+import numpy as np
+import pytest
+
+from tests.cases import make_case, rel_err
+
+pytestmark = pytest.mark.gpu
+DT = 360.0
+
+
+def _run(case, fusion, method, nsteps, calls=1, mutate=None, **cfgkw):
+    from mossco_code_b200 import SedimentDriver, default_config
+    kw = dict(inum=case.inum, jnum=case.jnum, knum=case.knum, dzmin=case.dzmin, dt_min=1.0)
+    kw.update(cfgkw)
+    cfg = default_config(**kw)
+    with SedimentDriver(cfg) as sed:
+        sed.set_step_fusion(fusion)
+        sed.set_mask(case.mask)
+        sed.init_concentrations()
+        sed.set_boundary(case.bdys, case.fluxes)
+        if mutate:
+            mutate(sed)
+        launches = sub = rhs = done = 0
+        rc = 0
+        for _ in range(calls):
+            rc = sed.step(DT, method, nsteps)
+            launches += sed.info.kernel_launches
+            sub += sed.info.subcycle_warnings
+            rhs += sed.info.rhs_evaluations
+            done += sed.info.steps_done
+            if rc:
+                break
+        return dict(conc=sed.conc, fluxes=sed.fluxes, denit=sed.field("denit"), launches=launches, sub=sub,
+                    rhs=rhs, done=done, rc=rc)
+
+
+def _same(a, b):
+    assert a["rc"] == b["rc"] and a["done"] == b["done"] and a["sub"] == b["sub"] and a["rhs"] == b["rhs"]
+    assert np.array_equal(a["conc"], b["conc"], equal_nan=True)
+    assert np.array_equal(a["fluxes"], b["fluxes"], equal_nan=True)
+    assert np.array_equal(a["denit"], b["denit"], equal_nan=True)
+
+
+@pytest.mark.parametrize("method", [2, 0])
+@pytest.mark.parametrize("nsteps", [3, 4, 10, 11])
+def test_fusion_is_bit_identical(gpu, oracle, method, nsteps):
+    case = make_case("fuse", 37, 21, 20, 0.003, seed=101, land_fraction=0.2, smooth_temperature=True)
+    on = _run(case, True, method, nsteps, calls=2)
+    off = _run(case, False, method, nsteps, calls=2)
+    _same(on, off)
+    assert on["launches"] < off["launches"]                 # pairs were really used
+    ref = oracle.OracleSediment(37, 21, 20, 0.003, mask2d=case.mask, dt_min=1.0)
+    ref.init_concentrations(); ref.set_boundary(case.bdys, case.fluxes)
+    assert ref.step(DT, method, 2 * nsteps) == 0
+    wet = case.mask == 0
+    assert rel_err(on["conc"][wet], ref.conc[wet]) <= 1e-11
+
+
+@pytest.mark.parametrize("kw", [dict(bcup_dissolved_variables=1), dict(bioturbation_profile=2),
+                                dict(bcup_dissolved_variables=3, bioturbation_profile=0),
+                                dict(minimum=[1., 2., 3., 0.5, 30., 1., 2., 150.]), dict(model=1)])
+def test_fusion_variants(gpu, kw):
+    case = make_case("fusev", 19, 9, 15, 0.004, seed=7)
+
+    def mutate(sed):
+        if kw.get("bcup_dissolved_variables") == 1:
+            fl = case.fluxes.copy(); fl[:, :, 3:] = 1e-6 * (1 + np.arange(5))
+            sed.set_boundary(None, fl)
+        sed.update_porosity(0.5 + 0.3 * np.random.default_rng(2).random((19, 9)))   # porosity mode 2
+
+    _same(_run(case, True, 2, 9, mutate=mutate, **kw), _run(case, False, 2, 9, mutate=mutate, **kw))
+
+
+def test_fusion_falls_back_when_a_step_is_rejected(gpu):
+    """rnit/rODUox boosted: the first steps sub-cycle.  A pair containing a rejected step is not committed;
+    the single-step path redoes it, and fusion stays off for a while afterwards."""
+    case = make_case("fuser", 12, 8, 15, 0.004, seed=2)
+    kw = dict(rnit=2.0e3, rODUox=2.0e3)
+    on = _run(case, True, 2, 7, calls=3, **kw)
+    off = _run(case, False, 2, 7, calls=3, **kw)
+    assert off["sub"] > 0
+    _same(on, off)
+
+
+def test_fusion_nan_stops_at_the_same_step(gpu):
+    case = make_case("fusen", 6, 5, 12, 0.004, seed=4)
+
+    def poison(sed):
+        c = sed.conc
+        c[3, 2, 5, 6] = np.nan
+        sed.conc = c
+
+    on = _run(case, True, 2, 9, mutate=poison)
+    off = _run(case, False, 2, 9, mutate=poison)
+    assert on["rc"] == off["rc"] == 1 and on["done"] == off["done"] == 1
+
+
+def test_fusion_stream_porosity_uses_single_steps(gpu):
+    """An arbitrary 3-D porosity field (restart) is outside the fused kernel's scope: same results, no pairs."""
+    case = make_case("fusep", 9, 6, 12, 0.004, seed=8)
+
+    def mutate(sed):
+        por = sed.field("porosity") * (1 + 0.05 * np.random.default_rng(1).random((9, 6, 12)))
+        sed.set_porosity(np.minimum(por, 0.95))
+
+    on = _run(case, True, 2, 8, mutate=mutate)
+    off = _run(case, False, 2, 8, mutate=mutate)
+    _same(on, off)
+    assert on["launches"] == off["launches"]
