@@ -120,14 +120,16 @@ pair_kernel(const __grid_constant__ KParams p)
     bool viol1 = false, nan1 = false, viol2 = false, nan2 = false;
     double *g_out = out;
 
-    // one step of one layer: finishes layer kk given its state cc, the state cn of the layer below,
-    // the flux F through its upper interface; returns the new state through `sink`
-    auto step_layer = [&](int kk, const double (&cc)[NV], auto cn, double (&F)[NV], bool &viol, bool &nanf,
-                          auto sink) {
-        const bool has_next = (kk + 1 < K);
+    // one step of one layer: finishes layer kk given its state cc, the state cn of the layer below and
+    // the flux F through its upper interface; the new state goes to `sink`.  HAS_NEXT and CLIP are
+    // compile-time so the steady-state loop body is branch-free and both steps can be interleaved.
+    auto step_layer = [&](auto has_next_tag, auto clip_tag, int kk, const double (&cc)[NV], auto cn,
+                          double (&F)[NV], bool &viol, bool &nanf, auto sink) {
+        constexpr bool HAS_NEXT = decltype(has_next_tag)::value;
+        constexpr bool CLIP = decltype(clip_tag)::value;
         const double porc = por_at(kk);
         double Fn[NV];
-        if (has_next) {
+        if (HAS_NEXT) {
             const double porn = por_at(kk + 1);
             double mDp, mDd;
             interface_coeffs(cpart, cdiss, porc, porn, p.bf[kk + 1], p.rdzc[kk], mDp, mDd);
@@ -156,7 +158,7 @@ pair_kernel(const __grid_constant__ KParams p)
             const double c0 = cc[n];
             double newc = euler_update(dt, rhs, c0);
             if (ADAPTIVE) viol |= violates(p.fac, c0, newc);
-            if (do_clip) {
+            if (CLIP) {
                 nanf |= (newc != newc);
                 const double mn = p.om.minimum[n];
                 newc = (newc < mn) ? mn : newc;
@@ -165,34 +167,53 @@ pair_kernel(const __grid_constant__ KParams p)
         }
     };
 
-    for (int k = 0; k <= K; ++k) {
-        if (k < K) {  // ---- step 1, layer k: state from the ring, result into the c1 window ----------
-            fetch_next();
-            cp_async_wait<RING_STAGES - 2>();
-            const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
-            const uint32_t sn = sbase + (uint32_t)((k + 1) & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
-            const uint32_t wk = wbase + (uint32_t)(k & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
-            double cc[NV];
+    // step 1, layer k: state from the ring, result into the c1 window
+    auto stage_a = [&](auto has_next_tag, auto clip_tag, int k) {
+        fetch_next();
+        cp_async_wait<RING_STAGES - 2>();
+        const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
+        const uint32_t sn = sbase + (uint32_t)((k + 1) & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
+        const uint32_t wk = wbase + (uint32_t)(k & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+        double cc[NV];
 #pragma unroll
-            for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
-            step_layer(k, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA, viol1, nan1,
-                       [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); });
-        }
-        if (k >= 1) {  // ---- step 2, layer j = k-1: state from the c1 window, result to HBM ---------
-            const int j = k - 1;
-            const uint32_t wj = wbase + (uint32_t)(j & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
-            const uint32_t wn = wbase + (uint32_t)((j + 1) & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
-            if (j == 0)
-                top_boundary([&](int n) { return lds64(wj + n * ROW_BYTES); }, por_at(0), FB, true);
-            double cc[NV];
+        for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
+        step_layer(has_next_tag, clip_tag, k, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA, viol1,
+                   nan1, [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); });
+    };
+    // step 2, layer j: state from the c1 window, result to HBM
+    auto stage_b = [&](auto has_next_tag, auto clip_tag, int j) {
+        const uint32_t wj = wbase + (uint32_t)(j & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+        const uint32_t wn = wbase + (uint32_t)((j + 1) & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+        double cc[NV];
 #pragma unroll
-            for (int n = 0; n < NV; ++n) cc[n] = lds64(wj + n * ROW_BYTES);
-            double *go = g_out;
-            step_layer(j, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB, viol2, nan2,
-                       [&](int n, double v) { go[(size_t)n * plane] = v; });
-            g_out += ld;
+        for (int n = 0; n < NV; ++n) cc[n] = lds64(wj + n * ROW_BYTES);
+        double *go = g_out;
+        step_layer(has_next_tag, clip_tag, j, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB, viol2,
+                   nan2, [&](int n, double v) { go[(size_t)n * plane] = v; });
+        g_out += ld;
+    };
+
+    auto sweep = [&](auto clip_tag) {
+        using Y = std::true_type;
+        using N = std::false_type;
+        if (K == 1) {  // degenerate column: both steps see a closed bottom right away
+            stage_a(N{}, clip_tag, 0);
+            top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
+            stage_b(N{}, clip_tag, 0);
+            return;
         }
-    }
+        stage_a(Y{}, clip_tag, 0);
+        top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
+        for (int k = 1; k < K - 1; ++k) {  // steady state: step 1 on layer k, step 2 on layer k-1
+            stage_a(Y{}, clip_tag, k);
+            stage_b(Y{}, clip_tag, k - 1);
+        }
+        stage_a(N{}, clip_tag, K - 1);
+        stage_b(Y{}, clip_tag, K - 2);
+        stage_b(N{}, clip_tag, K - 1);
+    };
+    if (do_clip) sweep(std::true_type{});
+    else sweep(std::false_type{});
     cp_async_wait<0>();
 
     int *wf = p.ctl->flags;
