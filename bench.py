@@ -54,11 +54,11 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def traffic_per_cell():
-    """DRAM bytes per cell-update of the column kernel from the committed ncu capture, or None."""
+def traffic_per_cell(kernel="column_kernel"):
+    """DRAM bytes per cell-update of a stepping kernel from the committed ncu capture, or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return float(json.load(open(p))["dram_bytes_per_cell_update"])
+        return float(json.load(open(p))[kernel]["dram_bytes_per_cell_update"])
     except Exception:
         return None
 
@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fusion", default="on", choices=["on", "off"],
+                    help="speculative two-step kernels (msed_set_step_fusion); results are identical")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -253,6 +255,7 @@ def main():
     sed.init_concentrations()
     sed.set_boundary(bdys, fluxes)
     init_flag_collective(sed)
+    sed.set_step_fusion(args.fusion == "on")
     cells_local = inum * rows * knum * (1.0 if land == 0 else float((mask == 0).mean()))
     cells_total = torch.tensor([cells_local], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -290,14 +293,14 @@ def main():
     if rc != 0:
         raise SystemExit(f"msed_step returned {rc}")
     info = sed.info
-    ms = torch.tensor([e0.elapsed_time(e1), info.kernel_ms], dtype=torch.float64, device="cuda")
+    ms = torch.tensor([e0.elapsed_time(e1), info.kernel_ms, info.fused_ms], dtype=torch.float64, device="cuda")
     counts = torch.tensor([info.kernel_launches, info.subcycle_warnings, info.rhs_evaluations,
-                           info.steps_done], dtype=torch.float64, device="cuda")
+                           info.steps_done, info.fused_pairs], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.MAX)
-    total_ms, kernel_ms = float(ms[0]), float(ms[1])
-    launches, subcycles, rhs_evals, steps_done = (int(x) for x in counts.tolist())
+    total_ms, kernel_ms, fused_ms = float(ms[0]), float(ms[1]), float(ms[2])
+    launches, subcycles, rhs_evals, steps_done, fused_pairs = (int(x) for x in counts.tolist())
     assert steps_done == args.steps
     value = cells_total * args.steps / (total_ms * 1e-3)
 
@@ -342,10 +345,24 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         balg = b_alg(knum)
-        cells_per_launch = cells_total / world              # per GPU, per column-kernel launch
-        avg_launch_s = kernel_ms * 1e-3 / max(rhs_evals, 1)
+        cells_per_gpu = cells_total / world
+        tpc_single, tpc_pair = traffic_per_cell("column_kernel"), traffic_per_cell("pair_kernel")
+        if fused_pairs > 0:
+            # dominant kernel: the fused two-step launch (2 cell-updates per cell-layer per launch)
+            kernel_name = "msed::pair_kernel<OMEXDIA_P, adaptive> (two ode_solver steps per launch)"
+            cells_per_launch = 2.0 * cells_per_gpu
+            avg_launch_s = fused_ms * 1e-3 / fused_pairs
+            tpc = tpc_pair
+            note = ("step fusion: two steps per HBM round trip, so DRAM traffic is about half the per-step "
+                    "algorithmic bytes and frac > 1; the launch is fp64/issue-bound, see achieved_dram and "
+                    "profiles/; --fusion off times the single-step HBM-bound kernel")
+        else:
+            kernel_name = "msed::column_kernel<OMEXDIA_P, OP_ADAPTIVE>"
+            cells_per_launch = cells_per_gpu
+            avg_launch_s = kernel_ms * 1e-3 / max(rhs_evals, 1)
+            tpc = tpc_single
+            note = "single-step kernel: state read once and written once per step"
         achieved = balg * cells_per_launch / avg_launch_s / 1e9
-        tpc = traffic_per_cell()
         line = {
             "metric": "sediment cell-updates/sec", "value": value, "unit": "cell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -353,6 +370,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "grid": [inum, jnum, knum], "rows_per_gpu": rows, "dt_s": DT,
                        "ode_method": METHOD, "sharding": f"j-slabs x{world}, no halo",
+                       "step_fusion": args.fusion,
                        "l2": "per-GPU state >= 5.4 GB >> 126 MB L2 (inputs larger than L2)"
                        if cells_per_launch * 128 > 1e9 else "state fits L2 (launch-latency regime)",
                        "subcycles_in_timed_region": subcycles, "rhs_evaluations": rhs_evals,
@@ -367,9 +385,10 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None if tpc is None else tpc * cells_per_launch,
-                         "kernel": "msed::column_kernel<OMEXDIA_P, OP_ADAPTIVE>",
+                         "achieved_dram": None if tpc is None else tpc * cells_per_launch / avg_launch_s / 1e9,
+                         "kernel": kernel_name, "cell_updates_per_launch": cells_per_launch,
                          "algorithmic_bytes_per_cell_update": balg, "peak_source": peak_src,
-                         "avg_launch_ms": avg_launch_s * 1e3},
+                         "avg_launch_ms": avg_launch_s * 1e3, "fused_pairs": fused_pairs, "note": note},
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_reference(wl, 0, 0, target_seconds=15.0)

@@ -108,6 +108,8 @@ typedef struct msed_step_info {
     int32_t nan_detected;
     double kernel_ms;             /* device time of the stepping kernels (CUDA events) */
     int64_t kernel_launches;      /* launches of this library's kernels in the call */
+    int64_t fused_pairs;          /* committed two-step launches (msed_set_step_fusion), 2 steps each */
+    double fused_ms;              /* part of kernel_ms spent in the fused-pair phase */
 } msed_step_info;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */

@@ -79,7 +79,7 @@ struct msed_handle {
     double bioturbation_eff = 0.0;  // sed%bioturbation (profile 3 overwrites it with 1, driver :623)
     double last_min_dt = (double)1.e20f;  // solver_library.F90:44 (default-real literal)
     int last_min_dt_grid_cell[4] = {-99, -99, -99, -99};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     cudaStream_t copy_stream = nullptr;           // PCIe traffic of msed_run_exchange
     cudaEvent_t ev_pool[2 * 16] = {};             // per-chunk H2D-done / compute-done events
     int exchange_chunks = 0;                      // 0 = choose from the tile size
@@ -411,6 +411,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         launches += 1;
     }
     const long long singles_planned = nsteps - 2 * npairs;
+    CUDA_TRY(h, cudaEventRecord(h->ev_mid, h->stream));
 
     long long remaining = singles_planned, issued = 0;
     const long long max_batch = 256;
@@ -479,8 +480,9 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     }
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_TRY(h, cudaEventSynchronize(h->ev1));
-    float ms = 0.f;
+    float ms = 0.f, ms_pairs = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms_pairs, h->ev0, h->ev_mid));
     if (nsteps == 0) {
         CUDA_TRY(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -519,6 +521,8 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         info->nan_detected = r.nan_detected;
         info->kernel_ms = ms;
         info->kernel_launches = launches;
+        info->fused_pairs = (npairs > 0 && r.pair_failures == 0) ? npairs : 0;
+        info->fused_ms = npairs > 0 ? ms_pairs : 0.0;
     }
     return r.nan_detected ? MSED_NAN_DETECTED : MSED_OK;
 }
@@ -659,6 +663,7 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (auto &e : h->ev_pool) CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreate(&h->ev0));
+    CREATE_TRY(cudaEventCreate(&h->ev_mid));
     CREATE_TRY(cudaEventCreate(&h->ev1));
     const size_t state_bytes = (size_t)NV * K * h->ld * sizeof(double);
     CREATE_TRY(cudaMalloc(&h->buf[0], state_bytes));
@@ -707,6 +712,7 @@ int msed_destroy(msed_handle *h)
     for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev_mid) cudaEventDestroy(h->ev_mid);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1038,6 +1044,8 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
             info->nan_detected |= b.nan_detected;
             info->kernel_ms += b.kernel_ms;
             info->kernel_launches += b.kernel_launches;
+            info->fused_pairs += b.fused_pairs;
+            info->fused_ms += b.fused_ms;
         }
     }
     return rc;
@@ -1154,6 +1162,8 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
             info->nan_detected |= b.nan_detected;
             info->kernel_ms += b.kernel_ms;
             info->kernel_launches += b.kernel_launches;
+            info->fused_pairs += b.fused_pairs;
+            info->fused_ms += b.fused_ms;
         }
     }
     return rc;
@@ -1253,6 +1263,8 @@ int msed_coupled_run(msed_handle *h, double dt, int method, double coupling_seco
         acc.nan_detected |= one.nan_detected;
         acc.kernel_ms += one.kernel_ms;
         acc.kernel_launches += one.kernel_launches + 2;
+        acc.fused_pairs += one.fused_pairs;
+        acc.fused_ms += one.fused_ms;
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (info) *info = acc;

@@ -51,6 +51,8 @@ module msed_b200
     integer(c_int32_t) :: nan_detected
     real(c_double)     :: kernel_ms
     integer(c_int64_t) :: kernel_launches
+    integer(c_int64_t) :: fused_pairs
+    real(c_double)     :: fused_ms
   end type
 
   interface
