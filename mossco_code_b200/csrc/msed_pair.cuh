@@ -123,21 +123,32 @@ pair_kernel(const __grid_constant__ KParams p)
     // one step of one layer: finishes layer kk given its state cc, the state cn of the layer below and
     // the flux F through its upper interface; the new state goes to `sink`.  HAS_NEXT and CLIP are
     // compile-time so the steady-state loop body is branch-free and both steps can be interleaved.
-    auto step_layer = [&](auto has_next_tag, auto clip_tag, int kk, const double (&cc)[NV], auto cn,
+    // state-independent coefficients of layer kk and of its lower interface: both steps of the pair
+    // need the same ones (step 2 one iteration later), so they are computed once
+    struct LayerCoef { double porc, porn, mDp, mDd, rpd; };
+    auto make_coef = [&](auto has_next_tag, int kk) -> LayerCoef {
+        LayerCoef lc;
+        lc.porc = por_at(kk);
+        lc.porn = lc.mDp = lc.mDd = 0.0;
+        if (decltype(has_next_tag)::value) {
+            lc.porn = por_at(kk + 1);
+            interface_coeffs(cpart, cdiss, lc.porc, lc.porn, p.bf[kk + 1], p.rdzc[kk], lc.mDp, lc.mDd);
+        }
+        lc.rpd = fast_rcp(lc.porc * p.dz[kk]);
+        return lc;
+    };
+
+    auto step_layer = [&](auto has_next_tag, auto clip_tag, const LayerCoef &lc, const double (&cc)[NV], auto cn,
                           double (&F)[NV], bool &viol, bool &nanf, auto sink) {
         constexpr bool HAS_NEXT = decltype(has_next_tag)::value;
         constexpr bool CLIP = decltype(clip_tag)::value;
-        const double porc = por_at(kk);
         double Fn[NV];
         if (HAS_NEXT) {
-            const double porn = por_at(kk + 1);
-            double mDp, mDd;
-            interface_coeffs(cpart, cdiss, porc, porn, p.bf[kk + 1], p.rdzc[kk], mDp, mDd);
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
                 const double c = cn(n);
-                if (n < NPART) Fn[n] = flux_particulate(mDp, c, porn, cc[n], porc);
-                else Fn[n] = flux_dissolved(mDd, c, cc[n]);
+                if (n < NPART) Fn[n] = flux_particulate(lc.mDp, c, lc.porn, cc[n], lc.porc);
+                else Fn[n] = flux_dissolved(lc.mDd, c, cc[n]);
             }
         } else {
 #pragma unroll
@@ -150,10 +161,9 @@ pair_kernel(const __grid_constant__ KParams p)
 #pragma unroll
             for (int n = 0; n < NV; ++n) r[n] = 0.0;
         }
-        const double rpd = fast_rcp(porc * p.dz[kk]);
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
-            const double rhs = layer_rhs(F[n], Fn[n], rpd, r[n]);
+            const double rhs = layer_rhs(F[n], Fn[n], lc.rpd, r[n]);
             F[n] = Fn[n];
             const double c0 = cc[n];
             double newc = euler_update(dt, rhs, c0);
@@ -167,28 +177,31 @@ pair_kernel(const __grid_constant__ KParams p)
         }
     };
 
-    // step 1, layer k: state from the ring, result into the c1 window
-    auto stage_a = [&](auto has_next_tag, auto clip_tag, int k) {
+    LayerCoef coef_prev;  // coefficients of the layer step 2 is about to process (made by step 1)
+    // step 1, layer k: state from the ring, result into the c1 window; returns the layer coefficients
+    auto stage_a = [&](auto has_next_tag, auto clip_tag, int k) -> LayerCoef {
         fetch_next();
         cp_async_wait<RING_STAGES - 2>();
         const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
         const uint32_t sn = sbase + (uint32_t)((k + 1) & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
         const uint32_t wk = wbase + (uint32_t)(k & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+        const LayerCoef lc = make_coef(has_next_tag, k);
         double cc[NV];
 #pragma unroll
         for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
-        step_layer(has_next_tag, clip_tag, k, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA, viol1,
+        step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA, viol1,
                    nan1, [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); });
+        return lc;
     };
     // step 2, layer j: state from the c1 window, result to HBM
-    auto stage_b = [&](auto has_next_tag, auto clip_tag, int j) {
+    auto stage_b = [&](auto has_next_tag, auto clip_tag, int j, const LayerCoef &lc) {
         const uint32_t wj = wbase + (uint32_t)(j & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
         const uint32_t wn = wbase + (uint32_t)((j + 1) & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
         double cc[NV];
 #pragma unroll
         for (int n = 0; n < NV; ++n) cc[n] = lds64(wj + n * ROW_BYTES);
         double *go = g_out;
-        step_layer(has_next_tag, clip_tag, j, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB, viol2,
+        step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB, viol2,
                    nan2, [&](int n, double v) { go[(size_t)n * plane] = v; });
         g_out += ld;
     };
@@ -197,20 +210,21 @@ pair_kernel(const __grid_constant__ KParams p)
         using Y = std::true_type;
         using N = std::false_type;
         if (K == 1) {  // degenerate column: both steps see a closed bottom right away
-            stage_a(N{}, clip_tag, 0);
+            coef_prev = stage_a(N{}, clip_tag, 0);
             top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
-            stage_b(N{}, clip_tag, 0);
+            stage_b(N{}, clip_tag, 0, coef_prev);
             return;
         }
-        stage_a(Y{}, clip_tag, 0);
+        coef_prev = stage_a(Y{}, clip_tag, 0);
         top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
         for (int k = 1; k < K - 1; ++k) {  // steady state: step 1 on layer k, step 2 on layer k-1
-            stage_a(Y{}, clip_tag, k);
-            stage_b(Y{}, clip_tag, k - 1);
+            const LayerCoef lc = stage_a(Y{}, clip_tag, k);
+            stage_b(Y{}, clip_tag, k - 1, coef_prev);
+            coef_prev = lc;
         }
-        stage_a(N{}, clip_tag, K - 1);
-        stage_b(Y{}, clip_tag, K - 2);
-        stage_b(N{}, clip_tag, K - 1);
+        const LayerCoef last = stage_a(N{}, clip_tag, K - 1);
+        stage_b(Y{}, clip_tag, K - 2, coef_prev);
+        stage_b(N{}, clip_tag, K - 1, last);
     };
     if (do_clip) sweep(std::true_type{});
     else sweep(std::false_type{});
