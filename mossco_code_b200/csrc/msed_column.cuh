@@ -48,6 +48,14 @@ __device__ __forceinline__ double fast_rcp(double x)
     return y;
 }
 
+// two reciprocals for the price of one Newton refinement: 1/a = b/(a*b), 1/b = a/(a*b)
+__device__ __forceinline__ void fast_rcp2(double a, double b, double &ra, double &rb)
+{
+    const double y = fast_rcp(a * b);
+    ra = y * b;
+    rb = y * a;
+}
+
 // hzg_omexdia_p local rates for one cell: SURVEY.md Appendix B (frozen project spec; the FABM
 // source is not part of the reference tree).  fT is the per-column Arrhenius factor; every a/b of
 // the spec is evaluated as a*fast_rcp(b).
@@ -59,12 +67,10 @@ __device__ __forceinline__ void omexdia_rates(const OmexDev &m, const double (&c
     const double relaxO2 = 0.04;
 
     const double r1 = fast_rcp(oxy + m.ksO2oxic + relaxO2 * (nh3 + odu));
-    const double r2 = fast_rcp(oxy + m.kinO2denit);
-    const double r3 = fast_rcp(no3 + m.ksNO3denit);
-    const double r4 = fast_rcp(oxy + m.kinO2anox);
-    const double r5 = fast_rcp(no3 + m.kinNO3anox);
-    const double r7 = fast_rcp(oxy + m.ksO2nitri + relaxO2 * (ldetC + odu));
-    const double r8 = fast_rcp(oxy + m.ksO2oduox + relaxO2 * (nh3 + ldetC));
+    double r2, r3, r4, r5, r7, r8;  // paired: every denominator is a positive half-saturation sum
+    fast_rcp2(oxy + m.kinO2denit, oxy + m.kinO2anox, r2, r4);
+    fast_rcp2(no3 + m.ksNO3denit, no3 + m.kinNO3anox, r3, r5);
+    fast_rcp2(oxy + m.ksO2nitri + relaxO2 * (ldetC + odu), oxy + m.ksO2oduox + relaxO2 * (nh3 + ldetC), r7, r8);
 
     const double Oxicminlim = oxy * r1;
     const double Denitrilim = (1.0 - oxy * r2) * no3 * r3;
