@@ -281,10 +281,40 @@ cudaError_t launch_pair(const msed_handle *h, int method, const KParams &p)
     return cudaGetLastError();
 }
 
+// one launch = two chained Runge-Kutta stages (msed_rkpair.cuh); which = 0 for stages 1+2, 1 for 3+4
+cudaError_t launch_rk_pair(const msed_handle *h, int method, int which, const KParams &p)
+{
+    const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
+    const int pair = (method == MSED_RUNGE_KUTTA_4 ? RK4_12 : RK38_12) + which;
+#define MSED_RKP(MODEL, PAIR) \
+    case PAIR: rk_pair_kernel<MODEL, PAIR><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p); break;
+    if (h->cfg.model == MSED_MODEL_OMEXDIA_P) {
+        switch (pair) {
+            MSED_RKP(MSED_MODEL_OMEXDIA_P, RK4_12) MSED_RKP(MSED_MODEL_OMEXDIA_P, RK4_34)
+            MSED_RKP(MSED_MODEL_OMEXDIA_P, RK38_12) MSED_RKP(MSED_MODEL_OMEXDIA_P, RK38_34)
+        }
+    } else {
+        switch (pair) {
+            MSED_RKP(MSED_MODEL_NONE, RK4_12) MSED_RKP(MSED_MODEL_NONE, RK4_34)
+            MSED_RKP(MSED_MODEL_NONE, RK38_12) MSED_RKP(MSED_MODEL_NONE, RK38_34)
+        }
+    }
+#undef MSED_RKP
+    return cudaGetLastError();
+}
+
 cudaError_t enable_pair_smem()
 {
     cudaError_t e;
     const int bytes = (int)PAIR_SMEM_BYTES;
+#define MSED_RKP_ATTR(MODEL, PAIR) \
+    if ((e = cudaFuncSetAttribute(rk_pair_kernel<MODEL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  bytes)) != cudaSuccess) return e;
+    MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK4_12) MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK4_34)
+    MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK38_12) MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK38_34)
+    MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_34)
+    MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_34)
+#undef MSED_RKP_ATTR
     if ((e = cudaFuncSetAttribute(pair_kernel<MSED_MODEL_OMEXDIA_P, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(pair_kernel<MSED_MODEL_OMEXDIA_P, false>,
@@ -384,10 +414,14 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
 
     // ---- fused pairs of steps first (msed_pair.cuh): speculative, nothing is committed on failure --
     const bool single_attempt = (method == MSED_EULER || method == MSED_ADAPTIVE_EULER);
+    // the configurations the fused kernels cover (msed_pair.cuh, msed_rkpair.cuh); the rest takes
+    // one launch per attempt / per stage
+    const bool fusable = h->step_fusion &&
+                         (h->cfg.model == MSED_MODEL_OMEXDIA_P || h->cfg.model == MSED_MODEL_NONE) &&
+                         h->cfg.bioturbation_profile != 3 && !h->cfg.distributed_pom_flux && h->por_mode != 0;
+    const bool rk_fused = fusable && !single_attempt;
     long long npairs = 0;
-    if (h->step_fusion && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 3 &&
-        (h->cfg.model == MSED_MODEL_OMEXDIA_P || h->cfg.model == MSED_MODEL_NONE) &&
-        h->cfg.bioturbation_profile != 3 && !h->cfg.distributed_pom_flux && h->por_mode != 0)
+    if (fusable && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 3)
         npairs = (nsteps - 1) / 2;  // the last step is always a single one (diagnostics, chunked export)
     bool first_pending = plan && plan->first && single_attempt;
     for (long long q = 0; q < npairs; ++q) {
@@ -449,6 +483,10 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
             } else if (method == MSED_ADAPTIVE_EULER) {
                 CUDA_TRY(h, launch_column(h, OP_ADAPTIVE, p));
                 launches += 1;
+            } else if (rk_fused) {
+                CUDA_TRY(h, launch_rk_pair(h, method, 0, p));
+                CUDA_TRY(h, launch_rk_pair(h, method, 1, p));
+                launches += 2;
             } else {
                 const int first = (method == MSED_RUNGE_KUTTA_4) ? OP_RK4_S1 : OP_RK38_S1;
                 for (int st = 0; st < 4; ++st) CUDA_TRY(h, launch_column(h, first + st, p));

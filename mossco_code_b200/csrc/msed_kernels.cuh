@@ -100,6 +100,7 @@ struct KParams {
 #include "msed_column.cuh"
 // two Euler / adaptive-Euler steps per pass over HBM (speculative, rollback-free)
 #include "msed_pair.cuh"
+#include "msed_rkpair.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // step-loop controller: the scalar part of ode_solver (:108,:126-139) and of the component

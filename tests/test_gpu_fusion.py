@@ -109,3 +109,55 @@ def test_fusion_stream_porosity_uses_single_steps(gpu):
     off = _run(case, False, 2, 8, mutate=mutate)
     _same(on, off)
     assert on["launches"] == off["launches"]
+
+
+# ---- Runge-Kutta stage pairs (msed_rkpair.cuh) --------------------------------------------------------
+@pytest.mark.parametrize("method", [1, 3])
+@pytest.mark.parametrize("knum", [2, 3, 4, 20])
+def test_rk_stage_fusion_is_bit_identical(gpu, oracle, method, knum):
+    case = make_case("rkf", 37, 21, knum, 0.003, seed=55 + knum, land_fraction=0.2, smooth_temperature=True)
+    on = _run(case, True, method, 5, calls=2)
+    off = _run(case, False, method, 5, calls=2)
+    _same(on, off)
+    assert on["launches"] < off["launches"]                 # two launches per step instead of four
+    ref = oracle.OracleSediment(37, 21, knum, 0.003, mask2d=case.mask, dt_min=1.0)
+    ref.init_concentrations(); ref.set_boundary(case.bdys, case.fluxes)
+    assert ref.step(DT, method, 10) == 0
+    wet = case.mask == 0
+    assert rel_err(on["conc"][wet], ref.conc[wet]) <= 1e-11
+
+
+@pytest.mark.parametrize("method", [1, 3])
+@pytest.mark.parametrize("kw", [dict(bcup_dissolved_variables=1), dict(bioturbation_profile=2),
+                                dict(bcup_dissolved_variables=0),
+                                dict(minimum=[1., 2., 3., 0.5, 30., 1., 2., 150.]), dict(model=1)])
+def test_rk_stage_fusion_variants(gpu, method, kw):
+    case = make_case("rkfv", 19, 9, 15, 0.004, seed=9)
+
+    def mutate(sed):
+        if kw.get("bcup_dissolved_variables") == 1:
+            fl = case.fluxes.copy(); fl[:, :, 3:] = 1e-6 * (1 + np.arange(5))
+            sed.set_boundary(None, fl)
+        sed.update_porosity(0.5 + 0.3 * np.random.default_rng(2).random((19, 9)))   # porosity mode 2
+
+    _same(_run(case, True, method, 6, mutate=mutate, **kw), _run(case, False, method, 6, mutate=mutate, **kw))
+
+
+@pytest.mark.parametrize("method", [1, 3])
+def test_rk_stage_fusion_nan_stops_at_the_same_step(gpu, method):
+    case = make_case("rkfn", 12, 8, 15, 0.004, seed=3)
+    kw = dict(rnit=5.0e5, rODUox=5.0e5)                     # explicit RK blows up within a few steps
+    on = _run(case, True, method, 40, **kw)
+    off = _run(case, False, method, 40, **kw)
+    assert on["rc"] == off["rc"] and on["done"] == off["done"]
+    assert np.array_equal(on["conc"], off["conc"], equal_nan=True)
+
+
+@pytest.mark.parametrize("method", [1, 3])
+def test_rk_unfusable_configs_take_the_staged_path(gpu, method):
+    case = make_case("rkfs", 12, 8, 15, 0.004, seed=4)
+    for kw in (dict(bioturbation_profile=3), dict(distributed_pom_flux=1)):
+        on = _run(case, True, method, 4, **kw)
+        off = _run(case, False, method, 4, **kw)
+        _same(on, off)
+        assert on["launches"] == off["launches"]
