@@ -204,6 +204,30 @@ class FabmSedimentComponent:
             raise ComponentError(rc, "check_domain failed after restart")
         return ESMF_SUCCESS
 
+    # ---- restart files: what netcdf_component writes from the export state and netcdf_input_component
+    # ---- feeds to ReadRestart, in mossco_netcdf.F90's layout (see soil_netcdf.py) -----------------
+    def write_restart_file(self, path: str, time_seconds: float = None, *, append: bool = False,
+                           with_diagnostics: bool = False):
+        from . import soil_netcdf
+        export: State = {}
+        self._fill_exports(export, with_3d=True)
+        keep = {f"{v}_in_soil" for v in VARIABLE_NAMES} | {"porosity_in_soil"}
+        if with_diagnostics:
+            keep = set(export)
+        fields = {k: v for k, v in export.items() if k in keep}
+        units = {f"{v}_in_soil": "mmol m-3" for v in VARIABLE_NAMES}
+        units.update({f"{v}_upward_flux_at_soil_surface": "mmol m-2 s-1" for v in VARIABLE_NAMES})
+        t = self.clock_seconds if time_seconds is None else time_seconds
+        soil_netcdf.write_fields(path, fields, t, units=units, append=append)
+        return ESMF_SUCCESS
+
+    def read_restart_file(self, path: str, record: int = -1):
+        from . import soil_netcdf
+        fields, t = soil_netcdf.read_fields(path, record)
+        rc = self.read_restart(fields, {})
+        self.clock_seconds = t
+        return rc
+
     # ---- Run (:1493-1829) -------------------------------------------------------------------------
     def run(self, import_state: State, export_state: State, clock=None, *, run_seconds: float = None):
         """One coupling interval.  ``clock`` may be a dict with 'currTime'/'stopTime' in seconds."""

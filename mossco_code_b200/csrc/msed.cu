@@ -287,7 +287,7 @@ cudaError_t launch_rk_pair(const msed_handle *h, int method, int which, const KP
     const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
     const int pair = (method == MSED_RUNGE_KUTTA_4 ? RK4_12 : RK38_12) + which;
 #define MSED_RKP(MODEL, PAIR) \
-    case PAIR: rk_pair_kernel<MODEL, PAIR><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p); break;
+    case PAIR: rk_pair_kernel<MODEL, PAIR><<<grid, block, rk_pair_smem(PAIR), h->stream>>>(p); break;
     if (h->cfg.model == MSED_MODEL_OMEXDIA_P) {
         switch (pair) {
             MSED_RKP(MSED_MODEL_OMEXDIA_P, RK4_12) MSED_RKP(MSED_MODEL_OMEXDIA_P, RK4_34)
@@ -309,7 +309,7 @@ cudaError_t enable_pair_smem()
     const int bytes = (int)PAIR_SMEM_BYTES;
 #define MSED_RKP_ATTR(MODEL, PAIR) \
     if ((e = cudaFuncSetAttribute(rk_pair_kernel<MODEL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  bytes)) != cudaSuccess) return e;
+                                  (int)rk_pair_smem(PAIR))) != cudaSuccess) return e;
     MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK4_12) MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK4_34)
     MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK38_12) MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK38_34)
     MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_34)

@@ -14,6 +14,17 @@
 
 enum RkPair : int { RK4_12 = 0, RK4_34, RK38_12, RK38_34 };
 
+// Shared memory of one CTA: a prefetch ring whose stage holds everything stage A reads of one layer
+// (the state it evaluates; for stages 3+4 also the base state and the accumulators), and a two-layer
+// window for the state handed from stage A to stage B.
+constexpr int RK_WIN = 2;
+__host__ __device__ constexpr int rk_ring_rows(int pair) { return (pair == RK4_12 || pair == RK38_12) ? NV : (pair == RK4_34 ? 3 * NV : 4 * NV); }
+__host__ __device__ constexpr int rk_ring_stages(int pair) { return pair == RK38_34 ? 3 : 4; }   // 2 CTAs/SM must fit in 227 KB
+__host__ __device__ constexpr size_t rk_pair_smem(int pair)
+{
+    return (size_t)(rk_ring_rows(pair) * rk_ring_stages(pair) + RK_WIN * NV) * ROW_BYTES;
+}
+
 #ifndef MSED_RKPAIR_MIN_BLOCKS
 #define MSED_RKPAIR_MIN_BLOCKS 2
 #endif
@@ -49,26 +60,34 @@ rk_pair_kernel(const __grid_constant__ KParams p)
     double *out = (FIRST ? p.buf[1 - cur] : p.buf[cur]) + col;   // c1, or conc itself for the final stage
     double *aux1 = p.aux1 + col, *aux2 = p.aux2 + col;
 
+    constexpr int STAGES = rk_ring_stages(PAIR);
+    constexpr uint32_t STAGE_B = (uint32_t)rk_ring_rows(PAIR) * ROW_BYTES;
+    constexpr uint32_t WIN_B = NV * ROW_BYTES;
     const uint32_t sbase = smem_u32(ring) + threadIdx.x * 8u;
-    const uint32_t wbase = sbase + PAIR_RING_BYTES;
-    const double *g_in = in;
+    const uint32_t wbase = sbase + STAGES * STAGE_B;
+    const double *g_in = in, *g_fb = base, *g_f1 = aux1, *g_f2 = aux2;   // next layer to fetch
     int k_fetch = 0;
     auto fetch_next = [&]() {
         if (k_fetch < K) {
-            const uint32_t sa = sbase + (uint32_t)(k_fetch & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
-            const double *g = g_in;
+            const uint32_t sa = sbase + (uint32_t)(k_fetch % STAGES) * STAGE_B;
+            const double *g = g_in, *gb = g_fb, *g1 = g_f1, *g2 = g_f2;
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
                 cp_async8(sa + n * ROW_BYTES, g);
-                g += plane;
+                if (!FIRST) {
+                    cp_async8(sa + (NV + n) * ROW_BYTES, gb);
+                    cp_async8(sa + (2 * NV + n) * ROW_BYTES, g1);
+                    if (IS38) cp_async8(sa + (3 * NV + n) * ROW_BYTES, g2);
+                }
+                g += plane; gb += plane; g1 += plane; g2 += plane;
             }
-            g_in += ld;
+            g_in += ld; g_fb += ld; g_f1 += ld; g_f2 += ld;
         }
         ++k_fetch;
         cp_async_commit();
     };
 #pragma unroll
-    for (int s = 0; s < RING_STAGES - 1; ++s) fetch_next();
+    for (int s = 0; s < STAGES - 1; ++s) fetch_next();
 
     const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
     auto por_at = [&](int kk) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
@@ -141,7 +160,7 @@ rk_pair_kernel(const __grid_constant__ KParams p)
         }
     };
 
-    cp_async_wait<RING_STAGES - 2>();
+    cp_async_wait<STAGES - 2>();
     double FA[NV], FB[NV];
     top_boundary([&](int n) { return lds64(sbase + n * ROW_BYTES); }, por_at(0), FA, false);
 
@@ -150,35 +169,26 @@ rk_pair_kernel(const __grid_constant__ KParams p)
     double carry_base[NV], carry_x[NV];
     LayerCoef coef_prev;
     bool nanf = false;
-    const double *g_base = base;
-    double *g_a1 = aux1, *g_a2 = aux2;   // read position of stage A (layer k)
     double *g_out = out, *g_w1 = aux1, *g_w2 = aux2;   // write position of stage B (layer j)
     double *g_c1 = p.buf[1 - cur] + col;               // stage-3 state of layer k (keep_c1 only)
 
     // ---- stage A on layer k -----------------------------------------------------------------------
     auto stage_a = [&](auto has_next_tag, int k, double (&baseA)[NV], double (&xA)[NV]) -> LayerCoef {
         fetch_next();
-        cp_async_wait<RING_STAGES - 2>();
-        const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
-        const uint32_t sn = sbase + (uint32_t)((k + 1) & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
-        const uint32_t wk = wbase + (uint32_t)(k & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+        cp_async_wait<STAGES - 2>();
+        const uint32_t sc = sbase + (uint32_t)(k % STAGES) * STAGE_B;
+        const uint32_t sn = sbase + (uint32_t)((k + 1) % STAGES) * STAGE_B;
+        const uint32_t wk = wbase + (uint32_t)(k & (RK_WIN - 1)) * WIN_B;
         double cc[NV], a1[NV], a2[NV];
 #pragma unroll
-        for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
-        if (FIRST) {
-#pragma unroll
-            for (int n = 0; n < NV; ++n) baseA[n] = cc[n];   // stage 1 evaluates the base state itself
-        } else {
-            const double *g = g_base;
-#pragma unroll
-            for (int n = 0; n < NV; ++n) { baseA[n] = *g; g += plane; }
-            g = g_a1;
-#pragma unroll
-            for (int n = 0; n < NV; ++n) { a1[n] = *g; g += plane; }
-            if (IS38) {
-                g = g_a2;
-#pragma unroll
-                for (int n = 0; n < NV; ++n) { a2[n] = *g; g += plane; }
+        for (int n = 0; n < NV; ++n) {
+            cc[n] = lds64(sc + n * ROW_BYTES);
+            if (FIRST) {
+                baseA[n] = cc[n];                        // stage 1 evaluates the base state itself
+            } else {
+                baseA[n] = lds64(sc + (NV + n) * ROW_BYTES);
+                a1[n] = lds64(sc + (2 * NV + n) * ROW_BYTES);
+                if (IS38) a2[n] = lds64(sc + (3 * NV + n) * ROW_BYTES);
             }
         }
         const LayerCoef lc = make_coef(has_next_tag, k);
@@ -204,15 +214,14 @@ rk_pair_kernel(const __grid_constant__ KParams p)
             if (!FIRST && keep_c1) g_c1[(size_t)n * plane] = yb;
         }
         g_c1 += ld;
-        g_base += ld; g_a1 += ld; g_a2 += ld;
         return lc;
     };
 
     // ---- stage B on layer j (one layer behind) ------------------------------------------------------
     auto stage_b = [&](auto has_next_tag, auto clip_tag, int j, const LayerCoef &lc, const double (&baseB)[NV],
                        const double (&xB)[NV]) {
-        const uint32_t wj = wbase + (uint32_t)(j & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
-        const uint32_t wn = wbase + (uint32_t)((j + 1) & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+        const uint32_t wj = wbase + (uint32_t)(j & (RK_WIN - 1)) * WIN_B;
+        const uint32_t wn = wbase + (uint32_t)((j + 1) & (RK_WIN - 1)) * WIN_B;
         if (j == 0) top_boundary([&](int n) { return lds64(wj + n * ROW_BYTES); }, por_at(0), FB, true);
         double cc[NV], rhs[NV];
 #pragma unroll

@@ -119,6 +119,36 @@ def test_component_restart_roundtrip(gpu):
     a.finalize(); b.finalize()
 
 
+def test_component_restart_through_netcdf_file(gpu, tmp_path):
+    """The same through a file in mossco_netcdf.F90's layout (soil_netcdf.py): doubles survive bit for bit."""
+    from scipy.io import netcdf_file
+    from mossco_code_b200.component import FabmSedimentComponent
+    case = make_case("rstf", 6, 5, 12, 0.004, seed=9, land_fraction=0.2)
+    nml = dict(numlayers=12, dzmin=0.004, dt=360.0, dt_min=1.0, ode_method=2)
+    a, b = FabmSedimentComponent(), FabmSedimentComponent()
+    ia, ea, ib, eb = {}, {}, {}, {}
+    a.initialize_p1(ia, ea, grid_shape=(6, 5), grid_mask=1 - case.mask, run_nml=nml)
+    ia.update(_import_state(case, None))
+    a.run(ia, ea, run_seconds=3600.0)
+    path = str(tmp_path / "restart_soil.nc")
+    a.write_restart_file(path, 3600.0)
+    a.run(ia, ea, run_seconds=3600.0)
+    a.write_restart_file(path, 7200.0, append=True)
+    nc = netcdf_file(path, "r", mmap=False)
+    v = nc.variables["dissolved_oxygen_in_soil"]
+    assert v.dimensions == ("time", "ungridded00012", "sedimentFluxes_2_O", "sedimentFluxes_1_O")
+    assert v.shape == (2, 12, 5, 6) and v.missing_value == -1.0e30
+    nc.close()
+    b.initialize_p1(ib, eb, grid_shape=(6, 5), grid_mask=1 - case.mask, run_nml=nml)
+    b.read_restart_file(path)                            # last record
+    assert np.array_equal(b.sed.conc, a.sed.conc)
+    ib.update(_import_state(case, None))
+    a.run(ia, ea, run_seconds=3600.0)
+    b.run(ib, eb, run_seconds=3600.0)
+    assert np.array_equal(b.sed.conc, a.sed.conc)
+    a.finalize(); b.finalize()
+
+
 def test_component_presimulation(gpu, oracle):
     """presimulation_years > 0: 1-D spin-up broadcast to every wet column (:557-632)."""
     from mossco_code_b200.component import FabmSedimentComponent
