@@ -199,6 +199,14 @@ constexpr size_t COLUMN_SMEM_BYTES = (size_t)RING_STAGES * STAGE_BYTES;
 // ---------------------------------------------------------------------------------------------
 // STREAM_POR: porosity is an arbitrary 3-D field streamed through the ring (KParams::por_mode 0);
 // otherwise it is por_surf * portab[k] (modes 1 and 2, see below), which costs no HBM traffic.
+#define MSED_PRAGMA_STR(x) _Pragma(#x)
+#define MSED_UNROLL_PRAGMA(n) MSED_PRAGMA_STR(unroll n)
+#ifdef MSED_COL_UNROLL
+#define MSED_COL_UNROLL_PRAGMA MSED_UNROLL_PRAGMA(MSED_COL_UNROLL)
+#else
+#define MSED_COL_UNROLL_PRAGMA
+#endif
+
 template <int MODEL, int OP, bool PROFILE3, bool STREAM_POR>
 __global__ void __launch_bounds__(COL_BLOCK, COL_MIN_BLOCKS)
 column_kernel(const __grid_constant__ KParams p)
@@ -364,6 +372,7 @@ column_kernel(const __grid_constant__ KParams p)
     double *g_a1 = aux1, *g_a2 = aux2;
     double *g_rhs = p.rhs_out + col;
 
+    MSED_COL_UNROLL_PRAGMA
     for (int k = 0; k < K; ++k) {
         const bool has_next = (k + 1 < K);
         fetch_next();                          // layer k+RING_STAGES-1 -> the slot layer k-1 just left

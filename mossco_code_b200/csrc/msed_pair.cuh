@@ -20,6 +20,10 @@
 // Restricted to the hot configuration: bcup_particulate = 1 (no distributed POM flux cascade),
 // bioturbation_profile != 3, closed-form porosity (KParams::por_mode 1 or 2).
 
+#ifndef MSED_PAIR_UNROLL
+#define MSED_PAIR_UNROLL 2
+#endif
+#define MSED_PAIR_UNROLL_PRAGMA MSED_UNROLL_PRAGMA(MSED_PAIR_UNROLL)
 constexpr int PAIR_WIN = 4;  // c1 window slots (3 live layers: j, j+1 and the one being written)
 constexpr uint32_t PAIR_STAGE_BYTES = NV * ROW_BYTES;                    // input ring: 8 rows per layer
 constexpr uint32_t PAIR_RING_BYTES = RING_STAGES * PAIR_STAGE_BYTES;
@@ -217,6 +221,7 @@ pair_kernel(const __grid_constant__ KParams p)
         }
         coef_prev = stage_a(Y{}, clip_tag, 0);
         top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
+        MSED_PAIR_UNROLL_PRAGMA
         for (int k = 1; k < K - 1; ++k) {  // steady state: step 1 on layer k, step 2 on layer k-1
             const LayerCoef lc = stage_a(Y{}, clip_tag, k);
             stage_b(Y{}, clip_tag, k - 1, coef_prev);

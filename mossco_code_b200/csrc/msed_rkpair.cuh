@@ -29,6 +29,12 @@ __host__ __device__ constexpr size_t rk_pair_smem(int pair)
 #define MSED_RKPAIR_MIN_BLOCKS 2
 #endif
 
+#ifdef MSED_RKPAIR_UNROLL
+#define MSED_RKPAIR_UNROLL_PRAGMA MSED_UNROLL_PRAGMA(MSED_RKPAIR_UNROLL)
+#else
+#define MSED_RKPAIR_UNROLL_PRAGMA
+#endif
+
 template <int MODEL, int PAIR>
 __global__ void __launch_bounds__(COL_BLOCK, MSED_RKPAIR_MIN_BLOCKS)
 rk_pair_kernel(const __grid_constant__ KParams p)
@@ -263,6 +269,7 @@ rk_pair_kernel(const __grid_constant__ KParams p)
             return;
         }
         coef_prev = stage_a(Y{}, 0, carry_base, carry_x);
+        MSED_RKPAIR_UNROLL_PRAGMA
         for (int k = 1; k < K - 1; ++k) {  // steady state: stage A on layer k, stage B on layer k-1
             double nb[NV], nx[NV];
             const LayerCoef lc = stage_a(Y{}, k, nb, nx);

@@ -20,6 +20,7 @@ ap.add_argument("--method", type=int, default=2)
 ap.add_argument("--spin", type=int, default=10)
 ap.add_argument("--perturb", type=float, default=0.1)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--fusion", choices=["on", "off"], default="on")
 a = ap.parse_args()
 dzmin = 0.0015 if a.knum == 40 else 0.002
 t0 = time.time()
@@ -27,6 +28,7 @@ case = make_case("qb", a.inum, a.jnum, a.knum, dzmin, seed=4096, perturb=a.pertu
 cfg = default_config(inum=a.inum, jnum=a.jnum, knum=a.knum, dzmin=dzmin, dt_min=1.0)
 sed = SedimentDriver(cfg)
 sed.init_concentrations()
+sed.set_step_fusion(a.fusion == "on")
 sed.set_boundary(case.bdys, case.fluxes)
 print(f"setup {time.time()-t0:.1f}s")
 sed.step(360.0, a.method, a.spin)
