@@ -35,17 +35,29 @@ __device__ __forceinline__ double lds64(uint32_t addr)
     return v;
 }
 
-// 1/x to within ~1 ulp: MUFU.RCP64H seed (>= 20 bits) + two Newton steps.  No IEEE slow path:
-// every denominator on this path is a positive, normal number (half-saturation sums, porosity*dz).
+// 1/x to within 2 ulp: MUFU.RCP64H seed (measured 2^-19.9) + one cubic step (3 DFMA); two Newton
+// steps (4 DFMA) give 1.7 ulp -- tools/rcp_accuracy.cu measures both.  No IEEE slow path: every
+// denominator on this path is a positive, normal number (half-saturation sums, porosity*dz).
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
+#ifndef MSED_RCP_NEWTON2
+    y = fma(y, fma(e, e, e), y);  // one cubic step: y*(1 + e + e^2)
+#else
+    y = fma(y, e, y);             // two Newton steps
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
+#endif
     return y;
+}
+// true if a or b is NaN: one DSETP for two values
+__device__ __forceinline__ bool either_nan(double a, double b)
+{
+    int r;
+    asm("{\n\t.reg .pred p;\n\tsetp.nan.f64 p, %1, %2;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(r) : "d"(a), "d"(b));
+    return r != 0;
 }
 
 // two reciprocals for the price of one Newton refinement: 1/a = b/(a*b), 1/b = a/(a*b)
@@ -87,9 +99,10 @@ __device__ __forceinline__ void omexdia_rates(const OmexDev &m, const double (&c
     const double rP = m.rLabile * (1.0 - Oxicminlim);
     const double Pprod = rP * detP;
 
-    const double OxicMin = Cprod * Oxicminlim * Rescale;
-    const double Denitrific = Cprod * Denitrilim * Rescale;
-    const double AnoxicMin = Cprod * Anoxiclim * Rescale;
+    const double CR = Cprod * Rescale;
+    const double OxicMin = CR * Oxicminlim;
+    const double Denitrific = CR * Denitrilim;
+    const double AnoxicMin = CR * Anoxiclim;
 
     const double Nitri = fT * m.rnit * nh3 * oxy * r7;
     const double OduOx = fT * m.rODUox * odu * oxy * r8;
@@ -97,7 +110,7 @@ __device__ __forceinline__ void omexdia_rates(const OmexDev &m, const double (&c
     r[0] = -fT * CprodL;
     r[1] = -fT * CprodS;
     r[2] = fT * (radsP - Pprod);
-    r[3] = fT * (Pprod - radsP);
+    r[3] = -r[2];  // = fT * (Pprod - radsP) exactly
     r[4] = -0.8 * Denitrific + Nitri;
     r[5] = (Nprod - Nitri) * m.rNH3Ads;
     r[6] = -OxicMin - 2.0 * Nitri - OduOx;
@@ -454,6 +467,7 @@ column_kernel(const __grid_constant__ KParams p)
         auto finish_layer = [&](auto clip_tag) {
             constexpr bool CLIP = decltype(clip_tag)::value;
             double *go = g_out, *ga1 = g_a1, *ga2 = g_a2, *gr = g_rhs;
+            double raw[NV];  // new state before the clip
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
                 const double rhs = layer_rhs(F[n], Fn[n], rpd, r[n]);
@@ -494,8 +508,9 @@ column_kernel(const __grid_constant__ KParams p)
                     newc = fma(dt * 1.0 / 8.0, a2[n] + rhs, basev[n]);
                 }
                 if (OP != OP_RHS) {
+                    raw[n] = newc;
                     if (CLIP) {
-                        nanf |= (newc != newc);                             // component :2392
+                        if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);  // component :2392
                         const double mn = p.om.minimum[n];                  // :1728-1730
                         newc = (newc < mn) ? mn : newc;
                     }

@@ -165,6 +165,7 @@ pair_kernel(const __grid_constant__ KParams p)
 #pragma unroll
             for (int n = 0; n < NV; ++n) r[n] = 0.0;
         }
+        double raw[NV];  // new state before the clip (check_NaN looks at it first, component :1718)
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
             const double rhs = layer_rhs(F[n], Fn[n], lc.rpd, r[n]);
@@ -172,8 +173,9 @@ pair_kernel(const __grid_constant__ KParams p)
             const double c0 = cc[n];
             double newc = euler_update(dt, rhs, c0);
             if (ADAPTIVE) viol |= violates(p.fac, c0, newc);
+            raw[n] = newc;
             if (CLIP) {
-                nanf |= (newc != newc);
+                if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
                 const double mn = p.om.minimum[n];
                 newc = (newc < mn) ? mn : newc;
             }

@@ -234,6 +234,7 @@ rk_pair_kernel(const __grid_constant__ KParams p)
         for (int n = 0; n < NV; ++n) cc[n] = lds64(wj + n * ROW_BYTES);
         layer_rates(has_next_tag, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB, rhs);
         double *go = g_out, *gw1 = g_w1, *gw2 = g_w2;
+        double raw[NV];  // new state before the clip
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
             double newc;
@@ -249,8 +250,9 @@ rk_pair_kernel(const __grid_constant__ KParams p)
             } else {                           // :182  c = c + dt*1/8*(Q' + k4)
                 newc = fma(dt * 1.0 / 8.0, xB[n] + rhs[n], baseB[n]);
             }
+            raw[n] = newc;
             if (!FIRST && decltype(clip_tag)::value) {  // final stage: check_NaN + clip (component :1718-1732)
-                nanf |= (newc != newc);
+                if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
                 const double mn = p.om.minimum[n];
                 newc = (newc < mn) ? mn : newc;
             }
