@@ -27,6 +27,7 @@ if ROOT not in sys.path:
 DT = 360.0                 # examples/esmf/sediment/run_sed.nml
 COUPLING_SECONDS = 3600.0  # examples/esmf/sediment/toplevel_component.F90:71 (1 h coupling)
 METHOD = 2                 # ADAPTIVE_EULER, component default (:62)
+JSON_OUT = sys.stdout
 SEGMENT = 40               # steps between restarts from the initial state inside a long timed region
 NVAR = 8
 ROW_BLOCK = 512            # forcing is seeded per block of 512 rows so the field is independent of N
@@ -197,7 +198,7 @@ def run_reference_arm(args, wl):
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -212,6 +213,12 @@ def main():
     ap.add_argument("--fusion", default="on", choices=["on", "off"],
                     help="speculative two-step kernels (msed_set_step_fusion); results are identical")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: native libraries that printf to fd 1 (NCCL's "NCCL version ..."
+    # banner) are sent to stderr, the JSON line goes to the original stdout
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl)
@@ -424,7 +431,7 @@ def main():
             v, cores, sample, _ = cpu_reference(wl, 0, 0, target_seconds=15.0)
             line["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port",
                                     "sample": sample}
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     sed.finalize()
     if world > 1:
         dist.barrier()
