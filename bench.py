@@ -173,7 +173,12 @@ def cpu_reference(wl, steps, warmup, target_seconds=None, as_arm=False):
     else:
         step_s = inum * want_rows * knum / rate
         nsteps = int(min(max((target_seconds or 15.0) / step_s, 3), 100))
-    secs, rows, sub = run(want_rows, nsteps)
+    # same policy as the GPU arm: restart from the initial state every SEGMENT steps (no sub-cycling regime)
+    secs, sub, left = 0.0, 0, nsteps
+    while left > 0:
+        m = min(SEGMENT, left)
+        s_, rows, sub_ = run(want_rows, m)
+        secs, sub, left = secs + s_, sub + sub_, left - m
     n = nsteps
     cells = inum * rows * knum
     sample = (f"{inum}x{rows}x{knum} slab of the workload, {n} steps, {cores} OpenMP threads "
