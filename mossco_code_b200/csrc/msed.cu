@@ -66,6 +66,8 @@ struct msed_handle {
     double *aux[2] = {nullptr, nullptr};
     double *por = nullptr, *bdys = nullptr, *fluxes = nullptr, *par_surface = nullptr;
     double *scratch = nullptr;  // [nvar][K][ld] staging (rhs / fields / packed transfers)
+    double *denit = nullptr;    // [K][ld] denit diagnostic left by the last fused pair of a call
+    bool denit_valid = false;   // ... and whether it describes the current state
     double *pel = nullptr;      // pelagic boxes: conc [nvar][ld], wz [nvar][ld], height [ld], temperature [ld]
     double *tables = nullptr;   // device copies of zc[K], cumdepth[K], porosity profile[K]
     unsigned char *mask = nullptr;
@@ -140,6 +142,7 @@ void fill_params(const msed_handle *h, KParams &p)
     p.aux1 = h->aux[0];
     p.aux2 = h->aux[1];
     p.rhs_out = h->scratch;
+    p.denit_out = nullptr;
     p.por = h->por;
     p.bdys = h->bdys;
     p.fluxes = h->fluxes;
@@ -267,17 +270,27 @@ int ensure_scratch(msed_handle *h)
     return MSED_OK;
 }
 
+int ensure_denit(msed_handle *h)
+{
+    if (!h->denit) CUDA_TRY(h, cudaMalloc(&h->denit, (size_t)h->K * h->ld * sizeof(double)));
+    return MSED_OK;
+}
+
 cudaError_t launch_pair(const msed_handle *h, int method, const KParams &p)
 {
     const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
     const bool adaptive = method == MSED_ADAPTIVE_EULER;
-    if (h->cfg.model == MSED_MODEL_OMEXDIA_P) {
-        if (adaptive) pair_kernel<MSED_MODEL_OMEXDIA_P, true><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);
-        else pair_kernel<MSED_MODEL_OMEXDIA_P, false><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);
-    } else {
-        if (adaptive) pair_kernel<MSED_MODEL_NONE, true><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);
-        else pair_kernel<MSED_MODEL_NONE, false><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);
-    }
+    const bool denit = p.denit_out != nullptr;  // the last pair of a call also stores the denit diagnostic
+#define MSED_PAIR(MODEL, AD, DN) pair_kernel<MODEL, AD, DN><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p)
+#define MSED_PAIR_MODEL(MODEL)                                   \
+    do {                                                         \
+        if (adaptive) { if (denit) MSED_PAIR(MODEL, true, true); else MSED_PAIR(MODEL, true, false); }   \
+        else          { if (denit) MSED_PAIR(MODEL, false, true); else MSED_PAIR(MODEL, false, false); } \
+    } while (0)
+    if (h->cfg.model == MSED_MODEL_OMEXDIA_P) MSED_PAIR_MODEL(MSED_MODEL_OMEXDIA_P);
+    else MSED_PAIR_MODEL(MSED_MODEL_NONE);
+#undef MSED_PAIR_MODEL
+#undef MSED_PAIR
     return cudaGetLastError();
 }
 
@@ -315,14 +328,15 @@ cudaError_t enable_pair_smem()
     MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_34)
     MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_34)
 #undef MSED_RKP_ATTR
-    if ((e = cudaFuncSetAttribute(pair_kernel<MSED_MODEL_OMEXDIA_P, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(pair_kernel<MSED_MODEL_OMEXDIA_P, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(pair_kernel<MSED_MODEL_NONE, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(pair_kernel<MSED_MODEL_NONE, false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#define MSED_PAIR_ATTR(MODEL, AD, DN) \
+    if ((e = cudaFuncSetAttribute(pair_kernel<MODEL, AD, DN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  bytes)) != cudaSuccess) return e;
+    MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, true, true) MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, true, false)
+    MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, false, true) MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, false, false)
+    MSED_PAIR_ATTR(MSED_MODEL_NONE, true, true) MSED_PAIR_ATTR(MSED_MODEL_NONE, true, false)
+    MSED_PAIR_ATTR(MSED_MODEL_NONE, false, true) MSED_PAIR_ATTR(MSED_MODEL_NONE, false, false)
+#undef MSED_PAIR_ATTR
+    return cudaSuccess;
 }
 
 int reduce_flags(msed_handle *h)
@@ -421,22 +435,48 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                          h->cfg.bioturbation_profile != 3 && !h->cfg.distributed_pom_flux && h->por_mode != 0;
     const bool rk_fused = fusable && !single_attempt;
     long long npairs = 0;
-    if (fusable && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 3)
-        npairs = (nsteps - 1) / 2;  // the last step is always a single one (diagnostics, chunked export)
+    bool last_is_pair = false;  // an even number of steps ends with a pair, which then leaves the
+                                // "state of the last get_rhs call" diagnostic behind (KParams::denit_out)
+    h->denit_valid = false;
+    if (fusable && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 2) {
+        npairs = nsteps / 2;
+        last_is_pair = (2 * npairs == nsteps);
+        if (last_is_pair && (rc = ensure_denit(h))) return rc;
+    }
+    // export of one chunk of msed_run_exchange while the next chunks are still being computed
+    auto export_chunk = [&](int c) -> int {
+        const int c0 = plan->c0[c], c1 = plan->c1[c];
+        CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pool[16 + c], 0));
+        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->copy_stream>>>(plan->neg + c0, h->fluxes + c0, h->ld,
+                                                                         c1 - c0, NV);
+        launches += 1;
+        CUDA_TRY(h, cudaMemcpy2DAsync(plan->host_out + c0, (size_t)h->ncol * sizeof(double), plan->neg + c0,
+                                      h->ld * sizeof(double), (size_t)(c1 - c0) * sizeof(double), NV,
+                                      cudaMemcpyDeviceToHost, h->copy_stream));
+        return MSED_OK;
+    };
     bool first_pending = plan && plan->first && single_attempt;
     for (long long q = 0; q < npairs; ++q) {
-        if (first_pending) {
+        const bool last_pair = last_is_pair && q == npairs - 1;
+        const bool chunk_last = last_pair && plan && plan->last;
+        KParams pq = p;
+        if (last_pair) pq.denit_out = h->denit;
+        if (first_pending || chunk_last) {
             for (int c = 0; c < plan->nchunks; ++c) {
-                if ((rc = boundary_chunk(c))) return rc;
-                KParams pc = p;
+                if (first_pending)
+                    if ((rc = boundary_chunk(c))) return rc;
+                KParams pc = pq;
                 pc.col0 = plan->c0[c];
                 pc.col_end = plan->c1[c];
                 CUDA_TRY(h, launch_pair(h, method, pc));
                 launches += 1;
+                if (chunk_last)
+                    if ((rc = export_chunk(c))) return rc;
             }
             first_pending = false;
         } else {
-            CUDA_TRY(h, launch_pair(h, method, p));
+            CUDA_TRY(h, launch_pair(h, method, pq));
             launches += 1;
         }
         if (collective)
@@ -450,7 +490,11 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     long long remaining = singles_planned, issued = 0;
     const long long max_batch = 256;
     int guard = 0;
-    while (remaining > 0) {
+    // with nothing but pairs planned the controller still has to be asked whether all of them were
+    // committed; a failed pair leaves its steps to the single-step loop
+    bool check_pairs = (singles_planned == 0 && npairs > 0);
+    while (remaining > 0 || check_pairs) {
+        check_pairs = false;
         const long long batch = remaining < max_batch ? remaining : max_batch;
         for (long long s = 0; s < batch; ++s, ++issued) {
             const bool chunk_first = first_pending && issued == 0;
@@ -465,17 +509,8 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                     pc.col_end = c1;
                     CUDA_TRY(h, launch_column(h, method == MSED_EULER ? OP_EULER : OP_ADAPTIVE, pc));
                     launches += 1;
-                    if (chunk_last) {  // export this chunk while the next ones are still being computed
-                        CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], h->stream));
-                        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pool[16 + c], 0));
-                        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->copy_stream>>>(
-                            plan->neg + c0, h->fluxes + c0, h->ld, c1 - c0, NV);
-                        launches += 1;
-                        CUDA_TRY(h, cudaMemcpy2DAsync(plan->host_out + c0, (size_t)h->ncol * sizeof(double),
-                                                      plan->neg + c0, h->ld * sizeof(double),
-                                                      (size_t)(c1 - c0) * sizeof(double), NV,
-                                                      cudaMemcpyDeviceToHost, h->copy_stream));
-                    }
+                    if (chunk_last)
+                        if ((rc = export_chunk(c))) return rc;
                 }
             } else if (method == MSED_EULER) {
                 CUDA_TRY(h, launch_column(h, OP_EULER, p));
@@ -537,6 +572,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     if (r.subcycles > 0 || r.pair_failures > 0) h->pair_cooldown = 64;
     else if (h->pair_cooldown > 0) h->pair_cooldown -= (int)std::min<long long>(nsteps, h->pair_cooldown);
     h->pairs_committed += (npairs > 0 && r.pair_failures == 0) ? npairs : 0;
+    h->denit_valid = last_is_pair && r.pair_failures == 0 && !r.stop && r.steps_done == nsteps;
     h->cur = r.cur;
     if (diag && r.last_min_dt < h->last_min_dt) {
         long long idx = -1;
@@ -744,7 +780,7 @@ int msed_destroy(msed_handle *h)
     if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->buf[0]); cudaFree(h->buf[1]); cudaFree(h->aux[0]); cudaFree(h->aux[1]);
     cudaFree(h->por); cudaFree(h->bdys); cudaFree(h->fluxes); cudaFree(h->par_surface);
-    cudaFree(h->scratch); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->ctl);
+    cudaFree(h->scratch); cudaFree(h->denit); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->ctl);
     cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->pel);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -851,6 +887,7 @@ int msed_check_domain(msed_handle *h)
 int msed_init_concentrations(msed_handle *h)
 {
     if (!h) return MSED_ERR_ARG;
+    h->denit_valid = false;
     CUDA_TRY(h, cudaSetDevice(h->device));
     InitVals iv;
     for (int n = 0; n < NV; ++n) iv.v[n] = h->cfg.initial_value[n];
@@ -864,6 +901,7 @@ int msed_init_concentrations(msed_handle *h)
 int msed_set_state(msed_handle *h, const double *conc)
 {
     if (!h || !conc) return fail(h, MSED_ERR_ARG, "null argument");
+    h->denit_valid = false;
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc = upload_rows(h, h->buf[h->cur], conc, (size_t)NV * h->K);
     if (rc) return rc;
@@ -885,6 +923,7 @@ int msed_get_state(msed_handle *h, double *conc)
 int msed_set_state_from_column(msed_handle *h, const double *conc1d)
 {
     if (!h || !conc1d) return fail(h, MSED_ERR_ARG, "null argument");
+    h->denit_valid = false;
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc = ensure_scratch(h);
     if (rc) return rc;
@@ -1017,6 +1056,12 @@ int msed_get_field(msed_handle *h, int which, double *out3d)
     // that is the buffer the accepted attempt read; for RK the last stage state c1 (same buffer)
     const double *state = h->buf[h->cur];
     if (which == MSED_FIELD_DENIT) state = h->buf[1 - h->cur];
+    if (which == MSED_FIELD_DENIT && h->denit_valid) {  // the call ended with a fused pair: stored field
+        denit_copy_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->scratch, h->denit, h->mask, h->ld,
+                                                                   h->ncol, h->K);
+        CUDA_TRY(h, cudaGetLastError());
+        return download_rows(h, out3d, h->scratch, h->K);
+    }
     field_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->scratch, which, p, h->par_surface, state,
                                                           h->tables + MAXK, h->cfg.k_par, -999.0);
     CUDA_TRY(h, cudaGetLastError());

@@ -60,12 +60,20 @@ __device__ __forceinline__ bool either_nan(double a, double b)
     return r != 0;
 }
 
-// two reciprocals for the price of one Newton refinement: 1/a = b/(a*b), 1/b = a/(a*b)
+// Every product, sum and fused multiply-add below is spelled out (DMUL/DADD/DFMA intrinsics), so the
+// compiler has no contraction freedom left: the same source gives the same bits in every kernel that
+// inlines it (single step, fused pair, RK stages, the diagnostics kernel), whatever else those kernels
+// use the intermediate values for.  Bit-identity between the fused and unfused paths rests on this.
+#define MSED_MUL(a, b) __dmul_rn((a), (b))
+#define MSED_ADD(a, b) __dadd_rn((a), (b))
+#define MSED_SUB(a, b) __dsub_rn((a), (b))
+
+// two reciprocals from one refinement: 1/a = b/(a*b), 1/b = a/(a*b)
 __device__ __forceinline__ void fast_rcp2(double a, double b, double &ra, double &rb)
 {
-    const double y = fast_rcp(a * b);
-    ra = y * b;
-    rb = y * a;
+    const double y = fast_rcp(MSED_MUL(a, b));
+    ra = MSED_MUL(y, b);
+    rb = MSED_MUL(y, a);
 }
 
 // hzg_omexdia_p local rates for one cell: SURVEY.md Appendix B (frozen project spec; the FABM
@@ -78,44 +86,42 @@ __device__ __forceinline__ void omexdia_rates(const OmexDev &m, const double (&c
     const double no3 = c[4], nh3 = c[5], oxy = c[6], odu = c[7];
     const double relaxO2 = 0.04;
 
-    const double r1 = fast_rcp(oxy + m.ksO2oxic + relaxO2 * (nh3 + odu));
+    const double r1 = fast_rcp(fma(relaxO2, MSED_ADD(nh3, odu), MSED_ADD(oxy, m.ksO2oxic)));
     double r2, r3, r4, r5, r7, r8;  // paired: every denominator is a positive half-saturation sum
-    fast_rcp2(oxy + m.kinO2denit, oxy + m.kinO2anox, r2, r4);
-    fast_rcp2(no3 + m.ksNO3denit, no3 + m.kinNO3anox, r3, r5);
-    fast_rcp2(oxy + m.ksO2nitri + relaxO2 * (ldetC + odu), oxy + m.ksO2oduox + relaxO2 * (nh3 + ldetC), r7, r8);
+    fast_rcp2(MSED_ADD(oxy, m.kinO2denit), MSED_ADD(oxy, m.kinO2anox), r2, r4);
+    fast_rcp2(MSED_ADD(no3, m.ksNO3denit), MSED_ADD(no3, m.kinNO3anox), r3, r5);
+    fast_rcp2(fma(relaxO2, MSED_ADD(ldetC, odu), MSED_ADD(oxy, m.ksO2nitri)),
+              fma(relaxO2, MSED_ADD(nh3, ldetC), MSED_ADD(oxy, m.ksO2oduox)), r7, r8);
 
-    const double Oxicminlim = oxy * r1;
-    const double Denitrilim = (1.0 - oxy * r2) * no3 * r3;
-    const double Anoxiclim = (1.0 - oxy * r4) * (1.0 - no3 * r5);
-    const double Rescale = fast_rcp(Oxicminlim + Denitrilim + Anoxiclim);
+    const double Oxicminlim = MSED_MUL(oxy, r1);
+    const double Denitrilim = MSED_MUL(MSED_MUL(fma(-oxy, r2, 1.0), no3), r3);
+    const double Anoxiclim = MSED_MUL(fma(-oxy, r4, 1.0), fma(-no3, r5, 1.0));
+    const double Rescale = fast_rcp(MSED_ADD(MSED_ADD(Oxicminlim, Denitrilim), Anoxiclim));
 
-    const double CprodL = m.rLabile * ldetC;
-    const double CprodS = m.rSemilabile * sdetC;
-    const double Csum = CprodL + CprodS;
+    const double CprodL = MSED_MUL(m.rLabile, ldetC);
+    const double CprodS = MSED_MUL(m.rSemilabile, sdetC);
+    const double Csum = MSED_ADD(CprodL, CprodS);
     const double Cprod = (Csum > m.CprodMax) ? m.CprodMax : Csum;
-    const double Nprod = CprodL * m.NCrLdet + CprodS * m.NCrSdet;
+    const double Nprod = fma(CprodS, m.NCrSdet, MSED_MUL(CprodL, m.NCrLdet));
 
-    const double radsP = m.PAds_rS * po4 * ((odu > m.PAdsODU) ? odu : m.PAdsODU);
-    const double rP = m.rLabile * (1.0 - Oxicminlim);
-    const double Pprod = rP * detP;
+    const double radsP = MSED_MUL(MSED_MUL(m.PAds_rS, po4), (odu > m.PAdsODU) ? odu : m.PAdsODU);
+    const double rP = MSED_MUL(m.rLabile, MSED_SUB(1.0, Oxicminlim));
 
-    const double CR = Cprod * Rescale;
-    const double OxicMin = CR * Oxicminlim;
-    const double Denitrific = CR * Denitrilim;
-    const double AnoxicMin = CR * Anoxiclim;
+    const double CR = MSED_MUL(Cprod, Rescale);
+    const double Denitrific = MSED_MUL(CR, Denitrilim);
 
-    const double Nitri = fT * m.rnit * nh3 * oxy * r7;
-    const double OduOx = fT * m.rODUox * odu * oxy * r8;
+    const double Nitri = MSED_MUL(MSED_MUL(MSED_MUL(MSED_MUL(fT, m.rnit), nh3), oxy), r7);
+    const double OduOx = MSED_MUL(MSED_MUL(MSED_MUL(MSED_MUL(fT, m.rODUox), odu), oxy), r8);
 
-    r[0] = -fT * CprodL;
-    r[1] = -fT * CprodS;
-    r[2] = fT * (radsP - Pprod);
+    r[0] = MSED_MUL(-fT, CprodL);
+    r[1] = MSED_MUL(-fT, CprodS);
+    r[2] = MSED_MUL(fT, fma(-rP, detP, radsP));                   // fT*(radsP - Pprod), Pprod = rP*detP
     r[3] = -r[2];  // = fT * (Pprod - radsP) exactly
-    r[4] = -0.8 * Denitrific + Nitri;
-    r[5] = (Nprod - Nitri) * m.rNH3Ads;
-    r[6] = -OxicMin - 2.0 * Nitri - OduOx;
-    r[7] = AnoxicMin - OduOx;
-    if (denit) *denit = 0.8 * Denitrific;
+    r[4] = fma(-0.8, Denitrific, Nitri);
+    r[5] = MSED_MUL(MSED_SUB(Nprod, Nitri), m.rNH3Ads);
+    r[6] = fma(-CR, Oxicminlim, fma(-2.0, Nitri, -OduOx));        // -OxicMin - 2 Nitri - OduOx
+    r[7] = fma(CR, Anoxiclim, -OduOx);                            // AnoxicMin - OduOx
+    if (denit) *denit = MSED_MUL(0.8, Denitrific);
 }
 
 // Zhang & Wirtz bioturbation factor of one cell, fabm_sediment_driver.F90:627-644
@@ -140,32 +146,35 @@ __device__ __forceinline__ double bf3_cell(const KParams &p, int k, double wt, d
 __device__ __forceinline__ void interface_coeffs(double cpart, double cdiss, double porc, double porn,
                                                  double bfk, double rdzc, double &mDp, double &mDd)
 {
-    const double intf = 0.5 * (porc + porn);  // intf_porosity, driver :435
-    const double Dp = cpart * (1.0 - intf) * bfk;
-    const double Dd = Dp + cdiss * intf;
-    mDp = -Dp * rdzc;
-    mDd = -Dd * rdzc;
+    const double intf = MSED_MUL(0.5, MSED_ADD(porc, porn));  // intf_porosity, driver :435
+    const double Dp = MSED_MUL(MSED_MUL(cpart, MSED_SUB(1.0, intf)), bfk);
+    const double Dd = fma(cdiss, intf, Dp);
+    mDp = MSED_MUL(-Dp, rdzc);
+    mDd = MSED_MUL(-Dd, rdzc);
 }
 __device__ __forceinline__ double flux_particulate(double mDp, double cn, double porn, double cc, double porc)
 {
-    return mDp * (cn * porn - cc * porc);  // C = conc*porosity, driver :663
+    return MSED_MUL(mDp, fma(cn, porn, -MSED_MUL(cc, porc)));  // C = conc*porosity, driver :663
 }
-__device__ __forceinline__ double flux_dissolved(double mDd, double cn, double cc) { return mDd * (cn - cc); }
+__device__ __forceinline__ double flux_dissolved(double mDd, double cn, double cc)
+{
+    return MSED_MUL(mDd, MSED_SUB(cn, cc));
+}
 // upper-boundary diffusivities: intf_porosity(:,:,1) = porosity(:,:,1), driver :434
 __device__ __forceinline__ void top_coeffs(double cpart, double cdiss, double por0, double bf0, double &Dp,
                                            double &Dd)
 {
-    Dp = cpart * (1.0 - por0) * bf0;
-    Dd = Dp + cdiss * por0;
+    Dp = MSED_MUL(MSED_MUL(cpart, MSED_SUB(1.0, por0)), bf0);
+    Dd = fma(cdiss, por0, Dp);
 }
 __device__ __forceinline__ double top_flux_dirichlet(double D, double C1, double Cup, double rdz0)
 {
-    return -D * (C1 - Cup) * rdz0;  // diff3d :786
+    return MSED_MUL(MSED_MUL(-D, MSED_SUB(C1, Cup)), rdz0);  // diff3d :786
 }
 // dC (:819) with the particulate rescaling (:677-678) folded: (Flux(k)-Flux(k+1))/(porosity*dz) + rate
 __device__ __forceinline__ double layer_rhs(double Fup, double Flow, double rpd, double rate)
 {
-    return fma(Fup - Flow, rpd, rate);  // driver :715
+    return fma(MSED_SUB(Fup, Flow), rpd, rate);  // driver :715
 }
 __device__ __forceinline__ double euler_update(double dt, double rhs, double c0) { return fma(dt, rhs, c0); }
 __device__ __forceinline__ bool violates(double fac, double c0, double newc)  // solver_library.F90:121
@@ -184,7 +193,7 @@ __device__ __forceinline__ void column_constants(const KParams &p, double temp, 
         const double f_T = exp(-4500.0 * (1.0 / (temp + 273.0) - (1.0 / 288.0)));  // :648
         cpart = p.bioturbation * f_T / 86400.0 / 10000.0;                          // :652
     }
-    cdiss = (p.diffusivity + temp * 0.035) / 86400.0 / 10000.0;                    // :682-683
+    cdiss = fma(temp, 0.035, p.diffusivity) / 86400.0 / 10000.0;                   // :682-683
     if (MODEL == MSED_MODEL_OMEXDIA_P) fT = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
 }
 
@@ -356,7 +365,7 @@ column_kernel(const __grid_constant__ KParams p)
             } else if (bc == 2) {                             // :786
                 const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
                 const double c1 = lds64(sbase + n * ROW_BYTES);
-                const double C1 = part ? c1 * por0 : c1;
+                const double C1 = part ? MSED_MUL(c1, por0) : c1;
                 f = top_flux_dirichlet(part ? Dp : Dd, C1, Cup, rdz0);
             } else if (bc != 3 && n > 0) {
                 // BcUp outside 1..4 (bcup_dissolved_variables = 0): diff3d never assigns Flux(1)
@@ -463,7 +472,7 @@ column_kernel(const __grid_constant__ KParams p)
 
         // dC (:819) with the particulate rescaling (:677-678) folded: both reduce to
         // (Flux(k)-Flux(k+1)) / (porosity*dz)
-        const double rpd = fast_rcp(porc * p.dz[k]);
+        const double rpd = fast_rcp(MSED_MUL(porc, p.dz[k]));
         auto finish_layer = [&](auto clip_tag) {
             constexpr bool CLIP = decltype(clip_tag)::value;
             double *go = g_out, *ga1 = g_a1, *ga2 = g_a2, *gr = g_rhs;

@@ -94,6 +94,7 @@ struct KParams {
     double beta, b, L1, L2, poc_factor[2], cumdepth_last;
     OmexDev om;
     double dz[MAXK], rdzc[MAXK], bf[MAXK], e1[MAXK], e2[MAXK], portab[MAXK];
+    double *denit_out;       // [K][ld]: FABM denit diagnostic of the second step of a call's last pair, or null
 };
 
 // loaders, reaction term and the fused column kernel
@@ -410,6 +411,16 @@ __global__ void field_kernel(double *out, int which, KParams p, const double *pa
         }
         out[q] = v;
     }
+}
+
+// the denitrification diagnostic stored by the last fused pair of a call -> <name>_in_soil layout
+__global__ void denit_copy_kernel(double *out, const double *denit, const unsigned char *mask, size_t ld,
+                                  int ncol, int K)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    const bool m = mask[col] != 0;
+    for (int k = 0; k < K; ++k) out[(size_t)k * ld + col] = m ? 0.0 : denit[(size_t)k * ld + col];
 }
 
 // minloc((c1-c)/c) in Fortran array order, NaNs skipped (solver_library.F90:133-134).

@@ -35,7 +35,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-template <int MODEL, bool ADAPTIVE>
+template <int MODEL, bool ADAPTIVE, bool DENIT>
 __global__ void __launch_bounds__(COL_BLOCK, PAIR_MIN_BLOCKS)
 pair_kernel(const __grid_constant__ KParams p)
 {
@@ -104,7 +104,7 @@ pair_kernel(const __grid_constant__ KParams p)
             } else if (bc == 2) {
                 const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
                 const double c1 = c0(n);
-                const double C1 = part ? c1 * por0 : c1;
+                const double C1 = part ? MSED_MUL(c1, por0) : c1;
                 f = top_flux_dirichlet(part ? Dp : Dd, C1, Cup, rdz0);
             } else if (bc != 3 && n > 0) {
                 f = F[n - 1];
@@ -123,6 +123,10 @@ pair_kernel(const __grid_constant__ KParams p)
 
     bool viol1 = false, nan1 = false, viol2 = false, nan2 = false;
     double *g_out = out;
+    // The last pair of a call leaves the denitrification diagnostic of its second step behind: it
+    // describes the state of the last get_rhs call, which here never reaches HBM.
+    double fT_diag = fT;
+    if (MODEL != MSED_MODEL_OMEXDIA_P && DENIT) fT_diag = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
 
     // one step of one layer: finishes layer kk given its state cc, the state cn of the layer below and
     // the flux F through its upper interface; the new state goes to `sink`.  HAS_NEXT and CLIP are
@@ -138,12 +142,12 @@ pair_kernel(const __grid_constant__ KParams p)
             lc.porn = por_at(kk + 1);
             interface_coeffs(cpart, cdiss, lc.porc, lc.porn, p.bf[kk + 1], p.rdzc[kk], lc.mDp, lc.mDd);
         }
-        lc.rpd = fast_rcp(lc.porc * p.dz[kk]);
+        lc.rpd = fast_rcp(MSED_MUL(lc.porc, p.dz[kk]));
         return lc;
     };
 
     auto step_layer = [&](auto has_next_tag, auto clip_tag, const LayerCoef &lc, const double (&cc)[NV], auto cn,
-                          double (&F)[NV], bool &viol, bool &nanf, auto sink) {
+                          double (&F)[NV], bool &viol, bool &nanf, auto sink, auto denit) {
         constexpr bool HAS_NEXT = decltype(has_next_tag)::value;
         constexpr bool CLIP = decltype(clip_tag)::value;
         double Fn[NV];
@@ -160,8 +164,10 @@ pair_kernel(const __grid_constant__ KParams p)
         }
         double r[NV];
         if (MODEL == MSED_MODEL_OMEXDIA_P) {
-            omexdia_rates(p.om, cc, fT, r, nullptr);
+            omexdia_rates(p.om, cc, fT, r, denit);
         } else {
+            // what field_kernel reports for this model
+            if (!std::is_same<decltype(denit), std::nullptr_t>::value) omexdia_rates(p.om, cc, fT_diag, r, denit);
 #pragma unroll
             for (int n = 0; n < NV; ++n) r[n] = 0.0;
         }
@@ -196,7 +202,7 @@ pair_kernel(const __grid_constant__ KParams p)
 #pragma unroll
         for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
         step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA, viol1,
-                   nan1, [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); });
+                   nan1, [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); }, nullptr);
         return lc;
     };
     // step 2, layer j: state from the c1 window, result to HBM
@@ -207,8 +213,15 @@ pair_kernel(const __grid_constant__ KParams p)
 #pragma unroll
         for (int n = 0; n < NV; ++n) cc[n] = lds64(wj + n * ROW_BYTES);
         double *go = g_out;
-        step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB, viol2,
-                   nan2, [&](int n, double v) { go[(size_t)n * plane] = v; });
+        if (DENIT) {
+            double dn = 0.0;
+            step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB,
+                       viol2, nan2, [&](int n, double v) { go[(size_t)n * plane] = v; }, &dn);
+            p.denit_out[(size_t)j * ld + col] = dn;
+        } else {
+            step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB,
+                       viol2, nan2, [&](int n, double v) { go[(size_t)n * plane] = v; }, nullptr);
+        }
         g_out += ld;
     };
 

@@ -115,7 +115,7 @@ rk_pair_kernel(const __grid_constant__ KParams p)
             } else if (bc == 2) {
                 const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
                 const double c1 = c0(n);
-                const double C1 = part ? c1 * por0 : c1;
+                const double C1 = part ? MSED_MUL(c1, por0) : c1;
                 f = top_flux_dirichlet(part ? Dp : Dd, C1, Cup, rdz0);
             } else if (bc != 3 && n > 0) {
                 f = F[n - 1];
@@ -134,7 +134,7 @@ rk_pair_kernel(const __grid_constant__ KParams p)
             lc.porn = por_at(kk + 1);
             interface_coeffs(cpart, cdiss, lc.porc, lc.porn, p.bf[kk + 1], p.rdzc[kk], lc.mDp, lc.mDd);
         }
-        lc.rpd = fast_rcp(lc.porc * p.dz[kk]);
+        lc.rpd = fast_rcp(MSED_MUL(lc.porc, p.dz[kk]));
         return lc;
     };
     // right-hand side of one layer (same inline arithmetic as column_kernel)

@@ -96,7 +96,7 @@ def test_pelagic_soil_couplers(gpu, oracle, full):
         assert scaled_err(sed.fluxes, ref.fluxes) <= 1e-10
 
 
-@pytest.mark.parametrize("nchunks,seconds", [(4, 3600.0), (3, 1000.0), (5, 360.0), (1, 3600.0)])
+@pytest.mark.parametrize("nchunks,seconds", [(4, 3600.0), (3, 1000.0), (5, 360.0), (1, 3600.0), (4, 720.0)])
 def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds):
     """msed_run_exchange (chunk-pipelined PCIe/compute overlap) must be bit-identical to
     get_boundary_conditions + run + upward_fluxes, incl. the shortened last step and a single step."""
@@ -126,8 +126,9 @@ def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds):
                     up = sed.upward_fluxes()
                 assert rc == 0
                 steps = sed.info.steps_done
-            res.append((sed.conc, up.copy(), sed.bdys, steps))
+            res.append((sed.conc, up.copy(), sed.bdys, steps, sed.field("denit")))
     assert res[0][3] == res[1][3]
+    assert np.array_equal(res[0][4], res[1][4])           # diagnostic of the last get_rhs state
     assert np.array_equal(res[0][0], res[1][0])
     assert np.array_equal(res[0][1], res[1][1])
     assert np.array_equal(res[0][2], res[1][2])

@@ -44,7 +44,7 @@ def _same(a, b):
 
 
 @pytest.mark.parametrize("method", [2, 0])
-@pytest.mark.parametrize("nsteps", [3, 4, 10, 11])
+@pytest.mark.parametrize("nsteps", [2, 3, 4, 10, 11])
 def test_fusion_is_bit_identical(gpu, oracle, method, nsteps):
     case = make_case("fuse", 37, 21, 20, 0.003, seed=101, land_fraction=0.2, smooth_temperature=True)
     on = _run(case, True, method, nsteps, calls=2)
