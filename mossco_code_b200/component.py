@@ -65,6 +65,7 @@ class FabmSedimentComponent:
         self.flux_buffer = None   # optional caller-owned (pinned) (inum,jnum,nvar) export buffer
         self._out = None          # output.dat handle (run_nml output > 0, component :266-269)
         self.advance_count = 0    # ESMF clock advanceCount
+        self.on_mesh = False      # geometry is a mesh: rank-1 surface fields (see initialize_p1)
 
     # ---- SetServices -----------------------------------------------------------------------
     def set_services(self):
@@ -85,8 +86,16 @@ class FabmSedimentComponent:
                       run_nml: Optional[dict] = None, sed_nml: Optional[dict] = None,
                       fabm_nml: Optional[dict] = None, grid_mask: Optional[np.ndarray] = None,
                       device: int = -1, j_offset: int = 0, output_path: str = "output.dat"):
-        """``grid_shape`` = (inum, jnum) of the foreign grid tile (:314-448); ``grid_mask`` is the
-        ESMF_GRIDITEM_MASK item: columns with grid_mask <= 0 are masked (:497-501)."""
+        """``grid_shape`` = (inum, jnum) of the foreign grid tile (:314-448), or ``(numElements,)`` for a
+        mesh (:391-446): the columns then are the owned mesh elements (``_INUM_`` = numElements,
+        ``_JNUM_`` = 1), surface fields have rank 1 and ``*_in_soil`` fields rank 2 (element, layer;
+        :693-770).  ``grid_mask`` is the ESMF_GRIDITEM_MASK item: columns with grid_mask <= 0 are masked
+        (:497-501)."""
+        self.on_mesh = len(tuple(grid_shape)) == 1
+        if self.on_mesh:
+            grid_shape = (int(grid_shape[0]), 1)
+            if grid_mask is not None:
+                grid_mask = np.asarray(grid_mask).reshape(grid_shape)
         if run_nml:
             unknown = set(run_nml) - set(RUN_NML_DEFAULTS)
             if unknown:
@@ -171,6 +180,16 @@ class FabmSedimentComponent:
         names.append("denit_in_soil")                       # FABM diagnostic, :1012-1040
         return names
 
+    def _surface(self, f):
+        """Import field -> the driver's (inum, jnum) layout (rank-1 mesh fields get a unit j axis)."""
+        if f is None or not self.on_mesh:
+            return f
+        return np.asarray(f, dtype=np.float64).reshape(self.sed.shape2d, order="F")
+
+    def _export(self, a):
+        """Driver array (inum, 1[, k]) -> the rank the geometry has (mesh: drop the unit j axis)."""
+        return a[:, 0] if self.on_mesh else a
+
     @staticmethod
     def _lookup(state: State, base: str, suffix: str):
         key = base + suffix
@@ -189,6 +208,8 @@ class FabmSedimentComponent:
             f = import_state.get(f"{v}_in_soil")
             if f is None:
                 continue
+            if self.on_mesh and f.ndim == 2:
+                f = np.asarray(f)[:, None, :]
             if tuple(f.shape) != sed.shape3d:               # bounds must match (:1440-1460)
                 continue
             if conc is None:
@@ -197,6 +218,8 @@ class FabmSedimentComponent:
         if conc is not None:
             sed.conc = conc
         por = import_state.get("porosity_in_soil")
+        if por is not None and self.on_mesh and por.ndim == 2:
+            por = np.asfortranarray(np.asarray(por)[:, None, :])
         if por is not None and tuple(por.shape) == sed.shape3d:
             sed.set_porosity(por)
         rc = sed.check_domain()                              # :1485
@@ -215,7 +238,9 @@ class FabmSedimentComponent:
         if with_diagnostics:
             keep = set(export)
         fields = {k: v for k, v in export.items() if k in keep}
-        units = {f"{v}_in_soil": "mmol m-3" for v in VARIABLE_NAMES}
+        if self.on_mesh:                                     # the file layout is (x, y[, layer]): unit y axis
+            fields = {k: np.asarray(v)[:, None] for k, v in fields.items()}
+        units ={f"{v}_in_soil": "mmol m-3" for v in VARIABLE_NAMES}
         units.update({f"{v}_upward_flux_at_soil_surface": "mmol m-2 s-1" for v in VARIABLE_NAMES})
         t = self.clock_seconds if time_seconds is None else time_seconds
         soil_netcdf.write_fields(path, fields, t, units=units, append=append)
@@ -235,16 +260,16 @@ class FabmSedimentComponent:
         r = self.run_nml
         if run_seconds is None:
             run_seconds = float(clock["stopTime"] - clock["currTime"])
-        par = import_state.get("photosynthetically_active_radiation_at_soil_surface")
+        par = self._surface(import_state.get("photosynthetically_active_radiation_at_soil_surface"))
         if par is not None:                                  # :1568-1596
             sed.set_par_surface(par)
-        por = import_state.get("porosity_at_soil_surface")
+        por = self._surface(import_state.get("porosity_at_soil_surface"))
         if por is not None:                                  # :1619-1643
             sed.update_porosity(por, from_surface=True)
-        temp = import_state.get("temperature_at_soil_surface")
-        cs = [self._lookup(import_state, v, "_at_soil_surface") for v in VARIABLE_NAMES]
-        wz = [self._lookup(import_state, v, "_z_velocity_at_soil_surface") if PARTICULATE[n] else None
-              for n, v in enumerate(VARIABLE_NAMES)]
+        temp = self._surface(import_state.get("temperature_at_soil_surface"))
+        cs = [self._surface(self._lookup(import_state, v, "_at_soil_surface")) for v in VARIABLE_NAMES]
+        wz = [self._surface(self._lookup(import_state, v, "_z_velocity_at_soil_surface")) if PARTICULATE[n]
+              else None for n, v in enumerate(VARIABLE_NAMES)]
         if self._out is not None:
             rc, up = self._run_with_output(temp, cs, wz, float(run_seconds))
         else:
@@ -323,18 +348,18 @@ class FabmSedimentComponent:
         if up is None:
             up = sed.upward_fluxes(self.flux_buffer)
         for n, v in enumerate(VARIABLE_NAMES):
-            export_state[f"{v}_upward_flux_at_soil_surface"] = up[:, :, n]
+            export_state[f"{v}_upward_flux_at_soil_surface"] = self._export(up[:, :, n])
         if not with_3d:
             return
         conc = sed.conc
         for n, v in enumerate(VARIABLE_NAMES):
-            export_state[f"{v}_in_soil"] = conc[:, :, :, n]
+            export_state[f"{v}_in_soil"] = self._export(conc[:, :, :, n])
         for s in STATIC_EXPORTS:
-            export_state[f"{s}_in_soil"] = sed.field(s)
+            export_state[f"{s}_in_soil"] = self._export(sed.field(s))
         if self.cfg.bioturbation_profile == 3:
             for s in PROFILE3_EXPORTS:
-                export_state[f"{s}_in_soil"] = sed.field(s)
-        export_state["denit_in_soil"] = sed.field("denit")
+                export_state[f"{s}_in_soil"] = self._export(sed.field(s))
+        export_state["denit_in_soil"] = self._export(sed.field("denit"))
 
     # ---- Finalize (:1833-1861) ------------------------------------------------------------------------
     def finalize(self, import_state: State = None, export_state: State = None, clock=None):

@@ -149,6 +149,44 @@ def test_component_restart_through_netcdf_file(gpu, tmp_path):
     a.finalize(); b.finalize()
 
 
+def test_component_on_a_mesh(gpu, tmp_path):
+    """Mesh geometry (:391-446, :693-770): columns = owned elements, rank-1 surface fields, rank-2
+    <name>_in_soil fields; the numbers are those of the same columns on an (n,1) grid."""
+    from mossco_code_b200.component import FabmSedimentComponent
+    from mossco_code_b200.sediment import VARIABLE_NAMES
+    case = make_case("mesh", 23, 1, 12, 0.004, seed=12, land_fraction=0.2)
+    nml = dict(numlayers=12, dzmin=0.004, dt=360.0, dt_min=1.0, ode_method=2)
+    g, m = FabmSedimentComponent(), FabmSedimentComponent()
+    ig, eg, im, em = {}, {}, {}, {}
+    g.initialize_p1(ig, eg, grid_shape=(23, 1), grid_mask=1 - case.mask, run_nml=nml)
+    m.initialize_p1(im, em, grid_shape=(23,), grid_mask=(1 - case.mask)[:, 0], run_nml=nml)
+    st = _import_state(case, None)
+    ig.update(st)
+    im.update({k: v[:, 0].copy() for k, v in st.items()})           # rank-1 fields
+    for _ in range(2):
+        g.run(ig, eg, run_seconds=3600.0)
+        m.run(im, em, run_seconds=3600.0)
+    for v in VARIABLE_NAMES:
+        assert em[f"{v}_in_soil"].shape == (23, 12) and em[f"{v}_upward_flux_at_soil_surface"].shape == (23,)
+        assert np.array_equal(em[f"{v}_in_soil"], eg[f"{v}_in_soil"][:, 0, :])
+        assert np.array_equal(em[f"{v}_upward_flux_at_soil_surface"], eg[f"{v}_upward_flux_at_soil_surface"][:, 0])
+    assert em["temperature_in_soil"].shape == (23, 12) and em["denit_in_soil"].shape == (23, 12)
+    # restart hand-over with rank-2 <name>_in_soil fields, and through a file
+    r = FabmSedimentComponent()
+    ir, er = {}, {}
+    r.initialize_p1(ir, er, grid_shape=(23,), grid_mask=(1 - case.mask)[:, 0], run_nml=nml)
+    r.read_restart({k: v for k, v in em.items() if k.endswith("_in_soil")}, er)
+    assert np.array_equal(r.sed.conc, m.sed.conc)
+    path = str(tmp_path / "mesh_restart.nc")
+    m.write_restart_file(path)
+    r2 = FabmSedimentComponent()
+    r2.initialize_p1({}, {}, grid_shape=(23,), grid_mask=(1 - case.mask)[:, 0], run_nml=nml)
+    r2.read_restart_file(path)
+    assert np.array_equal(r2.sed.conc, m.sed.conc)
+    for c in (g, m, r, r2):
+        c.finalize()
+
+
 def test_component_presimulation(gpu, oracle):
     """presimulation_years > 0: 1-D spin-up broadcast to every wet column (:557-632)."""
     from mossco_code_b200.component import FabmSedimentComponent
