@@ -137,6 +137,61 @@ module msed_b200
       import; type(c_ptr), value :: h; character(kind=c_char), intent(in) :: id(128)
       integer(c_int), value :: nranks, rank
     end function
+    integer(c_int) function msed_comm_destroy(h) bind(c, name='msed_comm_destroy')
+      import; type(c_ptr), value :: h
+    end function
+    !> text of the last error of a handle (NULL handle: of the last failed msed_create); a C string
+    type(c_ptr) function msed_last_error(h) bind(c, name='msed_last_error')
+      import; type(c_ptr), value :: h
+    end function
+    type(c_ptr) function msed_version() bind(c, name='msed_version')
+      import
+    end function
+    !> sizeof(msed_config) / sizeof(msed_step_info): checked against c_sizeof in `initialize`
+    integer(c_size_t) function msed_sizeof(what) bind(c, name='msed_sizeof')
+      import; integer(c_int), value :: what
+    end function
+    integer(c_int) function msed_set_state_from_column(h, conc1d) bind(c, name='msed_set_state_from_column')
+      import; type(c_ptr), value :: h; real(c_double), intent(in) :: conc1d(*)
+    end function
+    integer(c_int) function msed_get_boundary(h, bdys, fluxes) bind(c, name='msed_get_boundary')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: bdys(*), fluxes(*)
+    end function
+    !> speculative two-step launches / chained Runge-Kutta stages (results are identical either way)
+    integer(c_int) function msed_set_step_fusion(h, enable) bind(c, name='msed_set_step_fusion')
+      import; type(c_ptr), value :: h; integer(c_int), value :: enable
+    end function
+    integer(c_int) function msed_set_exchange_chunks(h, nchunks) bind(c, name='msed_set_exchange_chunks')
+      import; type(c_ptr), value :: h; integer(c_int), value :: nchunks
+    end function
+    !> 1-D pre-simulation, fabm_sediment_component.F90:557-632
+    integer(c_int) function msed_spinup_column(cfg, bdys1d, fluxes1d, nsteps, method, conc1d, info) &
+        bind(c, name='msed_spinup_column')
+      import; type(msed_config), intent(in) :: cfg; real(c_double), intent(in) :: bdys1d(*), fluxes1d(*)
+      integer(c_int64_t), value :: nsteps; integer(c_int), value :: method
+      real(c_double), intent(out) :: conc1d(*); type(msed_step_info), intent(out) :: info
+    end function
+    !> pelagic boxes coupled on the device (config 5): bed-flux update as fabm_pelagic_component.F90:2100-2105
+    integer(c_int) function msed_pelagic_init(h, conc2d, wz2d, layer_height2d, temperature2d) &
+        bind(c, name='msed_pelagic_init')
+      import; type(c_ptr), value :: h
+      real(c_double), intent(in) :: conc2d(*), wz2d(*), layer_height2d(*), temperature2d(*)
+    end function
+    integer(c_int) function msed_pelagic_get(h, conc2d) bind(c, name='msed_pelagic_get')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: conc2d(*)
+    end function
+    integer(c_int) function msed_coupled_run(h, dt, method, coupling_seconds, ncouplings, info) &
+        bind(c, name='msed_coupled_run')
+      import; type(c_ptr), value :: h; real(c_double), value :: dt, coupling_seconds
+      integer(c_int), value :: method; integer(c_int64_t), value :: ncouplings
+      type(msed_step_info), intent(out) :: info
+    end function
+    integer(c_int) function msed_set_stream(h, cuda_stream) bind(c, name='msed_set_stream')
+      import; type(c_ptr), value :: h, cuda_stream
+    end function
+    integer(c_int) function msed_synchronize(h) bind(c, name='msed_synchronize')
+      import; type(c_ptr), value :: h
+    end function
   end interface
 
   !> sediment grid (part of type_sed), fabm_sediment_driver.F90:41-56
@@ -195,6 +250,11 @@ contains
           bioturbation_depth, bioturbation_min, bioturb_k_l, bioturb_L1, &
           bioturb_L2, bioturb_beta, bioturb_b, bioturb_dry_density
 
+    block  ! the bind(c) types above must have the layout the library was built with
+      type(msed_step_info) :: probe
+      if (msed_sizeof(0_c_int) /= c_sizeof(sed%cfg) .or. msed_sizeof(1_c_int) /= c_sizeof(probe)) &
+        stop 'msed_b200: struct layout differs from libmsed_b200.so (include/msed.h changed?)'
+    end block
     rc = msed_config_defaults(sed%cfg)
     diffusivity = sed%cfg%diffusivity; bioturbation = sed%cfg%bioturbation
     bioturbation_profile = sed%cfg%bioturbation_profile
