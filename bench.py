@@ -267,7 +267,8 @@ def main():
         sed.set_par_surface(par)
     sed.init_concentrations()
     sed.set_boundary(bdys, fluxes)
-    init_flag_collective(sed)
+    if os.environ.get("MSED_BENCH_LOCAL_ACCEPT") != "1":   # diagnosis only: per-tile accept decision
+        init_flag_collective(sed)
     sed.set_step_fusion(args.fusion == "on")
     cells_local = inum * rows * knum * (1.0 if land == 0 else float((mask == 0).mean()))
     cells_total = torch.tensor([cells_local], dtype=torch.float64, device="cuda")
