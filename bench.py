@@ -267,6 +267,8 @@ def main():
         sed.set_par_surface(par)
     sed.init_concentrations()
     sed.set_boundary(bdys, fluxes)
+    if os.environ.get("MSED_BENCH_CHUNKS"):                 # diagnosis only: PCIe chunking of the e2e Run
+        sed.set_exchange_chunks(int(os.environ["MSED_BENCH_CHUNKS"]))
     if os.environ.get("MSED_BENCH_LOCAL_ACCEPT") != "1":   # diagnosis only: per-tile accept decision
         init_flag_collective(sed)
     sed.set_step_fusion(args.fusion == "on")
