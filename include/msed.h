@@ -249,6 +249,27 @@ typedef struct msed_pelagic_fluxes {
 int msed_benthic_pelagic_coupler(msed_handle *h, const msed_benthic_pelagic_params *par,
                                  const msed_pelagic_fluxes *out);
 
+/* soil_pelagic_connector Run, src/mediators/soil_pelagic_connector.F90:179-981 (the generic successor
+ * of benthic_pelagic_coupler; namelist /soil_pelagic_connector/ :140, defaults :36-41).  Output
+ * pointers are host arrays (inum,jnum); NULL = field not in the export state.  nitrate is passed
+ * through unscaled (:333-359), ammonium = convertN*NH4 (:409-411), DIN = (NH4+NO3+dinflux_const/year)*
+ * convertN (:467-472), DIP = convertP*(PO4+dipflux_const/year) (:529-533).  Oxygen and reduced
+ * substances: both wanted -> plain copies (:660-679); only odu -> odu-oxygen (:696-698); only oxygen
+ * -> oxygen-odu (:718-720).  detC = sum of the detritus*carbon fluxes (:842-874); detN and detP are
+ * sums over import fields named detritus*nitrogen / detritus*phosphorous (:786,:933), of which
+ * omexdia_p has none: both are 0. */
+typedef struct msed_soil_pelagic_params {
+    double dinflux_const;   /* :36, per year */
+    double dipflux_const;   /* :37; <0: dinflux_const/16 (:156) */
+    double convertN;        /* :41 */
+    double convertP;        /* :40 */
+} msed_soil_pelagic_params;
+typedef struct msed_soil_pelagic_fluxes {
+    double *nitrate, *ammonium, *DIN, *DIP, *oxygen, *odu, *detN, *detC, *detP;
+} msed_soil_pelagic_fluxes;
+int msed_soil_pelagic_connector(msed_handle *h, const msed_soil_pelagic_params *par,
+                                const msed_soil_pelagic_fluxes *out);
+
 /* ---- execution control -------------------------------------------------------------------- */
 /* all work is enqueued on this cudaStream_t (default: a private non-blocking stream) */
 int msed_set_stream(msed_handle *h, void *cuda_stream);

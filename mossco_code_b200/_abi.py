@@ -87,6 +87,15 @@ class PelagicFluxes(C.Structure):
         "nitrate", "ammonium", "DIN", "DIP", "detN", "detC", "detP", "oxygen")]
 
 
+class SoilPelagicParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("dinflux_const", "dipflux_const", "convertN", "convertP")]
+
+
+class SoilPelagicFluxes(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in (
+        "nitrate", "ammonium", "DIN", "DIP", "oxygen", "odu", "detN", "detC", "detP")]
+
+
 ALLREDUCE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 
 _dp = C.POINTER(C.c_double)
@@ -131,6 +140,7 @@ SYMBOLS = {
     "msed_coupled_run": (C.c_int, [_h, C.c_double, C.c_int, C.c_double, C.c_int64, C.POINTER(StepInfo)]),
     "msed_pelagic_benthic_coupler": (C.c_int, [_h, C.POINTER(PelagicState)]),
     "msed_benthic_pelagic_coupler": (C.c_int, [_h, C.POINTER(BenthicPelagicParams), C.POINTER(PelagicFluxes)]),
+    "msed_soil_pelagic_connector": (C.c_int, [_h, C.POINTER(SoilPelagicParams), C.POINTER(SoilPelagicFluxes)]),
     "msed_set_stream": (C.c_int, [_h, C.c_void_p]),
     "msed_synchronize": (C.c_int, [_h]),
     "msed_device_state": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

@@ -1423,6 +1423,33 @@ int msed_benthic_pelagic_coupler(msed_handle *h, const msed_benthic_pelagic_para
     return MSED_OK;
 }
 
+int msed_soil_pelagic_connector(msed_handle *h, const msed_soil_pelagic_params *par,
+                                const msed_soil_pelagic_fluxes *out)
+{
+    if (!h || !par || !out) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    // InitializeP1 :156: a negative dipflux_const follows dinflux_const in Redfield proportion
+    const double dip = par->dipflux_const < 0.0 ? par->dinflux_const / 16.0 : par->dipflux_const;
+    // 86400.0*365.0 is a default-real product in the reference (:469,:530); 31536000 is exact in binary32
+    const double year = 86400.0 * 365.0;
+    const int oxy_mode = (out->oxygen ? 1 : 0) | (out->odu ? 2 : 0);
+    soil_pelagic_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
+        h->scratch, h->fluxes, h->ld, h->ncol, par->dinflux_const / year, dip / year, par->convertN,
+        par->convertP, oxy_mode);
+    CUDA_TRY(h, cudaGetLastError());
+    struct { double *dst; int row; } rows[9] = {
+        {out->nitrate, 0}, {out->ammonium, 1}, {out->DIN, 2}, {out->DIP, 3}, {out->oxygen, 4},
+        {out->odu, 5},     {out->detC, 6},     {out->detN, 7}, {out->detP, 7}};
+    for (int r = 0; r < 9; ++r)
+        if (rows[r].dst)
+            CUDA_TRY(h, cudaMemcpyAsync(rows[r].dst, h->scratch + (size_t)rows[r].row * h->ld,
+                                        (size_t)h->ncol * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
 int msed_set_stream(msed_handle *h, void *cuda_stream)
 {
     if (!h) return MSED_ERR_ARG;

@@ -330,6 +330,31 @@ __global__ void benthic_pelagic_kernel(double *out, const double *fluxes, size_t
     out[7 * ld + col] = __dsub_rn(up[6], up[7]);                                         // :281
 }
 
+// soil_pelagic_connector Run (src/mediators/soil_pelagic_connector.F90:179-981), the generic successor of
+// benthic_pelagic_coupler.  out rows: 0 nitrate 1 ammonium 2 DIN 3 DIP 4 oxygen 5 odu 6 detC 7 zero.
+// Row 7 serves both detritus nitrogen and detritus phosphorus: the connector sums the import fields that
+// match 'detritus*nitrogen_upward_flux_at_soil_surface' (:786) and 'detritus*phosphorous_upward_flux_at_
+// soil_surface' (:933); omexdia_p exports neither (its P pool is spelled 'detritus_labile_phosphorus'), so
+// both sums stay at their initial 0.0 (:771-773, :918-920).
+// oxy_mode: 3 = oxygen and odu both wanted (plain copies, :660-679), 2 = only odu (odu - oxygen, :696-698),
+// 1 = only oxygen (oxygen - odu, :718-720).
+__global__ void soil_pelagic_kernel(double *out, const double *fluxes, size_t ld, int ncol, double din_per_s,
+                                    double dip_per_s, double convertN, double convertP, int oxy_mode)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    double up[NV];
+    for (int n = 0; n < NV; ++n) up[n] = -fluxes[(size_t)n * ld + col];                 // component :1819
+    out[0 * ld + col] = up[4];                                                           // :333-359 (no convertN)
+    out[1 * ld + col] = __dmul_rn(convertN, up[5]);                                      // :409-411
+    out[2 * ld + col] = __dmul_rn(__dadd_rn(__dadd_rn(up[5], up[4]), din_per_s), convertN);  // :467-472
+    out[3 * ld + col] = __dmul_rn(convertP, __dadd_rn(up[3], dip_per_s));                // :529-533
+    out[4 * ld + col] = (oxy_mode == 1) ? __dsub_rn(up[6], up[7]) : up[6];               // :677-679, :718-720
+    out[5 * ld + col] = (oxy_mode == 2) ? __dsub_rn(up[7], up[6]) : up[7];               // :660-662, :696-698
+    out[6 * ld + col] = __dadd_rn(__dadd_rn(0.0, up[0]), up[1]);                         // :842-874
+    out[7 * ld + col] = 0.0;                                                             // :771-773, :918-920
+}
+
 // pelagic boxes take up the bed flux: conc = conc + bfl*dt/layer_height where layer_height > 0
 // (src/components/fabm_pelagic_component.F90:2100-2105); bfl = upward flux = -fluxes (component :1819)
 __global__ void pelagic_flux_kernel(double *pel, const double *fluxes, const double *height,

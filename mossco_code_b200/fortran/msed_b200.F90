@@ -19,6 +19,7 @@ module msed_b200
   use, intrinsic :: iso_c_binding
   implicit none
   private
+  public :: msed_soil_pelagic_connector
 
   integer, parameter, public :: rk = c_double
   integer, parameter, public :: MSED_NVAR = 8
@@ -53,6 +54,16 @@ module msed_b200
     integer(c_int64_t) :: kernel_launches
     integer(c_int64_t) :: fused_pairs
     real(c_double)     :: fused_ms
+  end type
+
+  !> mirror `struct msed_soil_pelagic_params` / `msed_soil_pelagic_fluxes`: the soil_pelagic_connector
+  !! mediator's Run (src/mediators/soil_pelagic_connector.F90:179-981) on the device.  The flux members
+  !! are `c_loc` of the export fields' farrayPtr (c_null_ptr = field not in the export state).
+  type, bind(c), public :: msed_soil_pelagic_params
+    real(c_double) :: dinflux_const, dipflux_const, convertN, convertP
+  end type
+  type, bind(c), public :: msed_soil_pelagic_fluxes
+    type(c_ptr) :: nitrate, ammonium, DIN, DIP, oxygen, odu, detN, detC, detP
   end type
 
   interface
@@ -185,6 +196,11 @@ module msed_b200
       import; type(c_ptr), value :: h; real(c_double), value :: dt, coupling_seconds
       integer(c_int), value :: method; integer(c_int64_t), value :: ncouplings
       type(msed_step_info), intent(out) :: info
+    end function
+    integer(c_int) function msed_soil_pelagic_connector(h, par, fluxes_out) &
+        bind(c, name='msed_soil_pelagic_connector')
+      import; type(c_ptr), value :: h
+      type(msed_soil_pelagic_params), intent(in) :: par; type(msed_soil_pelagic_fluxes), intent(in) :: fluxes_out
     end function
     integer(c_int) function msed_set_stream(h, cuda_stream) bind(c, name='msed_set_stream')
       import; type(c_ptr), value :: h, cuda_stream

@@ -316,6 +316,21 @@ class SedimentDriver:
         self._check(self._lib.msed_benthic_pelagic_coupler(self._h, C.byref(par), C.byref(out)))
         return res
 
+    def soil_pelagic_connector(self, want=("nitrate", "ammonium", "DIP", "oxygen", "odu", "detC"),
+                               dinflux_const=0.0, dipflux_const=-1.0, convertN=1.0, convertP=1.0):
+        """``soil_pelagic_connector`` Run (src/mediators/soil_pelagic_connector.F90:179-981): returns a
+        dict of the requested pelagic flux fields; which of oxygen / odu is wanted selects the
+        reference's three oxygen branches (:660-720)."""
+        par = _abi.SoilPelagicParams(dinflux_const, dipflux_const, convertN, convertP)
+        out, res = _abi.SoilPelagicFluxes(), {}
+        for name in want:
+            if not hasattr(out, name):
+                raise AttributeError(f"msed_soil_pelagic_fluxes has no field {name!r}")
+            res[name] = np.zeros(self.shape2d, order="F")
+            setattr(out, name, _ptr(res[name]))
+        self._check(self._lib.msed_soil_pelagic_connector(self._h, C.byref(par), C.byref(out)))
+        return res
+
     # -- execution / multi-GPU ---------------------------------------------------------------
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.msed_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -904,3 +904,39 @@ void osed_benthic_pelagic_coupler(size_t n2, const double *up, double dinflux_co
         out[c + n2 * 7] = oxy - odu;                                                /* :281 */
     }
 }
+
+/* soil_pelagic_connector Run, src/mediators/soil_pelagic_connector.F90:179-981.
+ * up(n2,8) = <var>_upward_flux_at_soil_surface; out(n2,9): nitrate ammonium DIN DIP oxygen odu detN detC detP.
+ * want_oxygen / want_odu: which of the two fields the export state holds (branches :660-720). */
+void osed_soil_pelagic_connector(size_t n2, const double *up, double dinflux_const, double dipflux_const,
+                                 double convertN, double convertP, int want_oxygen, int want_odu, double *out)
+{
+    if (dipflux_const < 0.0) dipflux_const = dinflux_const / 16.0;                  /* :156 */
+    const double year = (double)(86400.0f * 365.0f);                                /* default-real product */
+    for (size_t c = 0; c < n2; ++c) {
+        const double ldetC = up[c], sdetC = up[c + n2], po4 = up[c + n2 * 3];
+        const double no3 = up[c + n2 * 4], nh3 = up[c + n2 * 5], oxy = up[c + n2 * 6], odu = up[c + n2 * 7];
+        out[c + n2 * 0] = no3;                                                      /* :333-359 */
+        out[c + n2 * 1] = convertN * nh3;                                           /* :409-411 */
+        out[c + n2 * 2] = (nh3 + no3 + dinflux_const / year) * convertN;            /* :467-472 */
+        out[c + n2 * 3] = convertP * (po4 + dipflux_const / year);                  /* :529-533 */
+        if (want_odu && want_oxygen) {                                              /* :660-679 */
+            out[c + n2 * 5] = odu;
+            out[c + n2 * 4] = oxy;
+        } else if (want_odu) {                                                      /* :696-698 */
+            out[c + n2 * 5] = odu - oxy;
+            out[c + n2 * 4] = oxy;   /* not in the export state; left as the plain flux */
+        } else {                                                                    /* :718-720 */
+            out[c + n2 * 4] = oxy - odu;
+            out[c + n2 * 5] = odu;   /* not in the export state */
+        }
+        double detN = 0.0, detC = 0.0, detP = 0.0;                                  /* :771,:842,:918 */
+        /* omexdia_p exports detritus_{labile,semilabile}_carbon only: no 'detritus*nitrogen' (:786) and no
+         * 'detritus*phosphorous' (:933; the model spells it 'phosphorus') field exists to be summed */
+        detC = detC + ldetC;                                                        /* :869-874 */
+        detC = detC + sdetC;
+        out[c + n2 * 6] = detN;
+        out[c + n2 * 7] = detC;
+        out[c + n2 * 8] = detP;
+    }
+}

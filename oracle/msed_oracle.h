@@ -151,6 +151,9 @@ double osed_bench_tiled(int inum, int jnum, int knum, double dzmin, const osed_s
 void osed_pelagic_benthic_coupler(size_t n2, const double *const in[10], double *csurf, double *wz);
 void osed_benthic_pelagic_coupler(size_t n2, const double *up, double dinflux_const, double dipflux_const,
                                   double convertN, double NC_fdet, double NC_sdet, double *out);
+/* soil_pelagic_connector Run (src/mediators/soil_pelagic_connector.F90:179-981); out(n2,9) */
+void osed_soil_pelagic_connector(size_t n2, const double *up, double dinflux_const, double dipflux_const,
+                                 double convertN, double convertP, int want_oxygen, int want_odu, double *out);
 
 /* ---- flat handle API for the Python test harness (oracle/msed_oracle.py) ------------------- */
 enum { OSEDPY_CONC = 0, OSEDPY_BDYS, OSEDPY_FLUXES, OSEDPY_POROSITY, OSEDPY_INTF_POROSITY,

@@ -91,6 +91,9 @@ def load(fast: bool = False):
                                      C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                      C.c_int, C.POINTER(C.c_long)]
     lib.osed_pelagic_benthic_coupler.argtypes = [C.c_size_t, C.POINTER(dp), dp, dp]
+    lib.osed_soil_pelagic_connector.argtypes = [C.c_size_t, dp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                C.c_int, C.c_int, dp]
+    lib.osed_soil_pelagic_connector.restype = None
     lib.osed_benthic_pelagic_coupler.argtypes = [C.c_size_t, dp, C.c_double, C.c_double, C.c_double,
                                                  C.c_double, C.c_double, dp]
     _libs[key] = lib
@@ -350,3 +353,17 @@ def benthic_pelagic_coupler(up, dinflux_const=0.0, dipflux_const=-1.0, convertN=
     load().osed_benthic_pelagic_coupler(n2, _p(up), dinflux_const, dipflux_const, convertN, NC_fdet, NC_sdet,
                                         _p(out))
     return {name: out[..., i] for i, name in enumerate(B2P_FIELDS)}
+
+
+S2P_FIELDS = ("nitrate", "ammonium", "DIN", "DIP", "oxygen", "odu", "detN", "detC", "detP")
+
+
+def soil_pelagic_connector(up, want=S2P_FIELDS, dinflux_const=0.0, dipflux_const=-1.0, convertN=1.0,
+                           convertP=1.0):
+    """Restated soil_pelagic_connector Run; ``want`` = the fields the export state holds."""
+    up = np.asfortranarray(np.asarray(up, dtype=np.float64))
+    n2 = int(np.prod(up.shape[:-1]))
+    out = np.zeros(up.shape[:-1] + (9,), order="F")
+    load().osed_soil_pelagic_connector(n2, _p(up), dinflux_const, dipflux_const, convertN, convertP,
+                                       int("oxygen" in want), int("odu" in want), _p(out))
+    return {name: out[..., i] for i, name in enumerate(S2P_FIELDS) if name in want}

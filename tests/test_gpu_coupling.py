@@ -96,6 +96,35 @@ def test_pelagic_soil_couplers(gpu, oracle, full):
         assert scaled_err(sed.fluxes, ref.fluxes) <= 1e-10
 
 
+@pytest.mark.parametrize("want", [("nitrate", "ammonium", "DIN", "DIP", "oxygen", "odu", "detN", "detC", "detP"),
+                                  ("DIN", "DIP", "odu", "detC"), ("nitrate", "ammonium", "DIP", "oxygen", "detP")])
+def test_soil_pelagic_connector(gpu, oracle, want):
+    """soil_pelagic_connector Run (src/mediators/soil_pelagic_connector.F90:179-981) on the device, incl.
+    the three oxygen/odu branches (:660-720) and the namelist factors (:140)."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    case = make_case("s2p", 11, 5, 15, 0.004, seed=67, land_fraction=0.2)
+    cfg = default_config(inum=11, jnum=5, knum=15, dzmin=0.004, dt_min=1.0)
+    kw = dict(dinflux_const=0.3, dipflux_const=-1.0 if "odu" in want else 0.01, convertN=1.5, convertP=0.75)
+    with SedimentDriver(cfg) as sed:
+        sed.set_mask(case.mask)
+        sed.init_concentrations()
+        sed.set_boundary(case.bdys, case.fluxes)
+        assert sed.step(360.0, 2, 3) == 0
+        got = sed.soil_pelagic_connector(want=want, **kw)
+        ref = oracle.soil_pelagic_connector(-sed.fluxes, want=want, **kw)
+        assert set(got) == set(want) == set(ref)
+        for k in want:
+            assert np.array_equal(got[k], ref[k]), k      # same IEEE operation sequence
+        up = -sed.fluxes
+        if "odu" in want and "oxygen" not in want:
+            assert np.array_equal(got["odu"], up[:, :, 7] - up[:, :, 6])
+        if "detC" in want:
+            assert np.array_equal(got["detC"], up[:, :, 0] + up[:, :, 1])
+        for k in ("detN", "detP"):
+            if k in want:
+                assert not got[k].any()
+
+
 @pytest.mark.parametrize("nchunks,seconds", [(4, 3600.0), (3, 1000.0), (5, 360.0), (1, 3600.0), (4, 720.0)])
 def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds):
     """msed_run_exchange (chunk-pipelined PCIe/compute overlap) must be bit-identical to

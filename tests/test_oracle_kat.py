@@ -308,3 +308,26 @@ def test_boundary_conditions_formulas(oracle):
         assert np.array_equal(s.bdys[:, :, n + 1], cs[n])
         want = -(s.conc[:, :, 0, n] - cs[n]) / dz[:, :, 0] * (0.9 + 0.9 + temp * 0.035) * por[:, :, 0] / 86400. / 10000.
         assert np.allclose(s.fluxes[:, :, n], want, rtol=1e-15)
+
+
+def test_soil_pelagic_connector_formulas(oracle):
+    """soil_pelagic_connector Run against the formulas read off the reference
+    (src/mediators/soil_pelagic_connector.F90:333-359,:409-411,:467-472,:529-533,:660-720,:842-874)."""
+    rng = np.random.default_rng(12)
+    up = np.asfortranarray(rng.normal(size=(6, 4, 8)) * 1e-5)
+    year = float(np.float32(86400.0) * np.float32(365.0))
+    assert year == 31536000.0
+    ldetC, sdetC, po4, no3, nh3, oxy, odu = (up[:, :, n] for n in (0, 1, 3, 4, 5, 6, 7))
+    r = oracle.soil_pelagic_connector(up, dinflux_const=0.3, convertN=1.5, convertP=0.75)
+    assert np.array_equal(r["nitrate"], no3)                                  # no convertN on nitrate
+    assert np.array_equal(r["ammonium"], 1.5 * nh3)
+    assert np.array_equal(r["DIN"], (nh3 + no3 + 0.3 / year) * 1.5)
+    assert np.array_equal(r["DIP"], 0.75 * (po4 + (0.3 / 16.0) / year))       # dipflux_const < 0: Redfield (:156)
+    assert np.array_equal(r["oxygen"], oxy) and np.array_equal(r["odu"], odu)
+    assert np.array_equal(r["detC"], ldetC + sdetC)
+    assert not r["detN"].any() and not r["detP"].any()                        # no matching import fields
+    r = oracle.soil_pelagic_connector(up, want=("odu", "DIP"), dipflux_const=0.02)
+    assert np.array_equal(r["odu"], odu - oxy) and set(r) == {"odu", "DIP"}
+    assert np.array_equal(r["DIP"], po4 + 0.02 / year)
+    r = oracle.soil_pelagic_connector(up, want=("oxygen",))
+    assert np.array_equal(r["oxygen"], oxy - odu)
