@@ -215,8 +215,10 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fusion", default="on", choices=["on", "off"],
-                    help="speculative two-step kernels (msed_set_step_fusion); results are identical")
+    ap.add_argument("--fusion", default="on", choices=["on", "off", "pairs", "chains"],
+                    help="speculative fused launches (msed_set_step_fusion); results are identical.  on = auto: "
+                         "chains (warp per column, up to 16 steps per launch) where knum <= 32, else pairs "
+                         "(thread per column, two steps per launch)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: native libraries that printf to fd 1 (NCCL's "NCCL version ..."
     # banner) are sent to stderr, the JSON line goes to the original stdout
@@ -271,7 +273,7 @@ def main():
         sed.set_exchange_chunks(int(os.environ["MSED_BENCH_CHUNKS"]))
     if os.environ.get("MSED_BENCH_LOCAL_ACCEPT") != "1":   # diagnosis only: per-tile accept decision
         init_flag_collective(sed)
-    sed.set_step_fusion(args.fusion == "on")
+    sed.set_step_fusion({"on": "auto"}.get(args.fusion, args.fusion))
     cells_local = inum * rows * knum * (1.0 if land == 0 else float((mask == 0).mean()))
     cells_total = torch.tensor([cells_local], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -293,7 +295,7 @@ def main():
     # a long timed region restarts from the initial state every SEGMENT steps (the re-initialisation
     # kernel runs inside the timed region and is counted in gpu_launches).
     totals = dict(kernel_ms=0.0, fused_ms=0.0, kernel_launches=0, subcycle_warnings=0, rhs_evaluations=0,
-                  steps_done=0, fused_pairs=0, reinits=0)
+                  steps_done=0, fused_pairs=0, fused_steps=0, reinits=0)
 
     def timed_steps(n):
         done = 0
@@ -334,13 +336,14 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1), totals["kernel_ms"], totals["fused_ms"]], dtype=torch.float64,
                       device="cuda")
     counts = torch.tensor([totals["kernel_launches"] + totals["reinits"], totals["subcycle_warnings"],
-                           totals["rhs_evaluations"], totals["steps_done"], totals["fused_pairs"]],
+                           totals["rhs_evaluations"], totals["steps_done"], totals["fused_pairs"],
+                           totals["fused_steps"]],
                           dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.MAX)
     total_ms, kernel_ms, fused_ms = float(ms[0]), float(ms[1]), float(ms[2])
-    launches, subcycles, rhs_evals, steps_done, fused_pairs = (int(x) for x in counts.tolist())
+    launches, subcycles, rhs_evals, steps_done, fused_pairs, fused_steps = (int(x) for x in counts.tolist())
     assert steps_done == args.steps
     value = cells_total * args.steps / (total_ms * 1e-3)
 
@@ -390,7 +393,18 @@ def main():
         balg = b_alg(knum)
         cells_per_gpu = cells_total / world
         tpc_single, tpc_pair = traffic_per_cell("column_kernel"), traffic_per_cell("pair_kernel")
-        if fused_pairs > 0:
+        if fused_pairs > 0 and fused_steps > 2 * fused_pairs:
+            # dominant kernel: the chain launch (warp per column, state in registers, several steps)
+            steps_per_launch = fused_steps / fused_pairs
+            kernel_name = (f"msed::chain_kernel<OMEXDIA_P, adaptive, clip> ({steps_per_launch:.1f} ode_solver steps "
+                           f"per launch on average)")
+            cells_per_launch = steps_per_launch * cells_per_gpu
+            avg_launch_s = fused_ms * 1e-3 / fused_pairs
+            tpc = traffic_per_cell("chain_kernel")
+            note = ("step fusion, chains: the column state stays in registers for all steps of a launch (one HBM "
+                    "round trip per launch), so frac counts algorithmic bytes the kernel never moves and reads "
+                    "> 1; the launch is fp64/issue-bound; --fusion pairs / off time the other kernels")
+        elif fused_pairs > 0:
             # dominant kernel: the fused two-step launch (2 cell-updates per cell-layer per launch)
             kernel_name = "msed::pair_kernel<OMEXDIA_P, adaptive> (two ode_solver steps per launch)"
             cells_per_launch = 2.0 * cells_per_gpu
@@ -433,7 +447,8 @@ def main():
                          "achieved_dram": None if tpc is None else tpc * cells_per_launch / avg_launch_s / 1e9,
                          "kernel": kernel_name, "cell_updates_per_launch": cells_per_launch,
                          "algorithmic_bytes_per_cell_update": balg, "peak_source": peak_src,
-                         "avg_launch_ms": avg_launch_s * 1e3, "fused_pairs": fused_pairs, "note": note},
+                         "avg_launch_ms": avg_launch_s * 1e3, "fused_pairs": fused_pairs,
+                         "fused_steps": fused_steps, "note": note},
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_reference(wl, 0, 0, target_seconds=15.0)

@@ -108,8 +108,9 @@ typedef struct msed_step_info {
     int32_t nan_detected;
     double kernel_ms;             /* device time of the stepping kernels (CUDA events) */
     int64_t kernel_launches;      /* launches of this library's kernels in the call */
-    int64_t fused_pairs;          /* committed two-step launches (msed_set_step_fusion), 2 steps each */
-    double fused_ms;              /* part of kernel_ms spent in the fused-pair phase */
+    int64_t fused_pairs;          /* committed fused launches (msed_set_step_fusion): pairs or chains */
+    double fused_ms;              /* part of kernel_ms spent in the fused phase */
+    int64_t fused_steps;          /* steps those launches advanced (2 per pair, up to 16 per chain) */
 } msed_step_info;
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -187,11 +188,15 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
 int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
                       const double *temperature2d, const double *const *csurf, const double *const *wz,
                       double *upward_fluxes, msed_step_info *info);
-/* Step fusion (default on): Euler / adaptive-Euler steps are issued in speculative pairs that read and
- * write the state once for two steps; a pair is committed only if neither step would be rejected
- * (solver_library.F90:126) or stopped by check_NaN, otherwise the same steps are redone singly from the
- * untouched state.  Results are bit-identical with fusion on or off; 0 switches it off. */
-int msed_set_step_fusion(msed_handle *h, int enable);
+/* Step fusion (default on): Euler / adaptive-Euler steps are issued in speculative fused launches that
+ * read and write the state once for several steps -- pairs (thread per column, two steps) or, for
+ * knum <= 32, chains (warp per column with the state in registers, up to 16 steps).  A fused launch is
+ * committed only if none of its steps would be rejected (solver_library.F90:126) or stopped by
+ * check_NaN, otherwise the same steps are redone singly from the untouched state.  Results are
+ * bit-identical in every mode.  mode: 0 off, 1 auto (default: chains where they apply, else pairs),
+ * 2 pairs only, 3 chains wherever knum allows.  Environment MSED_CHAIN_MAX_COLS limits the tile size
+ * (columns) up to which mode 1 picks chains. */
+int msed_set_step_fusion(msed_handle *h, int mode);
 /* number of column chunks msed_run_exchange uses (0 = choose from the tile size, 1 = no overlap) */
 int msed_set_exchange_chunks(msed_handle *h, int nchunks);
 /* 1-D pre-simulation (component :557-632) for the handle's configuration; conc1d(1,1,knum,nvar) out.

@@ -67,7 +67,7 @@ class StepInfo(C.Structure):
         ("steps_done", C.c_int64), ("rhs_evaluations", C.c_int64), ("subcycle_warnings", C.c_int64),
         ("last_min_dt", C.c_double), ("last_min_dt_grid_cell", C.c_int32 * 4),
         ("nan_detected", C.c_int32), ("kernel_ms", C.c_double), ("kernel_launches", C.c_int64),
-        ("fused_pairs", C.c_int64), ("fused_ms", C.c_double),
+        ("fused_pairs", C.c_int64), ("fused_ms", C.c_double), ("fused_steps", C.c_int64),
     ]
 
 

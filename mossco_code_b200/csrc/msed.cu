@@ -85,7 +85,9 @@ struct msed_handle {
     cudaStream_t copy_stream = nullptr;           // PCIe traffic of msed_run_exchange
     cudaEvent_t ev_pool[2 * 16] = {};             // per-chunk H2D-done / compute-done events
     int exchange_chunks = 0;                      // 0 = choose from the tile size
-    int step_fusion = 1;                          // fused pairs of Euler/adaptive steps allowed
+    int step_fusion = 1;                          // 0 off, 1 auto (chains where they apply, else pairs),
+                                                  // 2 pairs only, 3 chains wherever knum allows
+    long long chain_max_cols = 0;                 // auto mode: tiles up to this many columns take chain_kernel
     int pair_cooldown = 0;                        // steps to run singly after a rejection / failed pair
     long long pairs_committed = 0;
     ncclComm_t comm = nullptr;
@@ -294,6 +296,24 @@ cudaError_t launch_pair(const msed_handle *h, int method, const KParams &p)
     return cudaGetLastError();
 }
 
+// one launch = m chained Euler / adaptive-Euler steps, warp per column (msed_chain.cuh)
+cudaError_t launch_chain(const msed_handle *h, int method, const KParams &p, int m, bool clip)
+{
+    const dim3 grid(nblocks(p.col_end - p.col0, CHAIN_WARPS)), block(CHAIN_BLOCK);
+    const bool adaptive = method == MSED_ADAPTIVE_EULER;
+#define MSED_CHAIN(MODEL, AD, CL) chain_kernel<MODEL, AD, CL><<<grid, block, 0, h->stream>>>(p, m)
+#define MSED_CHAIN_MODEL(MODEL)                                                                        \
+    do {                                                                                               \
+        if (adaptive) { if (clip) MSED_CHAIN(MODEL, true, true); else MSED_CHAIN(MODEL, true, false); }   \
+        else          { if (clip) MSED_CHAIN(MODEL, false, true); else MSED_CHAIN(MODEL, false, false); } \
+    } while (0)
+    if (h->cfg.model == MSED_MODEL_OMEXDIA_P) MSED_CHAIN_MODEL(MSED_MODEL_OMEXDIA_P);
+    else MSED_CHAIN_MODEL(MSED_MODEL_NONE);
+#undef MSED_CHAIN_MODEL
+#undef MSED_CHAIN
+    return cudaGetLastError();
+}
+
 // one launch = two chained Runge-Kutta stages (msed_rkpair.cuh); which = 0 for stages 1+2, 1 for 3+4
 cudaError_t launch_rk_pair(const msed_handle *h, int method, int which, const KParams &p)
 {
@@ -400,6 +420,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     *h->ctl_host = c;
     CUDA_TRY(h, cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
 
+    const bool wrapper_clip = c.do_clip != 0;  // check_NaN + minimum clip after every step (chain_kernel<.., CLIP>)
     KParams p;
     fill_params(h, p);
     InitVals minimum;
@@ -434,12 +455,26 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                          (h->cfg.model == MSED_MODEL_OMEXDIA_P || h->cfg.model == MSED_MODEL_NONE) &&
                          h->cfg.bioturbation_profile != 3 && !h->cfg.distributed_pom_flux && h->por_mode != 0;
     const bool rk_fused = fusable && !single_attempt;
-    long long npairs = 0;
-    bool last_is_pair = false;  // an even number of steps ends with a pair, which then leaves the
-                                // "state of the last get_rhs call" diagnostic behind (KParams::denit_out)
+    long long npairs = 0;       // fused launches planned (pairs or chains)
+    long long fused_planned = 0;  // ... and the steps they hold
+    bool last_is_pair = false;  // the call ends with a fused launch, which then leaves the "state of
+                                // the last get_rhs call" diagnostic behind (KParams::denit_out)
     h->denit_valid = false;
-    if (fusable && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 2) {
+    // chains (msed_chain.cuh) cover every step of the call, whatever its parity
+    const bool chain_fit = h->K <= CHAIN_MAX_LAYERS &&
+                           (h->step_fusion == 3 || (h->step_fusion == 1 && h->ncol <= h->chain_max_cols));
+    const bool use_chain = fusable && chain_fit && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 1;
+    int chain_base = 0, chain_extra = 0;
+    if (use_chain) {
+        npairs = (nsteps + MSED_CHAIN_MAX_STEPS - 1) / MSED_CHAIN_MAX_STEPS;
+        chain_base = (int)(nsteps / npairs);     // the first chain_extra chains hold one step more
+        chain_extra = (int)(nsteps % npairs);
+        fused_planned = nsteps;
+        last_is_pair = true;
+        if ((rc = ensure_denit(h))) return rc;
+    } else if (fusable && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 2) {
         npairs = nsteps / 2;
+        fused_planned = 2 * npairs;
         last_is_pair = (2 * npairs == nsteps);
         if (last_is_pair && (rc = ensure_denit(h))) return rc;
     }
@@ -459,6 +494,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     bool first_pending = plan && plan->first && single_attempt;
     for (long long q = 0; q < npairs; ++q) {
         const bool last_pair = last_is_pair && q == npairs - 1;
+        const int m = use_chain ? chain_base + (q < chain_extra ? 1 : 0) : 2;  // steps in this launch
         const bool chunk_last = last_pair && plan && plan->last;
         KParams pq = p;
         if (last_pair) pq.denit_out = h->denit;
@@ -469,22 +505,23 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                 KParams pc = pq;
                 pc.col0 = plan->c0[c];
                 pc.col_end = plan->c1[c];
-                CUDA_TRY(h, launch_pair(h, method, pc));
+                CUDA_TRY(h, use_chain ? launch_chain(h, method, pc, m, wrapper_clip) : launch_pair(h, method, pc));
                 launches += 1;
                 if (chunk_last)
                     if ((rc = export_chunk(c))) return rc;
             }
             first_pending = false;
         } else {
-            CUDA_TRY(h, launch_pair(h, method, pq));
+            CUDA_TRY(h, use_chain ? launch_chain(h, method, pq, m, wrapper_clip) : launch_pair(h, method, pq));
             launches += 1;
         }
         if (collective)
             if ((rc = reduce_flags(h))) return rc;
-        pair_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method);
+        if (use_chain) chain_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method, m);
+        else pair_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method);
         launches += 1;
     }
-    const long long singles_planned = nsteps - 2 * npairs;
+    const long long singles_planned = nsteps - fused_planned;
     CUDA_TRY(h, cudaEventRecord(h->ev_mid, h->stream));
 
     long long remaining = singles_planned, issued = 0;
@@ -596,6 +633,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         info->kernel_ms = ms;
         info->kernel_launches = launches;
         info->fused_pairs = (npairs > 0 && r.pair_failures == 0) ? npairs : 0;
+        info->fused_steps = (npairs > 0 && r.pair_failures == 0) ? fused_planned : 0;
         info->fused_ms = npairs > 0 ? ms_pairs : 0.0;
     }
     return r.nan_detected ? MSED_NAN_DETECTED : MSED_OK;
@@ -687,6 +725,13 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     msed_handle *h = new (std::nothrow) msed_handle();
     if (!h) return fail(nullptr, MSED_ERR_ALLOC, "host allocation failed");
     h->cfg = *cfg;
+    // auto fusion mode: tiles up to this many columns take the warp-per-column chain kernel when knum <= 32
+    h->chain_max_cols = 1LL << 40;
+    if (const char *e = std::getenv("MSED_CHAIN_MAX_COLS")) h->chain_max_cols = std::atoll(e);
+    if (const char *e = std::getenv("MSED_STEP_FUSION")) {  // initial msed_set_step_fusion mode (0..3)
+        const int mode = std::atoi(e);
+        if (mode >= 0 && mode <= 3) h->step_fusion = mode;
+    }
     int dev = cfg->device;
     if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
     h->device = dev;
@@ -1128,6 +1173,7 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
             info->kernel_ms += b.kernel_ms;
             info->kernel_launches += b.kernel_launches;
             info->fused_pairs += b.fused_pairs;
+            info->fused_steps += b.fused_steps;
             info->fused_ms += b.fused_ms;
         }
     }
@@ -1137,7 +1183,8 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
 int msed_set_step_fusion(msed_handle *h, int enable)
 {
     if (!h) return MSED_ERR_ARG;
-    h->step_fusion = enable ? 1 : 0;
+    if (enable < 0 || enable > 3) return fail(h, MSED_ERR_ARG, "step fusion mode must be 0..3");
+    h->step_fusion = enable;
     h->pair_cooldown = 0;
     return MSED_OK;
 }
@@ -1246,6 +1293,7 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
             info->kernel_ms += b.kernel_ms;
             info->kernel_launches += b.kernel_launches;
             info->fused_pairs += b.fused_pairs;
+            info->fused_steps += b.fused_steps;
             info->fused_ms += b.fused_ms;
         }
     }
@@ -1347,6 +1395,7 @@ int msed_coupled_run(msed_handle *h, double dt, int method, double coupling_seco
         acc.kernel_ms += one.kernel_ms;
         acc.kernel_launches += one.kernel_launches + 2;
         acc.fused_pairs += one.fused_pairs;
+        acc.fused_steps += one.fused_steps;
         acc.fused_ms += one.fused_ms;
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));

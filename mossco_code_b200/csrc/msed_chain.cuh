@@ -1,0 +1,209 @@
+// msed_chain.cuh -- included inside namespace msed after msed_pair.cuh.
+//
+// A chain of consecutive Euler / adaptive-Euler steps with the column state held in REGISTERS: one
+// warp owns one sediment column, lane k owns layer k (knum <= 32).  The vertical stencil of diff3d is
+// one layer wide, so a step needs the state of the layer below (one __shfl_down per variable) and the
+// flux through the upper interface, which the lane above has just computed (one __shfl_up per
+// variable).  The state is read from HBM once, advanced nsub steps, and written once: per step the
+// chain moves 128/nsub bytes per cell instead of the 128 of the single-step kernel.
+//
+// Why a second fused kernel next to pair_kernel (thread per column, two steps per launch):
+//  - small tiles (BASELINE config 2: 100x100 columns) give the thread-per-column kernels 79 CTAs, less
+//    than one warp per SM scheduler, and every thread walks 30 layers x 282 dependent-ish instructions
+//    per step; with a warp per column the same tile is 10,000 warps, enough to fill the machine, and a
+//    whole coupling interval (10 steps) is one launch;
+//  - land columns cost nothing (a masked warp exits; thread-per-column warps idle their land lanes);
+//  - per-layer coefficients (porosity, interface diffusivities, 1/(porosity*dz)) are step-invariant
+//    and stay in registers for the whole chain.
+//
+// Semantics are those of nsub ode_solver calls (solver_library.F90:104-140), each followed by the
+// component's check_NaN / minimum clip (fabm_sediment_component.F90:1718-1732): a step's output is
+// clipped before the next step reads it, every step raises the violation / NaN flags, and
+// chain_controller_kernel commits the chain only if no step would have been rejected or stopped.
+// Otherwise nothing is committed (the input buffer is untouched) and the host redoes the same steps
+// with the single-step kernel -- speculation with a free rollback, exactly as for pairs.  The
+// arithmetic is the shared inline code of msed_column.cuh, so a committed chain is bit-identical to
+// nsub single steps.
+//
+// Same scope as pair_kernel: bcup_particulate = 1, bioturbation_profile != 3, closed-form porosity.
+
+constexpr int CHAIN_WARPS = 8;                  // columns per CTA: 8 adjacent columns = 64 contiguous bytes per row
+constexpr int CHAIN_BLOCK = CHAIN_WARPS * 32;
+constexpr int CHAIN_MAX_LAYERS = 32;
+#ifndef MSED_CHAIN_MIN_BLOCKS
+#define MSED_CHAIN_MIN_BLOCKS 2
+#endif
+#ifndef MSED_CHAIN_MAX_STEPS
+#define MSED_CHAIN_MAX_STEPS 16                 // steps per launch: bounds the work a failed speculation throws away
+#endif
+
+// CLIP: the component wrapper (check_NaN + minimum clip after every step) is on -- a host-side fact
+// (msed_step / msed_run set it, msed_ode_solver does not), mirrored in Ctl::do_clip
+template <int MODEL, bool ADAPTIVE, bool CLIP>
+__global__ void __launch_bounds__(CHAIN_BLOCK, MSED_CHAIN_MIN_BLOCKS)
+chain_kernel(const __grid_constant__ KParams p, const int nsub)
+{
+    const Ctl *ctl = p.ctl;
+    if (ctl->stop || ctl->pairs_disabled || ctl->steps_done + nsub > ctl->steps_target || ctl->dt_int != 0.0)
+        return;
+    const int cur = ctl->cur;
+    const double dt = ctl->dt;
+    // a violation can only be rejected while dt_red > dt_min (solver_library.F90:126); a chain whose
+    // violation flag is already up cannot be committed, so warps that start later skip their work
+    const bool rejectable = ADAPTIVE && dt > ctl->dt_min;
+    const volatile int *rflags = ctl->flags;
+    if (rejectable && (rflags[0] | rflags[2])) return;
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int col = p.col0 + blockIdx.x * CHAIN_WARPS + (threadIdx.x >> 5);
+    if (col >= p.col_end) return;  // warp-uniform from here on: the shuffles below see all 32 lanes
+    if (p.mask[col] != 0) return;  // conc stays missing_value in both buffers
+
+    const int K = p.K;
+    const bool active = lane < K;
+    const int k = active ? lane : K - 1;   // spare lanes shadow the deepest layer; they never store or flag
+    const bool has_next = lane + 1 < K;
+    const size_t ld = p.ld;
+    const size_t plane = (size_t)K * ld;
+
+    double cc[NV];
+    {
+        const double *in = p.buf[cur] + (size_t)k * ld + col;
+#pragma unroll
+        for (int n = 0; n < NV; ++n) cc[n] = in[(size_t)n * plane];
+    }
+
+    // ---- step-invariant coefficients of this lane's layer and of its lower interface ------------
+    const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
+    const double temp = ld_ro(p.bdys + col);
+    double cpart, cdiss, fT;
+    column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
+    double fT_diag = fT;  // what field_kernel reports for the reaction-free model
+    if (MODEL != MSED_MODEL_OMEXDIA_P && p.denit_out)
+        fT_diag = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
+
+    const double porc = __dmul_rn(por_surf, p.portab[k]);
+    double porn = 0.0, mDp = 0.0, mDd = 0.0;
+    if (has_next) {
+        porn = __dmul_rn(por_surf, p.portab[k + 1]);
+        interface_coeffs(cpart, cdiss, porc, porn, p.bf[k + 1], p.rdzc[k], mDp, mDd);
+    }
+    const double rpd = fast_rcp(MSED_MUL(porc, p.dz[k]));
+    // upper boundary (used by lane 0 only): diff3d :782-803
+    const int bc_diss = p.bcup_diss;
+    const double por0 = __dmul_rn(por_surf, p.portab[0]);
+    double Dp0, Dd0;
+    top_coeffs(cpart, cdiss, por0, p.bf[0], Dp0, Dd0);
+    const double rdz0 = 1.0 / p.dz[0];
+
+    bool viol = false, nanf = false;
+    double dn_last = 0.0;
+
+    for (int s = 0; s < nsub; ++s) {
+        const bool last = (s == nsub - 1);
+
+        // flux through the lower interface (diff3d :776-778; BcDown = 3 below the deepest layer)
+        double Fn[NV];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const double cn = __shfl_down_sync(FULL, cc[n], 1);
+            const double f = (n < NPART) ? flux_particulate(mDp, cn, porn, cc[n], porc)
+                                         : flux_dissolved(mDd, cn, cc[n]);
+            Fn[n] = has_next ? f : 0.0;
+        }
+        // flux through the upper interface = the lower-interface flux of the layer above
+        double F[NV];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) F[n] = __shfl_up_sync(FULL, Fn[n], 1);
+        if (lane == 0) {  // upper boundary, diff3d :782-803
+            // particulates: BcUp = 1 (the host only fuses configurations without the distributed POM
+            // flux cascade), Flux(1) = the imposed sinking flux (:783)
+#pragma unroll
+            for (int n = 0; n < NPART; ++n) F[n] = ld_ro(p.fluxes + (size_t)n * ld + col);
+            if (bc_diss == 2) {                                     // Dirichlet, :786
+#pragma unroll
+                for (int n = NPART; n < NV; ++n)
+                    F[n] = top_flux_dirichlet(Dd0, cc[n], ld_ro(p.bdys + (size_t)(n + 1) * ld + col), rdz0);
+            } else if (bc_diss == 1 || bc_diss == 4) {              // imposed flux (rewritten unchanged below)
+#pragma unroll
+                for (int n = NPART; n < NV; ++n) F[n] = ld_ro(p.fluxes + (size_t)n * ld + col);
+            } else {
+                // BcUp = 3: explicit zero (:789).  Any other value: diff3d never assigns Flux(1), which
+                // keeps what the previous variable left in get_rhs's intFlux -- see column_kernel
+                const double f = (bc_diss == 3) ? 0.0 : F[NPART - 1];
+#pragma unroll
+                for (int n = NPART; n < NV; ++n) F[n] = f;
+            }
+            if (last) {
+#pragma unroll
+                for (int n = NPART; n < NV; ++n) p.fluxes[(size_t)n * ld + col] = F[n];  // :692
+            }
+        }
+
+        // local reaction rates (fabm_do, driver :700)
+        double r[NV], dn = 0.0;
+        if (MODEL == MSED_MODEL_OMEXDIA_P) {
+            omexdia_rates(p.om, cc, fT, r, &dn);
+        } else {
+            if (last && p.denit_out) omexdia_rates(p.om, cc, fT_diag, r, &dn);
+#pragma unroll
+            for (int n = 0; n < NV; ++n) r[n] = 0.0;
+        }
+        if (last) dn_last = dn;  // the FABM diagnostic describes the state of the last get_rhs call
+
+        double raw[NV];  // new state before the clip (check_NaN looks at it first, component :1718)
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const double rhs = layer_rhs(F[n], Fn[n], rpd, r[n]);
+            const double c0 = cc[n];
+            double newc = euler_update(dt, rhs, c0);
+            if (ADAPTIVE) viol |= violates(p.fac, c0, newc);
+            raw[n] = newc;
+            if (CLIP) {
+                if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
+                const double mn = p.om.minimum[n];
+                newc = (newc < mn) ? mn : newc;
+            }
+            cc[n] = newc;
+        }
+        // a rejectable violation anywhere in the column: the chain will not be committed, stop here
+        if (rejectable && __any_sync(FULL, viol && active)) {
+            if (lane == 0) atomicOr(&p.ctl->flags[0], 1);
+            return;
+        }
+    }
+
+    if (active) {
+        double *out = p.buf[1 - cur] + (size_t)k * ld + col;
+#pragma unroll
+        for (int n = 0; n < NV; ++n) out[(size_t)n * plane] = cc[n];
+        if (p.denit_out) p.denit_out[(size_t)k * ld + col] = dn_last;
+    }
+    const bool any_viol = __any_sync(FULL, viol && active);
+    const bool any_nan = __any_sync(FULL, nanf && active);
+    if (lane == 0) {
+        if (ADAPTIVE && any_viol) atomicOr(&p.ctl->flags[0], 1);
+        if (any_nan) atomicOr(&p.ctl->flags[1], 1);
+    }
+}
+
+// commits a chain of m steps (or disables fused launches so the host falls back to single steps from the
+// same state); the gate is the one chain_kernel evaluated
+__global__ void chain_controller_kernel(Ctl *c, int method, int m)
+{
+    c->step_completed = 0;
+    if (c->stop || c->pairs_disabled || c->steps_done + m > c->steps_target || c->dt_int != 0.0) return;
+    const int v = c->flags[0] | c->flags[2], nn = c->flags[1] | c->flags[3];
+    c->flags[0] = c->flags[1] = c->flags[2] = c->flags[3] = 0;
+    const bool rejectable = (method == MSED_ADAPTIVE_EULER) && (c->dt_red > c->dt_min);
+    if ((rejectable && v) || (c->do_clip && nn)) {
+        c->pairs_disabled = 1;  // a step would be rejected (:126) or stopped (component :1718):
+        c->pair_failures += 1;  // nothing is committed, single steps redo it exactly
+        return;
+    }
+    c->cur ^= 1;
+    c->steps_done += m;
+    c->rhs_evals += m;
+    c->step_completed = 1;
+}

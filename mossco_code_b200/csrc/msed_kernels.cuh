@@ -101,6 +101,8 @@ struct KParams {
 #include "msed_column.cuh"
 // two Euler / adaptive-Euler steps per pass over HBM (speculative, rollback-free)
 #include "msed_pair.cuh"
+// a chain of steps with the column in registers: warp per column, lane per layer (knum <= 32)
+#include "msed_chain.cuh"
 #include "msed_rkpair.cuh"
 
 // ---------------------------------------------------------------------------------------------

@@ -54,6 +54,7 @@ module msed_b200
     integer(c_int64_t) :: kernel_launches
     integer(c_int64_t) :: fused_pairs
     real(c_double)     :: fused_ms
+    integer(c_int64_t) :: fused_steps
   end type
 
   !> mirror `struct msed_soil_pelagic_params` / `msed_soil_pelagic_fluxes`: the soil_pelagic_connector

@@ -258,9 +258,15 @@ class SedimentDriver:
                          allow=(_abi.NAN_DETECTED,))
         return rc, out
 
-    def set_step_fusion(self, enable: bool):
-        """Speculative two-step kernels on/off (results are bit-identical either way)."""
-        self._check(self._lib.msed_set_step_fusion(self._h, int(bool(enable))))
+    FUSION_MODES = {"off": 0, "auto": 1, "pairs": 2, "chains": 3}
+
+    def set_step_fusion(self, mode):
+        """Speculative fused launches (results are bit-identical in every mode): False/"off", True/"auto"
+        (chains -- warp per column, up to 16 steps per launch -- where knum <= 32, else pairs), "pairs"
+        (thread per column, two steps per launch) or "chains"."""
+        if isinstance(mode, str):
+            mode = self.FUSION_MODES[mode]
+        self._check(self._lib.msed_set_step_fusion(self._h, int(mode)))
 
     def set_exchange_chunks(self, nchunks: int):
         self._check(self._lib.msed_set_exchange_chunks(self._h, int(nchunks)))

@@ -1,6 +1,7 @@
-"""Step fusion (msed_pair.cuh): speculative two-step kernels must be invisible in the results --
-bit-identical state, bed fluxes, sub-cycle counts and NaN behaviour with fusion on or off -- and must
-actually be used (fewer launches) in the regime they are meant for."""
+"""Step fusion: the speculative fused launches -- pairs (msed_pair.cuh: thread per column, two steps) and
+chains (msed_chain.cuh: warp per column, state in registers, up to 16 steps) -- must be invisible in the
+results: bit-identical state, bed fluxes, diagnostics, sub-cycle counts and NaN behaviour with fusion on
+or off, and must actually be used (fewer launches) in the regime they are meant for."""
 import numpy as np
 import pytest
 
@@ -43,11 +44,15 @@ def _same(a, b):
     assert np.array_equal(a["denit"], b["denit"], equal_nan=True)
 
 
+MODES = ["pairs", "chains"]
+
+
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("method", [2, 0])
 @pytest.mark.parametrize("nsteps", [2, 3, 4, 10, 11])
-def test_fusion_is_bit_identical(gpu, oracle, method, nsteps):
+def test_fusion_is_bit_identical(gpu, oracle, method, nsteps, mode):
     case = make_case("fuse", 37, 21, 20, 0.003, seed=101, land_fraction=0.2, smooth_temperature=True)
-    on = _run(case, True, method, nsteps, calls=2)
+    on = _run(case, mode, method, nsteps, calls=2)
     off = _run(case, False, method, nsteps, calls=2)
     _same(on, off)
     assert on["launches"] < off["launches"]                 # pairs were really used
@@ -61,7 +66,8 @@ def test_fusion_is_bit_identical(gpu, oracle, method, nsteps):
 @pytest.mark.parametrize("kw", [dict(bcup_dissolved_variables=1), dict(bioturbation_profile=2),
                                 dict(bcup_dissolved_variables=3, bioturbation_profile=0),
                                 dict(minimum=[1., 2., 3., 0.5, 30., 1., 2., 150.]), dict(model=1)])
-def test_fusion_variants(gpu, kw):
+@pytest.mark.parametrize("mode", MODES)
+def test_fusion_variants(gpu, kw, mode):
     case = make_case("fusev", 19, 9, 15, 0.004, seed=7)
 
     def mutate(sed):
@@ -70,21 +76,58 @@ def test_fusion_variants(gpu, kw):
             sed.set_boundary(None, fl)
         sed.update_porosity(0.5 + 0.3 * np.random.default_rng(2).random((19, 9)))   # porosity mode 2
 
-    _same(_run(case, True, 2, 9, mutate=mutate, **kw), _run(case, False, 2, 9, mutate=mutate, **kw))
+    _same(_run(case, mode, 2, 9, mutate=mutate, **kw), _run(case, False, 2, 9, mutate=mutate, **kw))
 
 
-def test_fusion_falls_back_when_a_step_is_rejected(gpu):
+@pytest.mark.parametrize("method", [2, 0])
+@pytest.mark.parametrize("knum,dzmin,nsteps", [(1, 0.1, 5), (2, 0.05, 7), (31, 0.002, 16), (32, 0.002, 17), (30, 0.002, 33)])
+def test_chain_layer_counts_and_lengths(gpu, knum, dzmin, nsteps, method):
+    """Chains at the edges of their range: a single layer (no interface at all), a full warp (knum = 32),
+    idle lanes (knum < 32), and step counts that split into one, two and three launches."""
+    case = make_case("chk", 21, 13, knum, dzmin, seed=40 + knum, land_fraction=0.15)
+    on = _run(case, "chains", method, nsteps, calls=2)
+    off = _run(case, False, method, nsteps, calls=2)
+    _same(on, off)
+    assert on["launches"] < off["launches"]
+
+
+def test_chain_is_the_default_up_to_32_layers(gpu):
+    """auto mode: chains where knum <= 32, pairs above (fewer launches than pairs for the same call)."""
+    small = make_case("chd", 16, 8, 30, 0.002, seed=3)
+    deep = make_case("chd", 16, 8, 40, 0.0015, seed=3)
+    assert _run(small, "auto", 2, 10)["launches"] == _run(small, "chains", 2, 10)["launches"] \
+        < _run(small, "pairs", 2, 10)["launches"]
+    assert _run(deep, "auto", 2, 10)["launches"] == _run(deep, "pairs", 2, 10)["launches"] \
+        == _run(deep, "chains", 2, 10)["launches"]
+    _same(_run(deep, "auto", 2, 10), _run(deep, False, 2, 10))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_fusion_falls_back_when_a_step_is_rejected(gpu, mode):
     """rnit/rODUox boosted: the first steps sub-cycle.  A pair containing a rejected step is not committed;
     the single-step path redoes it, and fusion stays off for a while afterwards."""
     case = make_case("fuser", 12, 8, 15, 0.004, seed=2)
     kw = dict(rnit=2.0e3, rODUox=2.0e3)
-    on = _run(case, True, 2, 7, calls=3, **kw)
+    on = _run(case, mode, 2, 7, calls=3, **kw)
     off = _run(case, False, 2, 7, calls=3, **kw)
     assert off["sub"] > 0
     _same(on, off)
 
 
-def test_fusion_nan_stops_at_the_same_step(gpu):
+@pytest.mark.parametrize("mode", MODES)
+def test_fusion_accepts_violations_below_dt_min(gpu, mode):
+    """dt <= dt_min: a violating step is accepted (solver_library.F90:126), so fused launches commit too."""
+    case = make_case("fusem", 12, 8, 15, 0.004, seed=2)
+    kw = dict(rnit=2.0e3, rODUox=2.0e3, dt_min=400.0)
+    on = _run(case, mode, 2, 6, **kw)
+    off = _run(case, False, 2, 6, **kw)
+    assert off["sub"] == 0
+    _same(on, off)
+    assert on["launches"] < off["launches"]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_fusion_nan_stops_at_the_same_step(gpu, mode):
     case = make_case("fusen", 6, 5, 12, 0.004, seed=4)
 
     def poison(sed):
@@ -92,7 +135,7 @@ def test_fusion_nan_stops_at_the_same_step(gpu):
         c[3, 2, 5, 6] = np.nan
         sed.conc = c
 
-    on = _run(case, True, 2, 9, mutate=poison)
+    on = _run(case, mode, 2, 9, mutate=poison)
     off = _run(case, False, 2, 9, mutate=poison)
     assert on["rc"] == off["rc"] == 1 and on["done"] == off["done"] == 1
 

@@ -86,12 +86,14 @@ def test_get_rhs_distributed_pom_flux(gpu, oracle):
         sed.finalize()
 
 
+@pytest.mark.parametrize("fusion", ["auto", "off"])   # auto: a one-step chain (msed_chain.cuh); off: column_kernel
 @pytest.mark.parametrize("method", [0, 1, 2, 3])
 @pytest.mark.parametrize("which", ["C1", "C1b", "C2s", "C3s"])
-def test_one_step_parity(gpu, oracle, which, method):
+def test_one_step_parity(gpu, oracle, which, method, fusion):
     case = {"C1": lambda: config_case("C1"), "C1b": lambda: config_case("C1b"),
             "C2s": lambda: config_case("C2", 0.2), "C3s": lambda: config_case("C3", 0.03)}[which]()
     cfg, sed, ref = _pair(oracle, case)
+    sed.set_step_fusion(fusion)
     rc = sed.step(DT, method, 1)
     assert rc == 0
     assert ref.step(DT, method, 1) == 0

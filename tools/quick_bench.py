@@ -20,15 +20,18 @@ ap.add_argument("--method", type=int, default=2)
 ap.add_argument("--spin", type=int, default=10)
 ap.add_argument("--perturb", type=float, default=0.1)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--fusion", choices=["on", "off"], default="on")
+ap.add_argument("--fusion", choices=["on", "off", "pairs", "chains"], default="on")
+ap.add_argument("--land", type=float, default=0.0)
 a = ap.parse_args()
 dzmin = 0.0015 if a.knum == 40 else 0.002
 t0 = time.time()
-case = make_case("qb", a.inum, a.jnum, a.knum, dzmin, seed=4096, perturb=a.perturb)
+case = make_case("qb", a.inum, a.jnum, a.knum, dzmin, seed=4096, perturb=a.perturb, land_fraction=a.land)
 cfg = default_config(inum=a.inum, jnum=a.jnum, knum=a.knum, dzmin=dzmin, dt_min=1.0)
 sed = SedimentDriver(cfg)
+if a.land > 0:
+    sed.set_mask(case.mask)
 sed.init_concentrations()
-sed.set_step_fusion(a.fusion == "on")
+sed.set_step_fusion({"on": "auto"}.get(a.fusion, a.fusion))
 sed.set_boundary(case.bdys, case.fluxes)
 print(f"setup {time.time()-t0:.1f}s")
 sed.step(360.0, a.method, a.spin)
@@ -36,7 +39,7 @@ print("spin: subcycles", sed.info.subcycle_warnings, "rhs evals", sed.info.rhs_e
 for rep in range(a.reps):
     sed.step(360.0, a.method, a.steps)
     i = sed.info
-    cells = a.inum * a.jnum * a.knum
+    cells = a.inum * a.jnum * a.knum * (float((case.mask == 0).mean()) if a.land > 0 else 1.0)
     ms = i.kernel_ms / a.steps
     balg = 136.0 + 216.0 / a.knum
     print(f"rep{rep}: {ms:.3f} ms/step  {cells/ms/1e6:.2f} Gcell-updates/s  alg {cells*balg/ms/1e6:.0f} GB/s "
