@@ -90,6 +90,16 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
         interface_coeffs(cpart, cdiss, porc, porn, p.bf[k + 1], p.rdzc[k], mDp, mDd);
     }
     const double rpd = fast_rcp(MSED_MUL(porc, p.dz[k]));
+#ifndef MSED_CHAIN_SHFL_FLUX
+    // ... and of its upper interface: the flux through it is the lower-interface flux of the layer above;
+    // this lane recomputes it from the same operands with the same operations (so the bits are the same)
+    // rather than waiting for the lane above to compute and pass it down -- see the step loop
+    double poru = porc, uDp = 0.0, uDd = 0.0;
+    if (lane > 0 && active) {
+        poru = __dmul_rn(por_surf, p.portab[k - 1]);
+        interface_coeffs(cpart, cdiss, poru, porc, p.bf[k], p.rdzc[k - 1], uDp, uDd);
+    }
+#endif
     // upper boundary (used by lane 0 only): diff3d :782-803
     const int bc_diss = p.bcup_diss;
     const double por0 = __dmul_rn(por_surf, p.portab[0]);
@@ -100,48 +110,36 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     bool viol = false, nanf = false;
     double dn_last = 0.0;
 
+    // where lane 0 finds the upper-boundary input of a dissolved variable: the concentration above the
+    // bed for BcUp = 2 (bdys row n+1), the imposed flux for BcUp = 1 (fluxes row n); any other BcUp
+    // reads nothing, the address only has to be valid
+    const double *top_part = p.fluxes + col;
+    const double *top_diss = (bc_diss == 2) ? p.bdys + ld + col : p.fluxes + col;
+
+#ifdef MSED_CHAIN_UNROLL
+    MSED_UNROLL_PRAGMA(MSED_CHAIN_UNROLL)
+#endif
     for (int s = 0; s < nsub; ++s) {
         const bool last = (s == nsub - 1);
 
-        // flux through the lower interface (diff3d :776-778; BcDown = 3 below the deepest layer)
-        double Fn[NV];
+        // upper-boundary inputs, issued first and by every lane (one address per warp: a broadcast) so that
+        // their latency hides behind the shuffles and the reaction term instead of stalling lane 0
+        double tin[NV];
 #pragma unroll
-        for (int n = 0; n < NV; ++n) {
-            const double cn = __shfl_down_sync(FULL, cc[n], 1);
-            const double f = (n < NPART) ? flux_particulate(mDp, cn, porn, cc[n], porc)
-                                         : flux_dissolved(mDd, cn, cc[n]);
-            Fn[n] = has_next ? f : 0.0;
-        }
-        // flux through the upper interface = the lower-interface flux of the layer above
-        double F[NV];
-#pragma unroll
-        for (int n = 0; n < NV; ++n) F[n] = __shfl_up_sync(FULL, Fn[n], 1);
-        if (lane == 0) {  // upper boundary, diff3d :782-803
-            // particulates: BcUp = 1 (the host only fuses configurations without the distributed POM
-            // flux cascade), Flux(1) = the imposed sinking flux (:783)
-#pragma unroll
-            for (int n = 0; n < NPART; ++n) F[n] = ld_ro(p.fluxes + (size_t)n * ld + col);
-            if (bc_diss == 2) {                                     // Dirichlet, :786
-#pragma unroll
-                for (int n = NPART; n < NV; ++n)
-                    F[n] = top_flux_dirichlet(Dd0, cc[n], ld_ro(p.bdys + (size_t)(n + 1) * ld + col), rdz0);
-            } else if (bc_diss == 1 || bc_diss == 4) {              // imposed flux (rewritten unchanged below)
-#pragma unroll
-                for (int n = NPART; n < NV; ++n) F[n] = ld_ro(p.fluxes + (size_t)n * ld + col);
-            } else {
-                // BcUp = 3: explicit zero (:789).  Any other value: diff3d never assigns Flux(1), which
-                // keeps what the previous variable left in get_rhs's intFlux -- see column_kernel
-                const double f = (bc_diss == 3) ? 0.0 : F[NPART - 1];
-#pragma unroll
-                for (int n = NPART; n < NV; ++n) F[n] = f;
-            }
-            if (last) {
-#pragma unroll
-                for (int n = NPART; n < NV; ++n) p.fluxes[(size_t)n * ld + col] = F[n];  // :692
-            }
-        }
+        for (int n = 0; n < NV; ++n) tin[n] = ld_ro((n < NPART ? top_part : top_diss) + (size_t)n * ld);
 
-        // local reaction rates (fabm_do, driver :700)
+        // both neighbours' states are requested up front: the shuffles complete while the reaction term,
+        // which needs neither, is evaluated
+        double cn[NV];  // state of the layer below
+#pragma unroll
+        for (int n = 0; n < NV; ++n) cn[n] = __shfl_down_sync(FULL, cc[n], 1);
+#ifndef MSED_CHAIN_SHFL_FLUX
+        double cu[NV];  // state of the layer above
+#pragma unroll
+        for (int n = 0; n < NV; ++n) cu[n] = __shfl_up_sync(FULL, cc[n], 1);
+#endif
+
+        // local reaction rates (fabm_do, driver :700): independent of the neighbours
         double r[NV], dn = 0.0;
         if (MODEL == MSED_MODEL_OMEXDIA_P) {
             omexdia_rates(p.om, cc, fT, r, &dn);
@@ -151,6 +149,52 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
             for (int n = 0; n < NV; ++n) r[n] = 0.0;
         }
         if (last) dn_last = dn;  // the FABM diagnostic describes the state of the last get_rhs call
+
+        // flux through the lower interface (diff3d :776-778; BcDown = 3 below the deepest layer)
+        double Fn[NV];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const double f = (n < NPART) ? flux_particulate(mDp, cn[n], porn, cc[n], porc)
+                                         : flux_dissolved(mDd, cn[n], cc[n]);
+            Fn[n] = has_next ? f : 0.0;
+        }
+        // flux through the upper interface = the lower-interface flux of the layer above
+        double F[NV];
+#ifdef MSED_CHAIN_SHFL_FLUX
+#pragma unroll
+        for (int n = 0; n < NV; ++n) F[n] = __shfl_up_sync(FULL, Fn[n], 1);
+#else
+#pragma unroll
+        for (int n = 0; n < NV; ++n)  // the layer above is "current", this lane's layer is its "next"
+            F[n] = (n < NPART) ? flux_particulate(uDp, cc[n], porc, cu[n], poru) : flux_dissolved(uDd, cc[n], cu[n]);
+#endif
+        // upper boundary, diff3d :782-803: only lane 0 keeps the result.  Every lane evaluates it (a warp
+        // pays for a one-lane branch body anyway; selects keep the instruction stream straight).
+        // Particulates: BcUp = 1 (the host only fuses configurations without the distributed POM flux
+        // cascade), Flux(1) = the imposed sinking flux (:783)
+        const bool top = (lane == 0);
+#pragma unroll
+        for (int n = 0; n < NPART; ++n) F[n] = top ? tin[n] : F[n];
+        if (bc_diss == 2) {                                     // Dirichlet, :786
+#pragma unroll
+            for (int n = NPART; n < NV; ++n) {
+                const double f = top_flux_dirichlet(Dd0, cc[n], tin[n], rdz0);
+                F[n] = top ? f : F[n];
+            }
+        } else if (bc_diss == 1 || bc_diss == 4) {              // imposed flux (rewritten unchanged below)
+#pragma unroll
+            for (int n = NPART; n < NV; ++n) F[n] = top ? tin[n] : F[n];
+        } else {
+            // BcUp = 3: explicit zero (:789).  Any other value: diff3d never assigns Flux(1), which
+            // keeps what the previous variable left in get_rhs's intFlux -- see column_kernel
+            const double f = (bc_diss == 3) ? 0.0 : tin[NPART - 1];
+#pragma unroll
+            for (int n = NPART; n < NV; ++n) F[n] = top ? f : F[n];
+        }
+        if (last && top) {
+#pragma unroll
+            for (int n = NPART; n < NV; ++n) p.fluxes[(size_t)n * ld + col] = F[n];  // :692
+        }
 
         double raw[NV];  // new state before the clip (check_NaN looks at it first, component :1718)
 #pragma unroll
