@@ -726,7 +726,9 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     if (!h) return fail(nullptr, MSED_ERR_ALLOC, "host allocation failed");
     h->cfg = *cfg;
     // auto fusion mode: tiles up to this many columns take the warp-per-column chain kernel when knum <= 32
-    h->chain_max_cols = 1LL << 40;
+    // measured on B200 (profiles/r01_chain_kernel.md): chains win below ~60k columns, where the thread-per-
+    // column pair kernel cannot fill the machine (one wave = 148 SMs x 3 CTAs x 128 columns), and lose 5-10 % above
+    h->chain_max_cols = 65536;
     if (const char *e = std::getenv("MSED_CHAIN_MAX_COLS")) h->chain_max_cols = std::atoll(e);
     if (const char *e = std::getenv("MSED_STEP_FUSION")) {  // initial msed_set_step_fusion mode (0..3)
         const int mode = std::atoi(e);

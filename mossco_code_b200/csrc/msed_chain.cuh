@@ -90,16 +90,6 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
         interface_coeffs(cpart, cdiss, porc, porn, p.bf[k + 1], p.rdzc[k], mDp, mDd);
     }
     const double rpd = fast_rcp(MSED_MUL(porc, p.dz[k]));
-#ifndef MSED_CHAIN_SHFL_FLUX
-    // ... and of its upper interface: the flux through it is the lower-interface flux of the layer above;
-    // this lane recomputes it from the same operands with the same operations (so the bits are the same)
-    // rather than waiting for the lane above to compute and pass it down -- see the step loop
-    double poru = porc, uDp = 0.0, uDd = 0.0;
-    if (lane > 0 && active) {
-        poru = __dmul_rn(por_surf, p.portab[k - 1]);
-        interface_coeffs(cpart, cdiss, poru, porc, p.bf[k], p.rdzc[k - 1], uDp, uDd);
-    }
-#endif
     // upper boundary (used by lane 0 only): diff3d :782-803
     const int bc_diss = p.bcup_diss;
     const double por0 = __dmul_rn(por_surf, p.portab[0]);
@@ -107,7 +97,8 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     top_coeffs(cpart, cdiss, por0, p.bf[0], Dp0, Dd0);
     const double rdz0 = 1.0 / p.dz[0];
 
-    bool viol = false, nanf = false;
+    int viol = 0;  // sign bit = some relative change fell below relative_change_min (violates_acc)
+    bool nanf = false;
     double dn_last = 0.0;
 
     // where lane 0 finds the upper-boundary input of a dissolved variable: the concentration above the
@@ -128,16 +119,11 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
 #pragma unroll
         for (int n = 0; n < NV; ++n) tin[n] = ld_ro((n < NPART ? top_part : top_diss) + (size_t)n * ld);
 
-        // both neighbours' states are requested up front: the shuffles complete while the reaction term,
-        // which needs neither, is evaluated
-        double cn[NV];  // state of the layer below
+        // the state of the layer below is requested first: the shuffles complete while the reaction term,
+        // which does not need it, is evaluated
+        double cn[NV];
 #pragma unroll
         for (int n = 0; n < NV; ++n) cn[n] = __shfl_down_sync(FULL, cc[n], 1);
-#ifndef MSED_CHAIN_SHFL_FLUX
-        double cu[NV];  // state of the layer above
-#pragma unroll
-        for (int n = 0; n < NV; ++n) cu[n] = __shfl_up_sync(FULL, cc[n], 1);
-#endif
 
         // local reaction rates (fabm_do, driver :700): independent of the neighbours
         double r[NV], dn = 0.0;
@@ -158,16 +144,12 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
                                          : flux_dissolved(mDd, cn[n], cc[n]);
             Fn[n] = has_next ? f : 0.0;
         }
-        // flux through the upper interface = the lower-interface flux of the layer above
+        // flux through the upper interface = the lower-interface flux of the layer above.  (Shuffling the
+        // state up instead and recomputing that flux here, to drop this second exchange from the critical
+        // path, was measured 7-8 % slower: 19 more fp64 instructions per step.)
         double F[NV];
-#ifdef MSED_CHAIN_SHFL_FLUX
 #pragma unroll
         for (int n = 0; n < NV; ++n) F[n] = __shfl_up_sync(FULL, Fn[n], 1);
-#else
-#pragma unroll
-        for (int n = 0; n < NV; ++n)  // the layer above is "current", this lane's layer is its "next"
-            F[n] = (n < NPART) ? flux_particulate(uDp, cc[n], porc, cu[n], poru) : flux_dissolved(uDd, cc[n], cu[n]);
-#endif
         // upper boundary, diff3d :782-803: only lane 0 keeps the result.  Every lane evaluates it (a warp
         // pays for a one-lane branch body anyway; selects keep the instruction stream straight).
         // Particulates: BcUp = 1 (the host only fuses configurations without the distributed POM flux
@@ -202,7 +184,7 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
             const double rhs = layer_rhs(F[n], Fn[n], rpd, r[n]);
             const double c0 = cc[n];
             double newc = euler_update(dt, rhs, c0);
-            if (ADAPTIVE) viol |= violates(p.fac, c0, newc);
+            if (ADAPTIVE) violates_acc(viol, p.fac, c0, newc);
             raw[n] = newc;
             if (CLIP) {
                 if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
@@ -212,7 +194,7 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
             cc[n] = newc;
         }
         // a rejectable violation anywhere in the column: the chain will not be committed, stop here
-        if (rejectable && __any_sync(FULL, viol && active)) {
+        if (rejectable && __any_sync(FULL, viol < 0 && active)) {
             if (lane == 0) atomicOr(&p.ctl->flags[0], 1);
             return;
         }
@@ -224,7 +206,7 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
         for (int n = 0; n < NV; ++n) out[(size_t)n * plane] = cc[n];
         if (p.denit_out) p.denit_out[(size_t)k * ld + col] = dn_last;
     }
-    const bool any_viol = __any_sync(FULL, viol && active);
+    const bool any_viol = __any_sync(FULL, viol < 0 && active);
     const bool any_nan = __any_sync(FULL, nanf && active);
     if (lane == 0) {
         if (ADAPTIVE && any_viol) atomicOr(&p.ctl->flags[0], 1);

@@ -181,6 +181,15 @@ __device__ __forceinline__ bool violates(double fac, double c0, double newc)  //
 {
     return fma(-fac, c0, newc) < 0.0;
 }
+// The same test for the speculative kernels (pairs, chains), accumulated on the integer pipe: a negative
+// value has its sign bit set, so the high words are OR-ed and the sign of the result is looked at once.
+// -0.0 and negative NaNs set the bit too; in a speculative launch a false alarm only turns a commit into
+// a redo by the single-step kernel, which applies violates() itself -- results cannot change, and the
+// fp64 pipe, which bounds those kernels, is spared a DSETP per variable and step.
+__device__ __forceinline__ void violates_acc(int &acc, double fac, double c0, double newc)
+{
+    acc |= __double2hiint(fma(-fac, c0, newc));
+}
 // per-column Arrhenius factors and diffusivity prefactors (driver :648,:652,:682; omexdia_p f_T)
 template <int MODEL, bool PROFILE3>
 __device__ __forceinline__ void column_constants(const KParams &p, double temp, double &cpart, double &cdiss,

@@ -121,7 +121,8 @@ pair_kernel(const __grid_constant__ KParams p)
     // rewritten unchanged by step 2 (:692).
     top_boundary([&](int n) { return lds64(sbase + n * ROW_BYTES); }, por_at(0), FA, false);
 
-    bool viol1 = false, nan1 = false, viol2 = false, nan2 = false;
+    int viol1 = 0, viol2 = 0;  // sign bit = some relative change fell below relative_change_min (violates_acc)
+    bool nan1 = false, nan2 = false;
     double *g_out = out;
     // The last pair of a call leaves the denitrification diagnostic of its second step behind: it
     // describes the state of the last get_rhs call, which here never reaches HBM.
@@ -147,7 +148,7 @@ pair_kernel(const __grid_constant__ KParams p)
     };
 
     auto step_layer = [&](auto has_next_tag, auto clip_tag, const LayerCoef &lc, const double (&cc)[NV], auto cn,
-                          double (&F)[NV], bool &viol, bool &nanf, auto sink, auto denit) {
+                          double (&F)[NV], int &viol, bool &nanf, auto sink, auto denit) {
         constexpr bool HAS_NEXT = decltype(has_next_tag)::value;
         constexpr bool CLIP = decltype(clip_tag)::value;
         double Fn[NV];
@@ -178,7 +179,7 @@ pair_kernel(const __grid_constant__ KParams p)
             F[n] = Fn[n];
             const double c0 = cc[n];
             double newc = euler_update(dt, rhs, c0);
-            if (ADAPTIVE) viol |= violates(p.fac, c0, newc);
+            if (ADAPTIVE) violates_acc(viol, p.fac, c0, newc);
             raw[n] = newc;
             if (CLIP) {
                 if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
@@ -251,9 +252,9 @@ pair_kernel(const __grid_constant__ KParams p)
     cp_async_wait<0>();
 
     int *wf = p.ctl->flags;
-    if (ADAPTIVE && viol1) atomicOr(&wf[0], 1);
+    if (ADAPTIVE && viol1 < 0) atomicOr(&wf[0], 1);
     if (nan1) atomicOr(&wf[1], 1);
-    if (ADAPTIVE && viol2) atomicOr(&wf[2], 1);
+    if (ADAPTIVE && viol2 < 0) atomicOr(&wf[2], 1);
     if (nan2) atomicOr(&wf[3], 1);
 }
 

@@ -80,10 +80,11 @@ def test_fusion_variants(gpu, kw, mode):
 
 
 @pytest.mark.parametrize("method", [2, 0])
-@pytest.mark.parametrize("knum,dzmin,nsteps", [(1, 0.1, 5), (2, 0.05, 7), (31, 0.002, 16), (32, 0.002, 17), (30, 0.002, 33)])
+@pytest.mark.parametrize("knum,dzmin,nsteps", [(2, 0.05, 7), (3, 0.03, 5), (31, 0.002, 16), (32, 0.002, 17), (30, 0.002, 33)])
 def test_chain_layer_counts_and_lengths(gpu, knum, dzmin, nsteps, method):
-    """Chains at the edges of their range: a single layer (no interface at all), a full warp (knum = 32),
-    idle lanes (knum < 32), and step counts that split into one, two and three launches."""
+    """Chains at the edges of their range: the thinnest columns the driver accepts (knum = 2: every layer
+    touches a boundary), a full warp (knum = 32), idle lanes (knum < 32), and step counts that split into
+    one, two and three launches."""
     case = make_case("chk", 21, 13, knum, dzmin, seed=40 + knum, land_fraction=0.15)
     on = _run(case, "chains", method, nsteps, calls=2)
     off = _run(case, False, method, nsteps, calls=2)
