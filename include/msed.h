@@ -197,7 +197,8 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
  * 2 pairs only, 3 chains wherever knum allows.  Environment MSED_CHAIN_MAX_COLS limits the tile size
  * (columns) up to which mode 1 picks chains. */
 int msed_set_step_fusion(msed_handle *h, int mode);
-/* number of column chunks msed_run_exchange uses (0 = choose from the tile size, 1 = no overlap) */
+/* number of column chunks msed_run_exchange uses (0 = choose from the tile size: 1 to 8, always the
+ * asynchronous sequence; 1 = the plain sequence of the three separate calls, no overlap) */
 int msed_set_exchange_chunks(msed_handle *h, int nchunks);
 /* 1-D pre-simulation (component :557-632) for the handle's configuration; conc1d(1,1,knum,nvar) out.
  * bdys1d(nvar+1), fluxes1d(nvar). Runs a 1x1 tile on the same device. */

@@ -1209,8 +1209,12 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
     double rem = run_seconds - (double)nfull * dt;
     if (rem < 1e-9 * dt) rem = 0.0;
     int nchunks = h->exchange_chunks;
-    if (nchunks == 0) nchunks = h->ncol >= (1 << 20) ? 8 : (h->ncol >= (1 << 17) ? 4 : 1);
-    const bool pipelined = nchunks > 1 && (method == MSED_EULER || method == MSED_ADAPTIVE_EULER) &&
+    // chosen from the tile size: small tiles are one chunk -- nothing to overlap, but the asynchronous
+    // sequence below still saves the host synchronisations of the three separate calls, which dominate a
+    // Run of a few tens of microseconds; msed_set_exchange_chunks(1) asks for the plain sequence
+    const bool auto_chunks = nchunks == 0;
+    if (auto_chunks) nchunks = h->ncol >= (1 << 20) ? 8 : (h->ncol >= (1 << 17) ? 4 : 1);
+    const bool pipelined = (nchunks > 1 || auto_chunks) && (method == MSED_EULER || method == MSED_ADAPTIVE_EULER) &&
                            !h->cfg.adaptive_solver_diagnostics && (nfull + (rem > 0.0 ? 1 : 0)) > 0 &&
                            (size_t)NV * h->K >= 12 + NV;
     int rc;

@@ -125,7 +125,7 @@ def test_soil_pelagic_connector(gpu, oracle, want):
                 assert not got[k].any()
 
 
-@pytest.mark.parametrize("nchunks,seconds", [(4, 3600.0), (3, 1000.0), (5, 360.0), (1, 3600.0), (4, 720.0)])
+@pytest.mark.parametrize("nchunks,seconds", [(4, 3600.0), (3, 1000.0), (5, 360.0), (1, 3600.0), (4, 720.0), (0, 3600.0), (0, 1000.0), (0, 360.0)])
 def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds):
     """msed_run_exchange (chunk-pipelined PCIe/compute overlap) must be bit-identical to
     get_boundary_conditions + run + upward_fluxes, incl. the shortened last step and a single step."""
