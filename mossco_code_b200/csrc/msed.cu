@@ -71,6 +71,8 @@ struct msed_handle {
     double *pel = nullptr;      // pelagic boxes: conc [nvar][ld], wz [nvar][ld], height [ld], temperature [ld]
     double *tables = nullptr;   // device copies of zc[K], cumdepth[K], porosity profile[K]
     unsigned char *mask = nullptr;
+    int *colmap = nullptr;          // device list of the wet columns (null while the tile has no land)
+    std::vector<int> wet_idx;       // host copy: converts column ranges of chunked launches
     Ctl *ctl = nullptr;         // device
     Ctl *ctl_host = nullptr;    // pinned mirror
     double *minloc_val = nullptr;
@@ -149,6 +151,7 @@ void fill_params(const msed_handle *h, KParams &p)
     p.bdys = h->bdys;
     p.fluxes = h->fluxes;
     p.mask = h->mask;
+    p.colmap = nullptr;
     p.ctl = h->ctl;
     p.ld = h->ld;
     p.ncol = h->ncol;
@@ -278,12 +281,25 @@ int ensure_denit(msed_handle *h)
     return MSED_OK;
 }
 
-cudaError_t launch_pair(const msed_handle *h, int method, const KParams &p)
+cudaError_t launch_pair(const msed_handle *h, int method, const KParams &pin)
 {
+    KParams p = pin;
+    if (h->colmap) {  // masked tile: run over the wet columns of [col0, col_end) only
+        const auto lo = std::lower_bound(h->wet_idx.begin(), h->wet_idx.end(), pin.col0);
+        const auto hi = std::lower_bound(h->wet_idx.begin(), h->wet_idx.end(), pin.col_end);
+        p.col0 = (int)(lo - h->wet_idx.begin());
+        p.col_end = (int)(hi - h->wet_idx.begin());
+        p.colmap = h->colmap;
+        if (p.col_end <= p.col0) return cudaSuccess;  // all land: nothing to launch
+    }
     const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
     const bool adaptive = method == MSED_ADAPTIVE_EULER;
     const bool denit = p.denit_out != nullptr;  // the last pair of a call also stores the denit diagnostic
-#define MSED_PAIR(MODEL, AD, DN) pair_kernel<MODEL, AD, DN><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p)
+#define MSED_PAIR(MODEL, AD, DN)                                                                       \
+    do {                                                                                               \
+        if (p.colmap) pair_kernel<MODEL, AD, DN, true><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);   \
+        else pair_kernel<MODEL, AD, DN, false><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);           \
+    } while (0)
 #define MSED_PAIR_MODEL(MODEL)                                   \
     do {                                                         \
         if (adaptive) { if (denit) MSED_PAIR(MODEL, true, true); else MSED_PAIR(MODEL, true, false); }   \
@@ -349,7 +365,9 @@ cudaError_t enable_pair_smem()
     MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_34)
 #undef MSED_RKP_ATTR
 #define MSED_PAIR_ATTR(MODEL, AD, DN) \
-    if ((e = cudaFuncSetAttribute(pair_kernel<MODEL, AD, DN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    if ((e = cudaFuncSetAttribute(pair_kernel<MODEL, AD, DN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  bytes)) != cudaSuccess) return e;                                            \
+    if ((e = cudaFuncSetAttribute(pair_kernel<MODEL, AD, DN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                   bytes)) != cudaSuccess) return e;
     MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, true, true) MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, true, false)
     MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, false, true) MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, false, false)
@@ -827,7 +845,7 @@ int msed_destroy(msed_handle *h)
     if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->buf[0]); cudaFree(h->buf[1]); cudaFree(h->aux[0]); cudaFree(h->aux[1]);
     cudaFree(h->por); cudaFree(h->bdys); cudaFree(h->fluxes); cudaFree(h->par_surface);
-    cudaFree(h->scratch); cudaFree(h->denit); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->ctl);
+    cudaFree(h->scratch); cudaFree(h->denit); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->colmap); cudaFree(h->ctl);
     cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->pel);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -860,7 +878,16 @@ int msed_set_mask(msed_handle *h, const int32_t *mask2d)
     apply_mask_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->por, h->buf[0], h->buf[1], h->mask, h->ld,
                                                                h->ncol, h->K);
     CUDA_TRY(h, cudaGetLastError());
+    // list of the wet columns for pair_kernel (see there); a tile without land keeps the identity
+    h->wet_idx.clear();
+    for (int c = 0; c < h->ncol; ++c)
+        if (!m[c]) h->wet_idx.push_back(c);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->colmap) { cudaFree(h->colmap); h->colmap = nullptr; }
+    if ((int)h->wet_idx.size() < h->ncol && !h->wet_idx.empty() && !std::getenv("MSED_NO_COLMAP")) {
+        CUDA_TRY(h, cudaMalloc(&h->colmap, h->wet_idx.size() * sizeof(int)));
+        CUDA_TRY(h, cudaMemcpy(h->colmap, h->wet_idx.data(), h->wet_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     return MSED_OK;
 }
 

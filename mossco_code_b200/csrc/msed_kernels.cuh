@@ -95,6 +95,8 @@ struct KParams {
     OmexDev om;
     double dz[MAXK], rdzc[MAXK], bf[MAXK], e1[MAXK], e2[MAXK], portab[MAXK];
     double *denit_out;       // [K][ld]: FABM denit diagnostic of the second step of a call's last pair, or null
+    const int *colmap;       // pair_kernel on a masked tile: indices of the wet columns, ascending; col0/col_end
+                             // then count wet columns (null: identity)
 };
 
 // loaders, reaction term and the fused column kernel

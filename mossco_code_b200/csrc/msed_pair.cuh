@@ -35,7 +35,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-template <int MODEL, bool ADAPTIVE, bool DENIT>
+template <int MODEL, bool ADAPTIVE, bool DENIT, bool COLMAP = false>
 __global__ void __launch_bounds__(COL_BLOCK, PAIR_MIN_BLOCKS)
 pair_kernel(const __grid_constant__ KParams p)
 {
@@ -50,8 +50,14 @@ pair_kernel(const __grid_constant__ KParams p)
     const volatile int *flags = ctl->flags;
     if (ADAPTIVE && dt > ctl->dt_min && (flags[0] | flags[2])) return;
 
-    const int col = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
-    if (col >= p.col_end) return;
+    // On a tile with land the launch runs over the list of wet columns, so that every lane of a warp has
+    // a column to integrate (a land lane idles for the whole walk down its neighbours' columns, and a CTA
+    // with one wet warp holds a full CTA's registers and shared memory).  Wet neighbours stay neighbours:
+    // accesses remain coalesced except where a run of land is skipped.
+    const int t = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
+    if (t >= p.col_end) return;
+    const int col = COLMAP ? p.colmap[t] : t;   // COLMAP: the tile has land (a separate instantiation, so the
+                                                // land-free kernel keeps its register allocation)
     if (p.mask[col] != 0) return;  // conc stays missing_value in both buffers
 
     const int K = p.K;

@@ -126,7 +126,8 @@ def test_soil_pelagic_connector(gpu, oracle, want):
 
 
 @pytest.mark.parametrize("nchunks,seconds", [(4, 3600.0), (3, 1000.0), (5, 360.0), (1, 3600.0), (4, 720.0), (0, 3600.0), (0, 1000.0), (0, 360.0)])
-def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds):
+@pytest.mark.parametrize("mode", ["auto", "pairs"])   # auto: chains on this tile; pairs: the wet-column list, chunked
+def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds, mode):
     """msed_run_exchange (chunk-pipelined PCIe/compute overlap) must be bit-identical to
     get_boundary_conditions + run + upward_fluxes, incl. the shortened last step and a single step."""
     from mossco_code_b200 import SedimentDriver, default_config
@@ -145,6 +146,7 @@ def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds):
             sed.set_mask(case.mask)
             sed.init_concentrations()
             sed.set_boundary(case.bdys, case.fluxes)
+            sed.set_step_fusion(mode if fused else "off")
             for _ in range(2):
                 if fused:
                     sed.set_exchange_chunks(nchunks)
