@@ -323,9 +323,10 @@ def main():
     # idle clocks and needs tens of milliseconds under load to reach the clocks a production run sees (a C3
     # step measured 0.30 ms warm and 1.1 ms straight after start-up).  Same count on every rank (the adaptive
     # step holds a collective); the state is re-initialised before the timed region either way.
-    tw0 = time.perf_counter()
     sed.step(DT, METHOD, args.warmup)
-    per_step = torch.tensor([(time.perf_counter() - tw0) / max(args.warmup, 1)], dtype=torch.float64, device="cuda")
+    tw0 = time.perf_counter()            # two more untimed steps, past the first call's lazy initialisation
+    sed.step(DT, METHOD, 2)
+    per_step = torch.tensor([(time.perf_counter() - tw0) / 2.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(per_step, op=dist.ReduceOp.MAX)
     ramp_steps = 0

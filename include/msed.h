@@ -194,8 +194,8 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
  * committed only if none of its steps would be rejected (solver_library.F90:126) or stopped by
  * check_NaN, otherwise the same steps are redone singly from the untouched state.  Results are
  * bit-identical in every mode.  mode: 0 off, 1 auto (default: chains where they apply, else pairs),
- * 2 pairs only, 3 chains wherever knum allows.  Environment MSED_CHAIN_MAX_COLS limits the tile size
- * (columns) up to which mode 1 picks chains. */
+ * 2 pairs only, 3 chains wherever knum allows.  Mode 1 picks chains for tiles of up to 65536 wet columns
+ * (environment MSED_CHAIN_MAX_COLS), where a thread per column cannot fill the GPU. */
 int msed_set_step_fusion(msed_handle *h, int mode);
 /* number of column chunks msed_run_exchange uses (0 = choose from the tile size: 1 to 8, always the
  * asynchronous sequence; 1 = the plain sequence of the three separate calls, no overlap) */

@@ -479,8 +479,10 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                                 // the last get_rhs call" diagnostic behind (KParams::denit_out)
     h->denit_valid = false;
     // chains (msed_chain.cuh) cover every step of the call, whatever its parity
+    // both fused kernels only work on wet columns, so the tile size that decides between them counts those
+    const long long work_cols = h->colmap ? (long long)h->wet_idx.size() : (long long)h->ncol;
     const bool chain_fit = h->K <= CHAIN_MAX_LAYERS &&
-                           (h->step_fusion == 3 || (h->step_fusion == 1 && h->ncol <= h->chain_max_cols));
+                           (h->step_fusion == 3 || (h->step_fusion == 1 && work_cols <= h->chain_max_cols));
     const bool use_chain = fusable && chain_fit && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 1;
     int chain_base = 0, chain_extra = 0;
     if (use_chain) {
