@@ -262,7 +262,7 @@ int msed_benthic_pelagic_coupler(msed_handle *h, const msed_benthic_pelagic_para
  * convertN (:467-472), DIP = convertP*(PO4+dipflux_const/year) (:529-533).  Oxygen and reduced
  * substances: both wanted -> plain copies (:660-679); only odu -> odu-oxygen (:696-698); only oxygen
  * -> oxygen-odu (:718-720).  detC = sum of the detritus*carbon fluxes (:842-874); detN and detP are
- * sums over import fields named detritus*nitrogen / detritus*phosphorous (:786,:933), of which
+ * sums over import fields named detritus*nitrogen / detritus*phosphorous (:764,:911), of which
  * omexdia_p has none: both are 0. */
 typedef struct msed_soil_pelagic_params {
     double dinflux_const;   /* :36, per year */

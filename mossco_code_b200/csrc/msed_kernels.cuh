@@ -337,8 +337,8 @@ __global__ void benthic_pelagic_kernel(double *out, const double *fluxes, size_t
 // soil_pelagic_connector Run (src/mediators/soil_pelagic_connector.F90:179-981), the generic successor of
 // benthic_pelagic_coupler.  out rows: 0 nitrate 1 ammonium 2 DIN 3 DIP 4 oxygen 5 odu 6 detC 7 zero.
 // Row 7 serves both detritus nitrogen and detritus phosphorus: the connector sums the import fields that
-// match 'detritus*nitrogen_upward_flux_at_soil_surface' (:786) and 'detritus*phosphorous_upward_flux_at_
-// soil_surface' (:933); omexdia_p exports neither (its P pool is spelled 'detritus_labile_phosphorus'), so
+// match 'detritus*nitrogen_upward_flux_at_soil_surface' (:764) and 'detritus*phosphorous_upward_flux_at_
+// soil_surface' (:911); omexdia_p exports neither (its P pool is spelled 'detritus_labile_phosphorus'), so
 // both sums stay at their initial 0.0 (:771-773, :918-920).
 // oxy_mode: 3 = oxygen and odu both wanted (plain copies, :660-679), 2 = only odu (odu - oxygen, :696-698),
 // 1 = only oxygen (oxygen - odu, :718-720).

@@ -931,8 +931,8 @@ void osed_soil_pelagic_connector(size_t n2, const double *up, double dinflux_con
             out[c + n2 * 5] = odu;   /* not in the export state */
         }
         double detN = 0.0, detC = 0.0, detP = 0.0;                                  /* :771,:842,:918 */
-        /* omexdia_p exports detritus_{labile,semilabile}_carbon only: no 'detritus*nitrogen' (:786) and no
-         * 'detritus*phosphorous' (:933; the model spells it 'phosphorus') field exists to be summed */
+        /* omexdia_p exports detritus_{labile,semilabile}_carbon only: no 'detritus*nitrogen' (:764) and no
+         * 'detritus*phosphorous' (:911; the model spells it 'phosphorus') field exists to be summed */
         detC = detC + ldetC;                                                        /* :869-874 */
         detC = detC + sdetC;
         out[c + n2 * 6] = detN;

@@ -125,6 +125,61 @@ def test_soil_pelagic_connector(gpu, oracle, want):
                 assert not got[k].any()
 
 
+def test_mediator_mirrors_in_a_coupled_sequence(gpu, oracle):
+    """pelagic model -> PelagicBenthicCoupler -> sediment Run -> SoilPelagicConnector / BenthicPelagicCoupler ->
+    pelagic model, with the field names of an ECOSMO-like and a MAECS-like pelagic model
+    (mossco_code_b200/mediators.py), against the oracle's restatement of the same mediators."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    from mossco_code_b200.mediators import BenthicPelagicCoupler, PelagicBenthicCoupler, SoilPelagicConnector
+    from mossco_code_b200.sediment import VARIABLE_NAMES
+    sh = (9, 7)
+    rng = np.random.default_rng(8)
+    f3 = lambda lo, hi: np.asfortranarray(lo + (hi - lo) * rng.random(sh + (4,)))      # (i, j, layer): bottom = layer 0
+    pel = {"temperature_in_water": f3(4, 12), "oxygen_in_water": f3(150, 300),
+           "Detritus_Nitrogen_detN_in_water": f3(2, 3), "Detritus_Nitrogen_detN_z_velocity_in_water": -1e-5 * f3(1, 2),
+           "Detritus_Carbon_detC_in_water": f3(14, 20), "Dissolved_Inorganic_Nitrogen_DIN_nutN_in_water": f3(10, 15)}
+    cfg = default_config(inum=9, jnum=7, knum=15, dzmin=0.004, dt_min=1.0)
+    with SedimentDriver(cfg) as sed:
+        sed.init_concentrations()
+        exp = {}
+        assert PelagicBenthicCoupler(sed).run(pel, exp, fill_export=True) == 0
+        ref = oracle.OracleSediment.from_config(cfg)
+        ref.init_concentrations()
+        b = lambda k: pel[k][:, :, 0]
+        cs, wz = oracle.pelagic_benthic_coupler(sh, oxygen=b("oxygen_in_water"), detN=b("Detritus_Nitrogen_detN_in_water"),
+                                                detN_z_velocity=b("Detritus_Nitrogen_detN_z_velocity_in_water"),
+                                                detC=b("Detritus_Carbon_detC_in_water"),
+                                                DIN=b("Dissolved_Inorganic_Nitrogen_DIN_nutN_in_water"))
+        ref.get_boundary_conditions(b("temperature_in_water"), cs, wz)
+        assert np.array_equal(sed.bdys, ref.bdys) and np.array_equal(sed.fluxes, ref.fluxes)
+        assert np.array_equal(exp["dissolved_oxygen_at_soil_surface"], ref.bdys[:, :, 7])
+        assert sed.run(360.0, 2, 3600.0) == 0
+        soil = {f"{v}_upward_flux_at_soil_surface": None for v in VARIABLE_NAMES}     # presence is what is checked
+        up = -sed.fluxes
+        # ECOSMO-like names: separate nitrate/ammonium, phosphate, oxygen only (-> oxygen minus reduced substances)
+        eco = {n: np.zeros(sh, order="F") for n in (
+            "hzg_ecosmo_no3_upward_flux_at_soil_surface", "hzg_ecosmo_nh4_upward_flux_at_soil_surface",
+            "hzg_ecosmo_pho_upward_flux_at_soil_surface", "hzg_ecosmo_oxy_upward_flux_at_soil_surface")}
+        kw = dict(dinflux_const=0.3, convertN=1.5, convertP=0.75)
+        assert SoilPelagicConnector(sed, **kw).run(soil, eco) == 0
+        want = oracle.soil_pelagic_connector(up, want=("nitrate", "ammonium", "DIP", "oxygen"), **kw)
+        assert np.array_equal(eco["hzg_ecosmo_no3_upward_flux_at_soil_surface"], want["nitrate"])
+        assert np.array_equal(eco["hzg_ecosmo_nh4_upward_flux_at_soil_surface"], want["ammonium"])
+        assert np.array_equal(eco["hzg_ecosmo_pho_upward_flux_at_soil_surface"], want["DIP"])
+        assert np.array_equal(eco["hzg_ecosmo_oxy_upward_flux_at_soil_surface"], up[:, :, 6] - up[:, :, 7])
+        # MAECS-like names through the older coupler: DIN branch, detritus N from the carbon fluxes
+        maecs = {n: np.zeros(sh, order="F") for n in (
+            "Dissolved_Inorganic_Nitrogen_DIN_nutN_upward_flux_at_soil_surface",
+            "Dissolved_Inorganic_Phosphorus_DIP_nutP_upward_flux_at_soil_surface",
+            "Detritus_Nitrogen_detN_upward_flux_at_soil_surface", "Detritus_Carbon_detC_upward_flux_at_soil_surface",
+            "oxygen_upward_flux_at_soil_surface")}
+        assert BenthicPelagicCoupler(sed, dinflux_const=0.3).run(soil, maecs) == 0
+        want = oracle.benthic_pelagic_coupler(up, dinflux_const=0.3)
+        for name, key in (("Dissolved_Inorganic_Nitrogen_DIN_nutN", "DIN"), ("Dissolved_Inorganic_Phosphorus_DIP_nutP", "DIP"),
+                          ("Detritus_Nitrogen_detN", "detN"), ("Detritus_Carbon_detC", "detC"), ("oxygen", "oxygen")):
+            assert np.array_equal(maecs[f"{name}_upward_flux_at_soil_surface"], want[key]), key
+
+
 @pytest.mark.parametrize("nchunks,seconds", [(4, 3600.0), (3, 1000.0), (5, 360.0), (1, 3600.0), (4, 720.0), (0, 3600.0), (0, 1000.0), (0, 360.0)])
 @pytest.mark.parametrize("mode", ["auto", "pairs"])   # auto: chains on this tile; pairs: the wet-column list, chunked
 def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds, mode):
