@@ -113,8 +113,9 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     for (int s = 0; s < nsub; ++s) {
         const bool last = (s == nsub - 1);
 
-        // upper-boundary inputs, issued first and by every lane (one address per warp: a broadcast) so that
-        // their latency hides behind the shuffles and the reaction term instead of stalling lane 0
+        // upper-boundary inputs, read by every lane (one address per warp: a broadcast) and not inside a
+        // lane-0 branch: they are step-invariant, so the compiler lifts them out of the loop and keeps them in
+        // registers (inside the branch they were an L1 round trip per step on the critical path of lane 0)
         double tin[NV];
 #pragma unroll
         for (int n = 0; n < NV; ++n) tin[n] = ld_ro((n < NPART ? top_part : top_diss) + (size_t)n * ld);
