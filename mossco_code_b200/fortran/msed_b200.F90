@@ -169,9 +169,10 @@ module msed_b200
     integer(c_int) function msed_get_boundary(h, bdys, fluxes) bind(c, name='msed_get_boundary')
       import; type(c_ptr), value :: h; real(c_double), intent(out) :: bdys(*), fluxes(*)
     end function
-    !> speculative two-step launches / chained Runge-Kutta stages (results are identical either way)
-    integer(c_int) function msed_set_step_fusion(h, enable) bind(c, name='msed_set_step_fusion')
-      import; type(c_ptr), value :: h; integer(c_int), value :: enable
+    !> speculative fused launches (results are identical in every mode): 0 off, 1 auto (chains of up to 16
+    !! steps with the column in registers where knum <= 32 and the tile is small, else pairs), 2 pairs, 3 chains
+    integer(c_int) function msed_set_step_fusion(h, mode) bind(c, name='msed_set_step_fusion')
+      import; type(c_ptr), value :: h; integer(c_int), value :: mode
     end function
     integer(c_int) function msed_set_exchange_chunks(h, nchunks) bind(c, name='msed_set_exchange_chunks')
       import; type(c_ptr), value :: h; integer(c_int), value :: nchunks
