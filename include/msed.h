@@ -200,6 +200,11 @@ int msed_set_step_fusion(msed_handle *h, int mode);
 /* number of column chunks msed_run_exchange uses (0 = choose from the tile size: 1 to 8, always the
  * asynchronous sequence; 1 = the plain sequence of the three separate calls, no overlap) */
 int msed_set_exchange_chunks(msed_handle *h, int nchunks);
+/* order in which msed_run_exchange walks a coupling interval that consists of fused pairs only: 0 = step by
+ * step (each pair over all chunks, committed before the next), 1 = chunk by chunk (every chunk runs the whole
+ * interval as soon as its import fields have landed; one commit at the end, the committed state untouched
+ * until then).  Same results either way.  Initial value: environment MSED_EXCHANGE_CHUNK_MAJOR, else 0. */
+int msed_set_exchange_order(msed_handle *h, int chunk_major);
 /* 1-D pre-simulation (component :557-632) for the handle's configuration; conc1d(1,1,knum,nvar) out.
  * bdys1d(nvar+1), fluxes1d(nvar). Runs a 1x1 tile on the same device. */
 int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const double *fluxes1d,

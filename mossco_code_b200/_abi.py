@@ -132,6 +132,7 @@ SYMBOLS = {
     "msed_run_exchange": (C.c_int, [_h, C.c_double, C.c_int, C.c_double, _dp, C.POINTER(_dp), C.POINTER(_dp),
                                     _dp, C.POINTER(StepInfo)]),
     "msed_set_exchange_chunks": (C.c_int, [_h, C.c_int]),
+    "msed_set_exchange_order": (C.c_int, [_h, C.c_int]),
     "msed_set_step_fusion": (C.c_int, [_h, C.c_int]),
     "msed_spinup_column": (C.c_int, [C.POINTER(Config), _dp, _dp, C.c_int64, C.c_int, _dp,
                                      C.POINTER(StepInfo)]),

@@ -90,6 +90,9 @@ struct msed_handle {
     int step_fusion = 1;                          // 0 off, 1 auto (chains where they apply, else pairs),
                                                   // 2 pairs only, 3 chains wherever knum allows
     long long chain_max_cols = 0;                 // auto mode: tiles up to this many columns take chain_kernel
+    double *xstage = nullptr;                     // [20][ld] staging rows of msed_run_exchange when the staging buffer
+                                                  // itself serves as third state buffer (chunk-major Run)
+    int chunk_major = 0;                          // msed_run_exchange: whole coupling interval chunk by chunk
     int pair_cooldown = 0;                        // steps to run singly after a rejection / failed pair
     long long pairs_committed = 0;
     ncclComm_t comm = nullptr;
@@ -295,10 +298,11 @@ cudaError_t launch_pair(const msed_handle *h, int method, const KParams &pin)
     const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
     const bool adaptive = method == MSED_ADAPTIVE_EULER;
     const bool denit = p.denit_out != nullptr;  // the last pair of a call also stores the denit diagnostic
+#define MSED_PAIR_L(MODEL, AD, DN, CM, OV) pair_kernel<MODEL, AD, DN, CM, OV><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p)
 #define MSED_PAIR(MODEL, AD, DN)                                                                       \
     do {                                                                                               \
-        if (p.colmap) pair_kernel<MODEL, AD, DN, true><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);   \
-        else pair_kernel<MODEL, AD, DN, false><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p);           \
+        if (p.in_ovr) { if (p.colmap) MSED_PAIR_L(MODEL, AD, DN, true, true); else MSED_PAIR_L(MODEL, AD, DN, false, true); } \
+        else          { if (p.colmap) MSED_PAIR_L(MODEL, AD, DN, true, false); else MSED_PAIR_L(MODEL, AD, DN, false, false); } \
     } while (0)
 #define MSED_PAIR_MODEL(MODEL)                                   \
     do {                                                         \
@@ -309,6 +313,7 @@ cudaError_t launch_pair(const msed_handle *h, int method, const KParams &pin)
     else MSED_PAIR_MODEL(MSED_MODEL_NONE);
 #undef MSED_PAIR_MODEL
 #undef MSED_PAIR
+#undef MSED_PAIR_L
     return cudaGetLastError();
 }
 
@@ -364,16 +369,18 @@ cudaError_t enable_pair_smem()
     MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_34)
     MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_34)
 #undef MSED_RKP_ATTR
-#define MSED_PAIR_ATTR(MODEL, AD, DN) \
-    if ((e = cudaFuncSetAttribute(pair_kernel<MODEL, AD, DN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  bytes)) != cudaSuccess) return e;                                            \
-    if ((e = cudaFuncSetAttribute(pair_kernel<MODEL, AD, DN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+#define MSED_PAIR_ATTR1(MODEL, AD, DN, CM, OV) \
+    if ((e = cudaFuncSetAttribute(pair_kernel<MODEL, AD, DN, CM, OV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   bytes)) != cudaSuccess) return e;
+#define MSED_PAIR_ATTR(MODEL, AD, DN) \
+    MSED_PAIR_ATTR1(MODEL, AD, DN, false, false) MSED_PAIR_ATTR1(MODEL, AD, DN, true, false) \
+    MSED_PAIR_ATTR1(MODEL, AD, DN, false, true) MSED_PAIR_ATTR1(MODEL, AD, DN, true, true)
     MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, true, true) MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, true, false)
     MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, false, true) MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, false, false)
     MSED_PAIR_ATTR(MSED_MODEL_NONE, true, true) MSED_PAIR_ATTR(MSED_MODEL_NONE, true, false)
     MSED_PAIR_ATTR(MSED_MODEL_NONE, false, true) MSED_PAIR_ATTR(MSED_MODEL_NONE, false, false)
 #undef MSED_PAIR_ATTR
+#undef MSED_PAIR_ATTR1
     return cudaSuccess;
 }
 
@@ -405,6 +412,7 @@ struct ExchangePlan {
     double *neg = nullptr;     // device rows [nvar][ld] receiving -fluxes
     double *host_out = nullptr;
     bool export_done = false;  // out: host_out holds the final upward fluxes
+    bool stage_private = false;  // the staging rows are not in h->scratch, which may then hold a state
 };
 
 // the step loop shared by msed_ode_solver / msed_step / msed_run / msed_run_exchange
@@ -443,6 +451,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     fill_params(h, p);
     InitVals minimum;
     for (int n = 0; n < NV; ++n) minimum.v[n] = h->cfg.minimum[n];
+    // tiles that share an accept decision must issue the same sequence of flag reductions
     const bool collective = (h->comm != nullptr || h->hook != nullptr);
     long long launches = 0;
 
@@ -482,7 +491,10 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     // both fused kernels only work on wet columns, so the tile size that decides between them counts those
     const long long work_cols = h->colmap ? (long long)h->wet_idx.size() : (long long)h->ncol;
     const bool chain_fit = h->K <= CHAIN_MAX_LAYERS &&
-                           (h->step_fusion == 3 || (h->step_fusion == 1 && work_cols <= h->chain_max_cols));
+                           (h->step_fusion == 3 ||
+                            (h->step_fusion == 1 && !collective && work_cols <= h->chain_max_cols));
+    // (with a collective every rank has to take the same decision, and the tile size is a per-rank fact:
+    //  auto mode then stays with pairs; mode 3, set on every rank, selects chains)
     const bool use_chain = fusable && chain_fit && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 1;
     int chain_base = 0, chain_extra = 0;
     if (use_chain) {
@@ -512,7 +524,42 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         return MSED_OK;
     };
     bool first_pending = plan && plan->first && single_attempt;
-    for (long long q = 0; q < npairs; ++q) {
+    // Chunk-major Run (msed_run_exchange): when the whole coupling interval is pairs, chunk c runs its boundary
+    // assembly, ALL its pairs and its export as soon as its import fields have landed, so that only the first
+    // chunk's H2D and the last chunk's D2H are exposed (step-major order leaves the GPU short of work while the
+    // transfers of the first pair are still arriving).  The pairs of a chunk go A -> B -> S -> B -> ... through
+    // the two state buffers and the staging buffer; the committed state A is untouched until one controller has
+    // seen the flags of every pair of every chunk, so a rejected step anywhere still costs nothing but the redo.
+    const int cur_before = h->cur;
+    const bool seq_mode = plan && plan->stage_private && plan->first && plan->last && first_pending && !use_chain &&
+                          npairs >= 2 && fused_planned == nsteps && h->scratch != nullptr;
+    if (seq_mode) {
+        double *A = h->buf[cur_before], *B = h->buf[1 - cur_before], *S = h->scratch;
+        for (int c = 0; c < plan->nchunks; ++c) {
+            if ((rc = boundary_chunk(c))) return rc;
+            const double *in = A;
+            for (long long q = 0; q < npairs; ++q) {
+                double *out = (q % 2 == 0) ? B : S;
+                KParams pc = p;
+                pc.col0 = plan->c0[c];
+                pc.col_end = plan->c1[c];
+                pc.in_ovr = in;
+                pc.out_ovr = out;
+                if (q == npairs - 1) pc.denit_out = h->denit;
+                CUDA_TRY(h, launch_pair(h, method, pc));
+                launches += 1;
+                in = out;
+            }
+            if ((rc = export_chunk(c))) return rc;
+        }
+        first_pending = false;
+        if (collective)
+            if ((rc = reduce_flags(h))) return rc;
+        // commits all pairs at once (or none): same gate and bookkeeping as a chain of nsteps steps
+        chain_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method, (int)nsteps);
+        launches += 1;
+    }
+    for (long long q = 0; q < (seq_mode ? 0 : npairs); ++q) {
         const bool last_pair = last_is_pair && q == npairs - 1;
         const int m = use_chain ? chain_base + (q < chain_extra ? 1 : 0) : 2;  // steps in this launch
         const bool chunk_last = last_pair && plan && plan->last;
@@ -630,6 +677,10 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     else if (h->pair_cooldown > 0) h->pair_cooldown -= (int)std::min<long long>(nsteps, h->pair_cooldown);
     h->pairs_committed += (npairs > 0 && r.pair_failures == 0) ? npairs : 0;
     h->denit_valid = last_is_pair && r.pair_failures == 0 && !r.stop && r.steps_done == nsteps;
+    // a committed chunk-major sequence with an even number of pairs ends in the staging buffer: it becomes
+    // the state buffer the controller's flipped `cur` points at, the intermediate buffer becomes staging
+    if (seq_mode && r.pair_failures == 0 && !r.stop && r.steps_done == nsteps && npairs % 2 == 0)
+        std::swap(h->buf[1 - cur_before], h->scratch);
     h->cur = r.cur;
     if (diag && r.last_min_dt < h->last_min_dt) {
         long long idx = -1;
@@ -750,6 +801,7 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     // column pair kernel cannot fill the machine (one wave = 148 SMs x 3 CTAs x 128 columns), and lose 5-10 % above
     h->chain_max_cols = 65536;
     if (const char *e = std::getenv("MSED_CHAIN_MAX_COLS")) h->chain_max_cols = std::atoll(e);
+    if (const char *e = std::getenv("MSED_EXCHANGE_CHUNK_MAJOR")) h->chunk_major = std::atoi(e) != 0;
     if (const char *e = std::getenv("MSED_STEP_FUSION")) {  // initial msed_set_step_fusion mode (0..3)
         const int mode = std::atoi(e);
         if (mode >= 0 && mode <= 3) h->step_fusion = mode;
@@ -847,7 +899,7 @@ int msed_destroy(msed_handle *h)
     if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     cudaFree(h->buf[0]); cudaFree(h->buf[1]); cudaFree(h->aux[0]); cudaFree(h->aux[1]);
     cudaFree(h->por); cudaFree(h->bdys); cudaFree(h->fluxes); cudaFree(h->par_surface);
-    cudaFree(h->scratch); cudaFree(h->denit); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->colmap); cudaFree(h->ctl);
+    cudaFree(h->scratch); cudaFree(h->denit); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->colmap); cudaFree(h->xstage); cudaFree(h->ctl);
     cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->pel);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -1220,6 +1272,13 @@ int msed_set_step_fusion(msed_handle *h, int enable)
     return MSED_OK;
 }
 
+int msed_set_exchange_order(msed_handle *h, int chunk_major)
+{
+    if (!h) return MSED_ERR_ARG;
+    h->chunk_major = chunk_major ? 1 : 0;
+    return MSED_OK;
+}
+
 int msed_set_exchange_chunks(msed_handle *h, int nchunks)
 {
     if (!h || nchunks < 0 || nchunks > 16) return fail(h, MSED_ERR_ARG, "nchunks must be in [0,16]");
@@ -1270,6 +1329,11 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
     plan.nchunks = used;
     // staging rows: [0..11] import fields, [12..19] negated fluxes
     double *stage = h->scratch;
+    if (h->chunk_major) {  // the staging buffer proper is a state buffer of the chunk-major sequence (run_steps)
+        if (!h->xstage) CUDA_TRY(h, cudaMalloc(&h->xstage, (size_t)(12 + NV) * h->ld * sizeof(double)));
+        stage = h->xstage;
+        plan.stage_private = true;
+    }
     const double *host[12];
     const double **dev[12];
     int nf = 0;

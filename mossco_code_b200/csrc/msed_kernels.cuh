@@ -97,6 +97,8 @@ struct KParams {
     double *denit_out;       // [K][ld]: FABM denit diagnostic of the second step of a call's last pair, or null
     const int *colmap;       // pair_kernel on a masked tile: indices of the wet columns, ascending; col0/col_end
                              // then count wet columns (null: identity)
+    const double *in_ovr;    // pair_kernel<.., OVR>: explicit input / output state buffers of a launch inside a
+    double *out_ovr;         // chunk-major sequence (msed.cu run_steps), instead of buf[cur] / buf[1-cur]
 };
 
 // loaders, reaction term and the fused column kernel

@@ -35,7 +35,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-template <int MODEL, bool ADAPTIVE, bool DENIT, bool COLMAP = false>
+template <int MODEL, bool ADAPTIVE, bool DENIT, bool COLMAP = false, bool OVR = false>
 __global__ void __launch_bounds__(COL_BLOCK, PAIR_MIN_BLOCKS)
 pair_kernel(const __grid_constant__ KParams p)
 {
@@ -63,8 +63,10 @@ pair_kernel(const __grid_constant__ KParams p)
     const int K = p.K;
     const size_t ld = p.ld;
     const size_t plane = (size_t)K * ld;
-    const double *in = p.buf[cur] + col;
-    double *out = p.buf[1 - cur] + col;
+    // OVR: one launch of a chunk-major sequence (run_steps): the pairs of a coupling interval follow each
+    // other chunk by chunk through explicitly named buffers, the committed state stays untouched
+    const double *in = (OVR ? p.in_ovr : p.buf[cur]) + col;
+    double *out = (OVR ? p.out_ovr : p.buf[1 - cur]) + col;
 
     // ---- input ring (cp.async, as in column_kernel) and the c1 window --------------------------
     const uint32_t sbase = smem_u32(ring) + threadIdx.x * 8u;

@@ -177,6 +177,9 @@ module msed_b200
     integer(c_int) function msed_set_exchange_chunks(h, nchunks) bind(c, name='msed_set_exchange_chunks')
       import; type(c_ptr), value :: h; integer(c_int), value :: nchunks
     end function
+    integer(c_int) function msed_set_exchange_order(h, chunk_major) bind(c, name='msed_set_exchange_order')
+      import; type(c_ptr), value :: h; integer(c_int), value :: chunk_major
+    end function
     !> 1-D pre-simulation, fabm_sediment_component.F90:557-632
     integer(c_int) function msed_spinup_column(cfg, bdys1d, fluxes1d, nsteps, method, conc1d, info) &
         bind(c, name='msed_spinup_column')

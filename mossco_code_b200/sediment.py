@@ -271,6 +271,10 @@ class SedimentDriver:
     def set_exchange_chunks(self, nchunks: int):
         self._check(self._lib.msed_set_exchange_chunks(self._h, int(nchunks)))
 
+    def set_exchange_order(self, chunk_major: bool):
+        """``run_exchange``: walk a coupling interval of fused pairs chunk by chunk (True) or step by step."""
+        self._check(self._lib.msed_set_exchange_order(self._h, int(bool(chunk_major))))
+
     # -- benthic-pelagic exchange on device (BASELINE config 5) --------------------------------
     def pelagic_init(self, conc2d, wz2d, layer_height2d, temperature2d):
         c = _f64(conc2d, self.shape2d + (self.nvar,), "pelagic conc")

@@ -37,6 +37,7 @@ def scenario(case, world, rank, local, bump_row, nsteps):
     j0, j1 = slab_bounds(case.jnum, world, rank)
     sed = prepared(case, j0, j1, local, bump_row)
     init_flag_collective(sed)
+    sed.set_step_fusion("chains")   # under a collective auto mode keeps to pairs: the choice must not depend on the tile
     rc = sed.step(DT, 2, nsteps)
     mine = torch.from_numpy(np.ascontiguousarray(sed.conc)).cuda()
     sub = torch.tensor([sed.info.subcycle_warnings, sed.info.rhs_evaluations, rc, sed.info.fused_steps], device="cuda")
@@ -47,6 +48,7 @@ def scenario(case, world, rank, local, bump_row, nsteps):
     ok, text = True, ""
     if rank == 0:
         whole = prepared(case, 0, case.jnum, local, bump_row)
+        whole.set_step_fusion("chains")
         rc0 = whole.step(DT, 2, nsteps)
         got = gather_slabs([np.asfortranarray(p.cpu().numpy()) for p in parts])
         info = whole.info

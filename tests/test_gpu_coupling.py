@@ -220,6 +220,59 @@ def test_run_exchange_equals_separate_calls(gpu, nchunks, seconds, mode):
     assert np.array_equal(res[0][2], res[1][2])
 
 
+@pytest.mark.parametrize("nchunks,seconds,boost", [(4, 3600.0, False), (3, 2880.0, False), (5, 1440.0, False),
+                                                   (4, 3600.0, True), (2, 2880.0, True)])
+def test_run_exchange_chunk_major(gpu, nchunks, seconds, boost):
+    """Chunk-major order of a coupling interval (msed_set_exchange_order): every chunk runs all pairs of the
+    interval through explicitly named buffers and one controller commits them -- odd and even numbers of pairs
+    (the even case ends in the staging buffer: pointer rotation), a tile with land (wet-column list), several
+    Runs in a row, a Run with rejected attempts (nothing committed, redone step by step), and ordinary calls
+    afterwards must all give the bits of the separate unfused calls."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    from mossco_code_b200.sediment import PARTICULATE
+    case = make_case("xcm", 70, 37, 20, 0.003, seed=93, land_fraction=0.25)
+    rng = np.random.default_rng(6)
+    sh = (70, 37)
+    temp = 4 + 8 * rng.random(sh)
+    cs = [np.asfortranarray((-case.fluxes[:, :, n]) if PARTICULATE[n] else case.bdys[:, :, n + 1]) for n in range(8)]
+    wz = [np.ones(sh, order="F") if PARTICULATE[n] else None for n in range(8)]
+    kw = dict(rnit=2.0e3, rODUox=2.0e3) if boost else {}
+    res = []
+    for fused in (False, True):
+        cfg = default_config(inum=70, jnum=37, knum=20, dzmin=0.003, dt_min=1.0, **kw)
+        with SedimentDriver(cfg) as sed:
+            sed.set_mask(case.mask)
+            sed.init_concentrations()
+            sed.set_boundary(case.bdys, case.fluxes)
+            sed.set_step_fusion("pairs" if fused else "off")
+            ups, sub, fusedsteps = [], 0, 0
+            for _ in range(3):
+                if fused:
+                    sed.set_exchange_chunks(nchunks)
+                    sed.set_exchange_order(True)
+                    rc, up = sed.run_exchange(360.0, 2, seconds, temp, cs, wz)
+                else:
+                    sed.get_boundary_conditions(temp, cs, wz)
+                    rc = sed.run(360.0, 2, seconds)
+                    up = sed.upward_fluxes()
+                assert rc == 0
+                ups.append(up.copy())
+                sub += sed.info.subcycle_warnings
+                fusedsteps += sed.info.fused_steps
+            denit = sed.field("denit")
+            rhs = sed.get_rhs()                       # uses the staging buffer: must still be a valid one
+            assert sed.step(360.0, 2, 3) == 0         # and ordinary calls carry on from the rotated buffers
+            res.append((sed.conc, ups, sed.bdys, denit, rhs, sub, fusedsteps))
+    a, b = res
+    assert a[5] == b[5] and (a[5] > 0) == boost
+    if not boost and b[5] == 0:
+        assert b[6] == 3 * int(round(seconds / 360.0))          # every step of every Run went through the sequence
+    assert np.array_equal(a[0], b[0])
+    for x, y in zip(a[1], b[1]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+
+
 def test_run_exchange_with_rejected_attempt(gpu):
     """If an attempt is rejected the chunk-wise export is stale and must be redone from the final state."""
     from mossco_code_b200 import SedimentDriver, default_config
