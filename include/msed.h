@@ -203,7 +203,7 @@ int msed_set_exchange_chunks(msed_handle *h, int nchunks);
 /* order in which msed_run_exchange walks a coupling interval that consists of fused pairs only: 0 = step by
  * step (each pair over all chunks, committed before the next), 1 = chunk by chunk (every chunk runs the whole
  * interval as soon as its import fields have landed; one commit at the end, the committed state untouched
- * until then).  Same results either way.  Initial value: environment MSED_EXCHANGE_CHUNK_MAJOR, else 0. */
+ * until then).  Same results either way.  Initial value: environment MSED_EXCHANGE_CHUNK_MAJOR, else 1. */
 int msed_set_exchange_order(msed_handle *h, int chunk_major);
 /* 1-D pre-simulation (component :557-632) for the handle's configuration; conc1d(1,1,knum,nvar) out.
  * bdys1d(nvar+1), fluxes1d(nvar). Runs a 1x1 tile on the same device. */

@@ -92,7 +92,7 @@ struct msed_handle {
     long long chain_max_cols = 0;                 // auto mode: tiles up to this many columns take chain_kernel
     double *xstage = nullptr;                     // [20][ld] staging rows of msed_run_exchange when the staging buffer
                                                   // itself serves as third state buffer (chunk-major Run)
-    int chunk_major = 0;                          // msed_run_exchange: whole coupling interval chunk by chunk
+    int chunk_major = 1;                          // msed_run_exchange: whole coupling interval chunk by chunk
     int pair_cooldown = 0;                        // steps to run singly after a rejection / failed pair
     long long pairs_committed = 0;
     ncclComm_t comm = nullptr;
