@@ -73,6 +73,7 @@ struct msed_handle {
     unsigned char *mask = nullptr;
     int *colmap = nullptr;          // device list of the wet columns (null while the tile has no land)
     std::vector<int> wet_idx;       // host copy: converts column ranges of chunked launches
+    bool has_land = false;          // msed_set_mask marked at least one column as land
     Ctl *ctl = nullptr;         // device
     Ctl *ctl_host = nullptr;    // pinned mirror
     double *minloc_val = nullptr;
@@ -679,8 +680,17 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     h->denit_valid = last_is_pair && r.pair_failures == 0 && !r.stop && r.steps_done == nsteps;
     // a committed chunk-major sequence with an even number of pairs ends in the staging buffer: it becomes
     // the state buffer the controller's flipped `cur` points at, the intermediate buffer becomes staging
-    if (seq_mode && r.pair_failures == 0 && !r.stop && r.steps_done == nsteps && npairs % 2 == 0)
+    if (seq_mode && r.pair_failures == 0 && !r.stop && r.steps_done == nsteps && npairs % 2 == 0) {
         std::swap(h->buf[1 - cur_before], h->scratch);
+        // the stepping kernels never write land columns, so the buffer rotated in holds whatever last used the
+        // staging area there: restore conc = missing_value (driver :464) before anything can read it
+        if (h->has_land) {
+            fill_masked_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->buf[1 - cur_before], h->mask, h->ld,
+                                                                        h->ncol, NV * h->K, 1.0e20);
+            CUDA_TRY(h, cudaGetLastError());
+            launches += 1;
+        }
+    }
     h->cur = r.cur;
     if (diag && r.last_min_dt < h->last_min_dt) {
         long long idx = -1;
@@ -936,6 +946,7 @@ int msed_set_mask(msed_handle *h, const int32_t *mask2d)
     h->wet_idx.clear();
     for (int c = 0; c < h->ncol; ++c)
         if (!m[c]) h->wet_idx.push_back(c);
+    h->has_land = (int)h->wet_idx.size() < h->ncol;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->colmap) { cudaFree(h->colmap); h->colmap = nullptr; }
     if ((int)h->wet_idx.size() < h->ncol && !h->wet_idx.empty() && !std::getenv("MSED_NO_COLMAP")) {

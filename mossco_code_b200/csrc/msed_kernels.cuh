@@ -211,6 +211,17 @@ __global__ void apply_mask_kernel(double *por, double *b0, double *b1, const uns
     }
 }
 
+// conc = missing_value on the land columns of ONE state buffer: the staging buffer that a chunk-major Run
+// rotates in as state buffer (msed.cu run_steps) was never written there, because every stepping kernel
+// skips land columns (driver :464,:535)
+__global__ void fill_masked_kernel(double *b, const unsigned char *mask, size_t ld, int ncol, int rows,
+                                   double missing)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol || !mask[col]) return;
+    for (int q = 0; q < rows; ++q) b[(size_t)q * ld + col] = missing;
+}
+
 // init_concentrations, driver :455-468
 struct InitVals { double v[NV]; };
 __global__ void init_conc_kernel(double *b0, double *b1, const double *por, const unsigned char *mask,

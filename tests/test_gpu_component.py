@@ -240,3 +240,41 @@ def test_component_output_dat(gpu, tmp_path):
     assert np.all(np.diff(rows[:, 1]) > 0)                       # depth increases
     assert FabmSedimentComponent._fortran_e(-1234.5678, 15, 4, 3).strip() == "-0.1235E+004"
     assert FabmSedimentComponent._fortran_e(0.99996, 15, 4, 3).strip() == "0.1000E+001"
+
+
+@pytest.mark.parametrize("seconds", [1440.0, 3600.0])     # 2 pairs (state ends in the rotated-in staging buffer), 5 pairs
+def test_component_masked_tile_pairs_chunk_major(gpu, seconds):
+    """A masked K=40 tile driven through the component with fused pairs in several chunks (chunk-major Run):
+    every Run uses the staging buffer (porosity import, 3-D exports) AND may rotate it in as the state buffer,
+    so land cells of every <name>_in_soil export must stay at missing_value and the wet cells must carry the
+    bits of the unfused, unchunked component."""
+    from mossco_code_b200.component import FabmSedimentComponent
+    from mossco_code_b200.sediment import VARIABLE_NAMES
+    case = make_case("cm", 70, 23, 40, 0.0015, seed=29, land_fraction=0.3, par_max=30.0)
+    land = case.mask > 0
+    surf = np.asfortranarray(0.55 + 0.2 * np.random.default_rng(3).random((70, 23)))
+    out = []
+    for fused in (False, True):
+        comp = FabmSedimentComponent()
+        imp, exp = {}, {}
+        comp.initialize_p1(imp, exp, grid_shape=(70, 23), grid_mask=1 - case.mask,
+                           run_nml=dict(numlayers=40, dzmin=0.0015, dt=360.0, dt_min=1.0, ode_method=2))
+        comp.sed.set_step_fusion("pairs" if fused else "off")
+        comp.sed.set_exchange_chunks(4 if fused else 1)
+        comp.sed.set_exchange_order(True)
+        imp.update(_import_state(case, None))
+        imp["porosity_at_soil_surface"] = surf
+        snaps = []
+        for it in range(4):
+            comp.run(imp, exp, run_seconds=seconds)
+            for v in VARIABLE_NAMES:
+                assert np.all(exp[f"{v}_in_soil"][land] == 1e20), (it, v)
+            snaps.append({k: np.array(a, copy=True) for k, a in exp.items()})
+        if fused:
+            assert comp.last_info.fused_steps == int(round(seconds / 360.0))
+        out.append(snaps)
+        comp.finalize()
+    for a, b in zip(*out):
+        assert set(a) == set(b)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
