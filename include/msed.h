@@ -189,10 +189,15 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
                       const double *temperature2d, const double *const *csurf, const double *const *wz,
                       double *upward_fluxes, msed_step_info *info);
 /* Step fusion (default on): Euler / adaptive-Euler steps are issued in speculative fused launches that
- * read and write the state once for several steps -- pairs (thread per column, two steps) or, for
- * knum <= 32, chains (warp per column with the state in registers, up to 16 steps).  A fused launch is
- * committed only if none of its steps would be rejected (solver_library.F90:126) or stopped by
- * check_NaN, otherwise the same steps are redone singly from the untouched state.  Results are
+ * read and write the state once for several accepted sub-steps -- pairs (thread per column, two sub-steps) or,
+ * for knum <= 32, chains (warp per column with the state in registers, up to 16 sub-steps).  Each call is
+ * planned as a definite piece of the reference's attempt sequence (solver_library.F90:104-140), the way the
+ * last completed step went: every step accepted at dt on its first attempt, or -- in a sub-cycling episode --
+ * every step as the rejected attempts at dt (, dt/4) followed by 4 (16) accepted sub-steps of dt/4 (dt/16); a
+ * rejected attempt leaves the state unchanged, so its RHS is the one of the sub-step that follows and costs no
+ * pass of its own.  A fused launch is committed only if the reference would have taken exactly the planned
+ * decisions (every planned rejection seen, no accepted sub-step that should have been rejected :126, nothing
+ * stopped by check_NaN); otherwise the same attempts are redone singly from the untouched state.  Results are
  * bit-identical in every mode.  mode: 0 off, 1 auto (default: chains where they apply, else pairs),
  * 2 pairs only, 3 chains wherever knum allows.  Mode 1 picks chains for tiles of up to 65536 wet columns
  * (environment MSED_CHAIN_MAX_COLS), where a thread per column cannot fill the GPU. */
@@ -209,6 +214,25 @@ int msed_set_exchange_order(msed_handle *h, int chunk_major);
  * bdys1d(nvar+1), fluxes1d(nvar). Runs a 1x1 tile on the same device. */
 int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const double *fluxes1d,
                        int64_t nsteps, int method, double *conc1d, msed_step_info *info);
+
+/* The same pre-simulation for a BATCH of nmembers independent 1-D columns in one launch (warp per member,
+ * the column in registers for all nsteps calls; knum <= 32, no distributed POM flux -- other configurations
+ * loop over msed_spinup_column).  Members share cfg's grid and sed_nml and differ in bdys1d(nmembers,nvar+1),
+ * fluxes1d(nmembers,nvar) (Fortran order: member fastest) and, if members != NULL, in their reaction
+ * parameters and initial values.  Every member is its own domain, as sed1d is in the reference: the accept
+ * test (solver_library.F90:121), last_min_dt and last_min_dt_grid_cell (:130-135) are per member.
+ * Outputs: conc1d(nmembers,1,knum,nvar); info[nmembers] (steps_done, rhs_evaluations, subcycle_warnings,
+ * last_min_dt, last_min_dt_grid_cell; kernel_ms / kernel_launches of the one launch in every entry), may be
+ * NULL.  Bit-identical to msed_spinup_column member by member. */
+typedef struct msed_spinup_member {
+    double rLabile, rSemilabile, NCrLdet, NCrSdet, PAds, PAdsODU, NH3Ads, CprodMax;
+    double rnit, ksO2nitri, rODUox, ksO2oduox, ksO2oxic, ksNO3denit, kinO2denit;
+    double kinNO3anox, kinO2anox;                 /* as in msed_config (rates per day) */
+    double initial_value[MSED_NVAR];
+} msed_spinup_member;
+int msed_spinup_batch(const msed_config *cfg, int32_t nmembers, const msed_spinup_member *members,
+                      const double *bdys1d, const double *fluxes1d, int64_t nsteps, int method,
+                      double *conc1d, msed_step_info *info);
 
 /* ---- benthic-pelagic exchange on device (BASELINE config 5) -------------------------------- */
 /* One well-mixed pelagic box per column, resident on the device, so that a coupling step needs no
@@ -281,6 +305,76 @@ typedef struct msed_soil_pelagic_fluxes {
 int msed_soil_pelagic_connector(msed_handle *h, const msed_soil_pelagic_params *par,
                                 const msed_soil_pelagic_fluxes *out);
 
+/* pelagic_soil_connector Run, src/mediators/pelagic_soil_connector.F90:176-2122 (the generic successor of
+ * pelagic_benthic_coupler; namelist /pelagic_soil_connector/ :146-148, defaults :38-46): bottom-layer pelagic
+ * fields (inum,jnum; NULL = field absent from the import state) -> the sediment's *_at_soil_surface /
+ * *_z_velocity_at_soil_surface fields, fed straight into get_boundary_conditions (component :1865-2030)
+ * without leaving the device.  Temperature (:351) and PAR (:330) are passed through.
+ *   detritus: C:N = detC/(1E-5+detN) (106/16 without detC, :1022-1066) splits detN into the labile and
+ *     semilabile carbon pools with the end members NC_ldet, NC_sdet (:1082-1095); the sinking velocity handed
+ *     to the sediment is sinking_factor * fac_env * velocity, fac_env = depth^2/(depth^2+half_sedimentation_
+ *     depth^2) * half_sedimentation_tke/(tke+half_sedimentation_tke) + sinking_factor_min/sinking_factor, times
+ *     1/(1+(detC/critical_detritus)^4) (:1150-1232; each factor only if its field / parameter is there);
+ *   detritus P: detP, else convertN*detN/16 (:1521-1559);
+ *   ammonium / nitrate: the field if imported, else DIN - the other one, else DIN/2, else the other one
+ *     (:1816-1845, :1930-1965), times convertN;  phosphate: convertP*DIP, else convertP*convertN*DIN/16 with DIN
+ *     taken as nitrate+ammonium or twice the one that exists (:2040-2110);
+ *   oxygen / reduced substances: both imported -> copies; only one -> its positive part and the positive part
+ *     of its negative (:800-860).
+ * MSED_COMPAT_P2S_HEAD (msed_set_compat) reproduces what the HEAD revision of the file computes where that
+ * differs from the above and is defined: the labile/semilabile carbon CONCENTRATION fields are overwritten with
+ * sinking_factor*fac_env*detN (the "velocity" block fetches fieldList(1) again, :1291-1295, :1351-1355) and the
+ * two carbon velocity fields are never written (here: 0, the value the component creates them with); the
+ * phosphorus velocity is sinking_factor*fac_env*detN unless a detP velocity is imported (:1595-1630);
+ * phosphate is recomputed from DIN even when DIP is imported (:2092-2094).  (HEAD's oxygen-only branch
+ * dereferences the unassociated odu pointer, :849-853: there is nothing to reproduce.) */
+typedef struct msed_pelagic_soil_state {
+    const double *temperature;        /* temperature_in_water (required) */
+    const double *par;                /* photosynthetically_active_radiation_in_water, NULL: par_surface untouched */
+    const double *oxygen, *odu;       /* dissolved_oxygen_in_water / dissolved_reduced_substances_in_water */
+    const double *detN;               /* Detritus_Nitrogen_detN_in_water (required) */
+    const double *detN_z_velocity;    /* (required) */
+    const double *detC;               /* Detritus_Carbon_detC_in_water */
+    const double *detP, *detP_z_velocity;
+    const double *nitrate, *ammonium, *DIN, *DIP;   /* at least one of nitrate, ammonium, DIN */
+    const double *water_depth;        /* water_depth_at_soil_surface */
+    const double *tke;                /* turbulent_kinetic_energy_at_soil_surface */
+} msed_pelagic_soil_state;
+typedef struct msed_pelagic_soil_params {
+    double sinking_factor, sinking_factor_min, NC_ldet, NC_sdet;
+    double half_sedimentation_depth, half_sedimentation_tke, critical_detritus, convertN, convertP;
+} msed_pelagic_soil_params;
+/* the module defaults, :38-46 (sinking_factor_min, half_sedimentation_depth and critical_detritus are
+ * default-real literals there: 0.02, 0.1 and 60.0 rounded to binary32) */
+int msed_pelagic_soil_params_defaults(msed_pelagic_soil_params *par);
+int msed_pelagic_soil_connector(msed_handle *h, const msed_pelagic_soil_state *state,
+                                const msed_pelagic_soil_params *par);
+
+/* Reference quirks that are NOT reproduced by default, switchable for bit parity with reference coupled runs
+ * (flags are OR-ed):
+ *   MSED_COMPAT_P2B_OXYGEN_LAST_CELL  pelagic_benthic_coupler assigns the whole oxy/odu arrays inside its i,j
+ *     loop (pelagic_benthic_coupler.F90:344-349), so every column gets max(0, +-O2) of the tile's LAST cell;
+ *     default: per column.
+ *   MSED_COMPAT_P2S_HEAD              see msed_pelagic_soil_connector. */
+#define MSED_COMPAT_P2B_OXYGEN_LAST_CELL 1
+#define MSED_COMPAT_P2S_HEAD 2
+int msed_set_compat(msed_handle *h, int flags);
+
+/* ---- whole-domain diagnostics (the optional reductions beside the accept flag) ---- */
+/* Sums over the wet columns of the tile -- and, with reduce_over_ranks != 0 and a communicator
+ * (msed_comm_init), over all tiles by ncclAllReduce(double, SUM, 2*nvar) -- of the bed flux fluxes(:,:,n)
+ * [mmol m-2 s-1 x columns] and of the inventory sum_k conc*porosity*dz [mmol m-2 x columns] per variable.
+ * Multiply by the cell area for budgets.  The per-tile sums have a fixed summation order. */
+int msed_diagnostics(msed_handle *h, double *bed_flux_sum, double *inventory, int reduce_over_ranks);
+/* Checksum of the state over the wet columns that does not depend on how the domain is cut into tiles:
+ * out[0] = sum bits(conc)*(2g+1) mod 2^64, out[1] = xor bits(conc), g = index of the cell in the GLOBAL
+ * conc(inum,jnum_global,knum,nvar) array.  global_ncol = inum*jnum_global, col_offset = inum*j_offset.  Tile
+ * values combine by wrapping addition / xor; a sharded run must reproduce the single-tile pair. */
+int msed_state_checksum(msed_handle *h, int64_t global_ncol, int64_t col_offset, uint64_t out[2]);
+/* fp64 pipe throughput of `device` measured with a DFMA micro-kernel (8 independent chains per thread, every
+ * SM filled): *tflops = 2 x FMA/s.  The denominator of the fp64 roofline bench.py reports for fused launches. */
+int msed_measure_fp64_peak(int device, double *tflops);
+
 /* ---- execution control -------------------------------------------------------------------- */
 /* all work is enqueued on this cudaStream_t (default: a private non-blocking stream) */
 int msed_set_stream(msed_handle *h, void *cuda_stream);
@@ -299,8 +393,10 @@ int msed_nccl_unique_id(char id[128]);
 int msed_comm_init(msed_handle *h, const char id[128], int nranks, int rank);
 int msed_comm_destroy(msed_handle *h);
 /* split phase for hosts that own the collective themselves (e.g. torch.distributed):
- * msed_step runs attempt kernels and calls hook(user, dev_flags, 2, stream) to MAX-reduce
- * two int32 device flags across ranks before each accept/reject decision. */
+ * msed_step runs attempt kernels and calls hook(user, dev_flags, count, stream) to MAX-reduce
+ * `count` int32 device flags across ranks before each accept/reject decision (count = 4, or 40 for a fused
+ * group that plans rejected attempts).  With adaptive_solver_diagnostics the minloc of :131-135 is reduced
+ * over the tiles as well (NCCL communicator only) and reported in global grid indices (i_offset, j_offset). */
 typedef int (*msed_allreduce_hook)(void *user, void *dev_flags_i32, int count, void *cuda_stream);
 int msed_set_allreduce_hook(msed_handle *h, msed_allreduce_hook hook, void *user);
 

@@ -96,6 +96,29 @@ class SoilPelagicFluxes(C.Structure):
         "nitrate", "ammonium", "DIN", "DIP", "oxygen", "odu", "detN", "detC", "detP")]
 
 
+class PelagicSoilState(C.Structure):
+    """``msed_pelagic_soil_state`` -- inputs of pelagic_soil_connector (NULL = field absent)."""
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in (
+        "temperature", "par", "oxygen", "odu", "detN", "detN_z_velocity", "detC", "detP", "detP_z_velocity",
+        "nitrate", "ammonium", "DIN", "DIP", "water_depth", "tke")]
+
+
+class PelagicSoilParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "sinking_factor", "sinking_factor_min", "NC_ldet", "NC_sdet", "half_sedimentation_depth",
+        "half_sedimentation_tke", "critical_detritus", "convertN", "convertP")]
+
+
+class SpinupMember(C.Structure):
+    """``msed_spinup_member`` -- reaction parameters and initial values of one member of a spin-up batch."""
+    _fields_ = [(n, C.c_double) for n in (
+        "rLabile", "rSemilabile", "NCrLdet", "NCrSdet", "PAds", "PAdsODU", "NH3Ads", "CprodMax", "rnit",
+        "ksO2nitri", "rODUox", "ksO2oduox", "ksO2oxic", "ksNO3denit", "kinO2denit", "kinNO3anox",
+        "kinO2anox")] + [("initial_value", C.c_double * NVAR)]
+
+
+COMPAT_P2B_OXYGEN_LAST_CELL, COMPAT_P2S_HEAD = 1, 2
+
 ALLREDUCE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 
 _dp = C.POINTER(C.c_double)
@@ -142,6 +165,14 @@ SYMBOLS = {
     "msed_pelagic_benthic_coupler": (C.c_int, [_h, C.POINTER(PelagicState)]),
     "msed_benthic_pelagic_coupler": (C.c_int, [_h, C.POINTER(BenthicPelagicParams), C.POINTER(PelagicFluxes)]),
     "msed_soil_pelagic_connector": (C.c_int, [_h, C.POINTER(SoilPelagicParams), C.POINTER(SoilPelagicFluxes)]),
+    "msed_spinup_batch": (C.c_int, [C.POINTER(Config), C.c_int32, C.POINTER(SpinupMember), _dp, _dp, C.c_int64,
+                                    C.c_int, _dp, C.POINTER(StepInfo)]),
+    "msed_pelagic_soil_params_defaults": (C.c_int, [C.POINTER(PelagicSoilParams)]),
+    "msed_pelagic_soil_connector": (C.c_int, [_h, C.POINTER(PelagicSoilState), C.POINTER(PelagicSoilParams)]),
+    "msed_set_compat": (C.c_int, [_h, C.c_int]),
+    "msed_diagnostics": (C.c_int, [_h, _dp, _dp, C.c_int]),
+    "msed_state_checksum": (C.c_int, [_h, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
+    "msed_measure_fp64_peak": (C.c_int, [C.c_int, _dp]),
     "msed_set_stream": (C.c_int, [_h, C.c_void_p]),
     "msed_synchronize": (C.c_int, [_h]),
     "msed_device_state": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),

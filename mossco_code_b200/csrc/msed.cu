@@ -5,6 +5,7 @@
 // the device in the reference's own Fortran layout, the column kernels in msed_kernels.cuh do the
 // array work.  There is no CPU compute path in this file.
 #include "msed_kernels.cuh"
+#include "msed_launch.h"
 
 #include <algorithm>
 #include <cmath>
@@ -51,7 +52,11 @@ NcclApi &nccl_api()
     return api;
 }
 constexpr int kNcclInt32 = 2;  // ncclInt32
+constexpr int kNcclInt64 = 4;  // ncclInt64
+constexpr int kNcclFloat64 = 8;  // ncclFloat64
+constexpr int kNcclSum = 0;    // ncclSum
 constexpr int kNcclMax = 2;    // ncclMax
+constexpr int kNcclMin = 3;    // ncclMin
 }  // namespace
 
 // ---- handle -----------------------------------------------------------------------------------
@@ -78,6 +83,8 @@ struct msed_handle {
     Ctl *ctl_host = nullptr;    // pinned mirror
     double *minloc_val = nullptr;
     long long *minloc_idx = nullptr;
+    double *red = nullptr;      // 32 doubles of device scratch for the small cross-tile reductions
+    int compat = 0;             // MSED_COMPAT_* (msed_set_compat)
     int cur = 0;
     int por_mode = 1;           // how the column kernel obtains porosity (see KParams::por_mode)
     std::vector<double> zi, zc, dz, dzc, bf, por_profile, cumdepth;
@@ -94,7 +101,8 @@ struct msed_handle {
     double *xstage = nullptr;                     // [20][ld] staging rows of msed_run_exchange when the staging buffer
                                                   // itself serves as third state buffer (chunk-major Run)
     int chunk_major = 1;                          // msed_run_exchange: whole coupling interval chunk by chunk
-    int pair_cooldown = 0;                        // steps to run singly after a rejection / failed pair
+    int pred_depth = 0;                           // how the next call's steps are predicted to go: every step at
+                                                  // dt/4^pred_depth (what the last completed step did); -1: no prediction
     long long pairs_committed = 0;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -141,6 +149,32 @@ int download_rows(msed_handle *h, double *dst, const double *src, size_t rows)
     return MSED_OK;
 }
 
+// hzg_omexdia_p namelist values (rates per day) -> what the kernels use (rates per second, folded constants)
+OmexDev omex_dev(const msed_config &c)
+{
+    OmexDev m;
+    m.rLabile = c.rLabile / 86400.0;
+    m.rSemilabile = c.rSemilabile / 86400.0;
+    m.NCrLdet = c.NCrLdet;
+    m.NCrSdet = c.NCrSdet;
+    m.PAds_rS = c.PAds * m.rSemilabile;
+    m.PAdsODU = c.PAdsODU;
+    m.rNH3Ads = 1.0 / (1.0 + c.NH3Ads);
+    m.CprodMax = c.CprodMax / 86400.0;
+    m.rnit = c.rnit / 86400.0;
+    m.ksO2nitri = c.ksO2nitri;
+    m.rODUox = c.rODUox / 86400.0;
+    m.ksO2oduox = c.ksO2oduox;
+    m.ksO2oxic = c.ksO2oxic;
+    m.ksNO3denit = c.ksNO3denit;
+    m.kinO2denit = c.kinO2denit;
+    m.kinNO3anox = c.kinNO3anox;
+    m.kinO2anox = c.kinO2anox;
+    m.E_a = 0.1 * std::log(1.5) * 288.15 * (288.15 + 10.0);
+    for (int n = 0; n < NV; ++n) m.minimum[n] = c.minimum[n];
+    return m;
+}
+
 void fill_params(const msed_handle *h, KParams &p)
 {
     std::memset(&p, 0, sizeof(p));
@@ -182,26 +216,7 @@ void fill_params(const msed_handle *h, KParams &p)
     p.poc_factor[0] = 1.0 / 1.2 * 12.01 / c.bioturb_dry_density / 1000.0;  // driver :383
     p.poc_factor[1] = 1.0 / 6.0 * 12.01 / c.bioturb_dry_density / 1000.0;  // driver :386
     p.cumdepth_last = h->cumdepth[h->K - 1];
-    OmexDev &m = p.om;
-    m.rLabile = c.rLabile / 86400.0;
-    m.rSemilabile = c.rSemilabile / 86400.0;
-    m.NCrLdet = c.NCrLdet;
-    m.NCrSdet = c.NCrSdet;
-    m.PAds_rS = c.PAds * m.rSemilabile;
-    m.PAdsODU = c.PAdsODU;
-    m.rNH3Ads = 1.0 / (1.0 + c.NH3Ads);
-    m.CprodMax = c.CprodMax / 86400.0;
-    m.rnit = c.rnit / 86400.0;
-    m.ksO2nitri = c.ksO2nitri;
-    m.rODUox = c.rODUox / 86400.0;
-    m.ksO2oduox = c.ksO2oduox;
-    m.ksO2oxic = c.ksO2oxic;
-    m.ksNO3denit = c.ksNO3denit;
-    m.kinO2denit = c.kinO2denit;
-    m.kinNO3anox = c.kinNO3anox;
-    m.kinO2anox = c.kinO2anox;
-    m.E_a = 0.1 * std::log(1.5) * 288.15 * (288.15 + 10.0);
-    for (int n = 0; n < NV; ++n) m.minimum[n] = c.minimum[n];
+    p.om = omex_dev(c);
     for (int k = 0; k < h->K; ++k) {
         p.dz[k] = h->dz[k];
         p.rdzc[k] = (k < h->K - 1) ? 1.0 / h->dzc[k] : 0.0;
@@ -213,50 +228,13 @@ void fill_params(const msed_handle *h, KParams &p)
     }
 }
 
-template <int MODEL, bool P3, bool SP>
-cudaError_t launch_op(int op, const KParams &p, cudaStream_t s)
-{
-    const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
-    switch (op) {
-#define MSED_CASE(OPV) \
-    case OPV: column_kernel<MODEL, OPV, P3, SP><<<grid, block, COLUMN_SMEM_BYTES, s>>>(p); break;
-        MSED_CASE(OP_RHS)
-        MSED_CASE(OP_EULER)
-        MSED_CASE(OP_ADAPTIVE)
-        MSED_CASE(OP_RK4_S1)
-        MSED_CASE(OP_RK4_S2)
-        MSED_CASE(OP_RK4_S3)
-        MSED_CASE(OP_RK4_S4)
-        MSED_CASE(OP_RK38_S1)
-        MSED_CASE(OP_RK38_S2)
-        MSED_CASE(OP_RK38_S3)
-        MSED_CASE(OP_RK38_S4)
-#undef MSED_CASE
-    default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
-}
-
 cudaError_t launch_column(const msed_handle *h, int op, const KParams &p)
 {
     // the (rare) Zhang & Wirtz path always streams the 3-D porosity field, which is kept current in
     // every mode; the closed-form porosity variants exist for the hot profile-0/1/2 kernels only
     const bool p3 = h->cfg.bioturbation_profile == 3;
     const bool sp = p3 || p.por_mode == 0;
-    switch (h->cfg.model) {
-    case MSED_MODEL_OMEXDIA_P:
-        if (p3) return launch_op<MSED_MODEL_OMEXDIA_P, true, true>(op, p, h->stream);
-        return sp ? launch_op<MSED_MODEL_OMEXDIA_P, false, true>(op, p, h->stream)
-                  : launch_op<MSED_MODEL_OMEXDIA_P, false, false>(op, p, h->stream);
-    case MSED_MODEL_NONE:
-        if (p3) return launch_op<MSED_MODEL_NONE, true, true>(op, p, h->stream);
-        return sp ? launch_op<MSED_MODEL_NONE, false, true>(op, p, h->stream)
-                  : launch_op<MSED_MODEL_NONE, false, false>(op, p, h->stream);
-    case MSED_MODEL_TEST_SOLVER:
-        if (op != OP_RHS && op != OP_EULER) return cudaErrorInvalidValue;
-        return launch_op<MSED_MODEL_TEST_SOLVER, false, true>(op, p, h->stream);
-    default: return cudaErrorInvalidValue;
-    }
+    return tu_launch_column(h->cfg.model, p3, sp, op, p, h->stream);
 }
 
 int ensure_aux(msed_handle *h, int count)
@@ -296,105 +274,38 @@ cudaError_t launch_pair(const msed_handle *h, int method, const KParams &pin)
         p.colmap = h->colmap;
         if (p.col_end <= p.col0) return cudaSuccess;  // all land: nothing to launch
     }
-    const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
-    const bool adaptive = method == MSED_ADAPTIVE_EULER;
-    const bool denit = p.denit_out != nullptr;  // the last pair of a call also stores the denit diagnostic
-#define MSED_PAIR_L(MODEL, AD, DN, CM, OV) pair_kernel<MODEL, AD, DN, CM, OV><<<grid, block, PAIR_SMEM_BYTES, h->stream>>>(p)
-#define MSED_PAIR(MODEL, AD, DN)                                                                       \
-    do {                                                                                               \
-        if (p.in_ovr) { if (p.colmap) MSED_PAIR_L(MODEL, AD, DN, true, true); else MSED_PAIR_L(MODEL, AD, DN, false, true); } \
-        else          { if (p.colmap) MSED_PAIR_L(MODEL, AD, DN, true, false); else MSED_PAIR_L(MODEL, AD, DN, false, false); } \
-    } while (0)
-#define MSED_PAIR_MODEL(MODEL)                                   \
-    do {                                                         \
-        if (adaptive) { if (denit) MSED_PAIR(MODEL, true, true); else MSED_PAIR(MODEL, true, false); }   \
-        else          { if (denit) MSED_PAIR(MODEL, false, true); else MSED_PAIR(MODEL, false, false); } \
-    } while (0)
-    if (h->cfg.model == MSED_MODEL_OMEXDIA_P) MSED_PAIR_MODEL(MSED_MODEL_OMEXDIA_P);
-    else MSED_PAIR_MODEL(MSED_MODEL_NONE);
-#undef MSED_PAIR_MODEL
-#undef MSED_PAIR
-#undef MSED_PAIR_L
-    return cudaGetLastError();
+    return tu_launch_pair(h->cfg.model, method == MSED_ADAPTIVE_EULER, p, h->stream);
 }
 
-// one launch = m chained Euler / adaptive-Euler steps, warp per column (msed_chain.cuh)
+// one launch = m ode_solver calls, warp per column (msed_chain.cuh)
 cudaError_t launch_chain(const msed_handle *h, int method, const KParams &p, int m, bool clip)
 {
-    const dim3 grid(nblocks(p.col_end - p.col0, CHAIN_WARPS)), block(CHAIN_BLOCK);
-    const bool adaptive = method == MSED_ADAPTIVE_EULER;
-#define MSED_CHAIN(MODEL, AD, CL) chain_kernel<MODEL, AD, CL><<<grid, block, 0, h->stream>>>(p, m)
-#define MSED_CHAIN_MODEL(MODEL)                                                                        \
-    do {                                                                                               \
-        if (adaptive) { if (clip) MSED_CHAIN(MODEL, true, true); else MSED_CHAIN(MODEL, true, false); }   \
-        else          { if (clip) MSED_CHAIN(MODEL, false, true); else MSED_CHAIN(MODEL, false, false); } \
-    } while (0)
-    if (h->cfg.model == MSED_MODEL_OMEXDIA_P) MSED_CHAIN_MODEL(MSED_MODEL_OMEXDIA_P);
-    else MSED_CHAIN_MODEL(MSED_MODEL_NONE);
-#undef MSED_CHAIN_MODEL
-#undef MSED_CHAIN
-    return cudaGetLastError();
+    return tu_launch_chain(h->cfg.model, method == MSED_ADAPTIVE_EULER, clip, p, m, h->stream);
 }
 
 // one launch = two chained Runge-Kutta stages (msed_rkpair.cuh); which = 0 for stages 1+2, 1 for 3+4
 cudaError_t launch_rk_pair(const msed_handle *h, int method, int which, const KParams &p)
 {
-    const dim3 grid(nblocks(p.col_end - p.col0, COL_BLOCK)), block(COL_BLOCK);
-    const int pair = (method == MSED_RUNGE_KUTTA_4 ? RK4_12 : RK38_12) + which;
-#define MSED_RKP(MODEL, PAIR) \
-    case PAIR: rk_pair_kernel<MODEL, PAIR><<<grid, block, rk_pair_smem(PAIR), h->stream>>>(p); break;
-    if (h->cfg.model == MSED_MODEL_OMEXDIA_P) {
-        switch (pair) {
-            MSED_RKP(MSED_MODEL_OMEXDIA_P, RK4_12) MSED_RKP(MSED_MODEL_OMEXDIA_P, RK4_34)
-            MSED_RKP(MSED_MODEL_OMEXDIA_P, RK38_12) MSED_RKP(MSED_MODEL_OMEXDIA_P, RK38_34)
-        }
-    } else {
-        switch (pair) {
-            MSED_RKP(MSED_MODEL_NONE, RK4_12) MSED_RKP(MSED_MODEL_NONE, RK4_34)
-            MSED_RKP(MSED_MODEL_NONE, RK38_12) MSED_RKP(MSED_MODEL_NONE, RK38_34)
-        }
-    }
-#undef MSED_RKP
-    return cudaGetLastError();
+    return tu_launch_rk_pair(h->cfg.model, method, which, p, h->stream);
 }
 
 cudaError_t enable_pair_smem()
 {
-    cudaError_t e;
-    const int bytes = (int)PAIR_SMEM_BYTES;
-#define MSED_RKP_ATTR(MODEL, PAIR) \
-    if ((e = cudaFuncSetAttribute(rk_pair_kernel<MODEL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)rk_pair_smem(PAIR))) != cudaSuccess) return e;
-    MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK4_12) MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK4_34)
-    MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK38_12) MSED_RKP_ATTR(MSED_MODEL_OMEXDIA_P, RK38_34)
-    MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK4_34)
-    MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_12) MSED_RKP_ATTR(MSED_MODEL_NONE, RK38_34)
-#undef MSED_RKP_ATTR
-#define MSED_PAIR_ATTR1(MODEL, AD, DN, CM, OV) \
-    if ((e = cudaFuncSetAttribute(pair_kernel<MODEL, AD, DN, CM, OV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  bytes)) != cudaSuccess) return e;
-#define MSED_PAIR_ATTR(MODEL, AD, DN) \
-    MSED_PAIR_ATTR1(MODEL, AD, DN, false, false) MSED_PAIR_ATTR1(MODEL, AD, DN, true, false) \
-    MSED_PAIR_ATTR1(MODEL, AD, DN, false, true) MSED_PAIR_ATTR1(MODEL, AD, DN, true, true)
-    MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, true, true) MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, true, false)
-    MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, false, true) MSED_PAIR_ATTR(MSED_MODEL_OMEXDIA_P, false, false)
-    MSED_PAIR_ATTR(MSED_MODEL_NONE, true, true) MSED_PAIR_ATTR(MSED_MODEL_NONE, true, false)
-    MSED_PAIR_ATTR(MSED_MODEL_NONE, false, true) MSED_PAIR_ATTR(MSED_MODEL_NONE, false, false)
-#undef MSED_PAIR_ATTR
-#undef MSED_PAIR_ATTR1
-    return cudaSuccess;
+    cudaError_t e = tu_enable_pair_smem();
+    return e != cudaSuccess ? e : tu_enable_rk_smem();
 }
 
-int reduce_flags(msed_handle *h)
+// nflags: 4 (violation / NaN of up to two stages) or, for a group that plans rejections, all of Ctl::flags
+int reduce_flags(msed_handle *h, int nflags = 4)
 {
     if (h->hook) {
         void *flags = (void *)((char *)h->ctl + offsetof(Ctl, flags));
-        if (h->hook(h->hook_user, flags, 4, (void *)h->stream) != 0)
+        if (h->hook(h->hook_user, flags, nflags, (void *)h->stream) != 0)
             return fail(h, MSED_ERR_NCCL, "allreduce hook failed");
     } else if (h->comm) {
         NcclApi &api = nccl_api();
         int *flags = (int *)((char *)h->ctl + offsetof(Ctl, flags));
-        int rc = api.AllReduce(flags, flags, 4, kNcclInt32, kNcclMax, h->comm, h->stream);
+        int rc = api.AllReduce(flags, flags, (size_t)nflags, kNcclInt32, kNcclMax, h->comm, h->stream);
         if (rc != 0)
             return fail(h, MSED_ERR_NCCL, std::string("ncclAllReduce: ") +
                                               (api.GetErrorString ? api.GetErrorString(rc) : "error"));
@@ -415,6 +326,38 @@ struct ExchangePlan {
     bool export_done = false;  // out: host_out holds the final upward fluxes
     bool stage_private = false;  // the staging rows are not in h->scratch, which may then hold a state
 };
+
+// One fused launch of a call's plan: a pair (two accepted sub-steps), or a chain of m ode_solver calls
+struct FusedLaunch {
+    int kind = PAIR_FULL;   // PairKind; chains ignore it
+    int m = 0;              // chain: ode_solver calls in the launch
+    int step = 0;           // index (within the call) of the ode_solver call the launch starts in
+    PlanCommit pc;          // what committing this launch alone does to the control block
+};
+
+// The plan of a call: every one of its nsteps ode_solver calls is predicted to run at dt/4^depth -- the way
+// the last completed call went (Ctl::last_depth; sub-cycling comes in episodes of many consecutive steps) --
+// i.e. as the reference's attempt sequence  dt (rejected) .. dt/4^(depth-1) (rejected), then 4^depth accepted
+// sub-steps of dt_acc = dt/4^depth (solver_library.F90:104-140).  Returns false if that sequence cannot be
+// planned: a step size that must be rejected is not rejectable (:126), or the sub-steps do not add up to dt in
+// the reference's own floating-point loop (:108,:138).
+bool plan_depth(double dt, double dt_min, int depth, double &dt_acc, long long &nq)
+{
+    if (depth < 0 || depth > MAX_PLAN_DEPTH) return false;
+    double dq = dt;
+    for (int l = 0; l < depth; ++l) {
+        if (!(dq > dt_min)) return false;   // a violation at dq would be accepted as it is
+        dq *= 0.25;                          // :127
+    }
+    nq = 1LL << (2 * depth);
+    double di = 0.0;
+    for (long long i = 1; i <= nq; ++i) {
+        di = di + dq;                        // :138
+        if ((i < nq) != (di < dt)) return false;
+    }
+    dt_acc = dq;
+    return true;
+}
 
 // the step loop shared by msed_ode_solver / msed_step / msed_run / msed_run_exchange
 int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrapper, msed_step_info *info,
@@ -444,6 +387,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     c.cur = h->cur;
     c.do_clip = (wrapper && !diag) ? 1 : 0;
     c.diagnostics = diag ? 1 : 0;
+    c.last_depth = h->pred_depth < 0 ? 0 : h->pred_depth;
     *h->ctl_host = c;
     CUDA_TRY(h, cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
 
@@ -475,7 +419,8 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         return MSED_OK;
     };
 
-    // ---- fused pairs of steps first (msed_pair.cuh): speculative, nothing is committed on failure --
+    // ---- the fused part of the call (msed_pair.cuh, msed_chain.cuh): speculative, nothing is committed on
+    // ---- failure ---------------------------------------------------------------------------------------
     const bool single_attempt = (method == MSED_EULER || method == MSED_ADAPTIVE_EULER);
     // the configurations the fused kernels cover (msed_pair.cuh, msed_rkpair.cuh); the rest takes
     // one launch per attempt / per stage
@@ -483,34 +428,103 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                          (h->cfg.model == MSED_MODEL_OMEXDIA_P || h->cfg.model == MSED_MODEL_NONE) &&
                          h->cfg.bioturbation_profile != 3 && !h->cfg.distributed_pom_flux && h->por_mode != 0;
     const bool rk_fused = fusable && !single_attempt;
-    long long npairs = 0;       // fused launches planned (pairs or chains)
-    long long fused_planned = 0;  // ... and the steps they hold
-    bool last_is_pair = false;  // the call ends with a fused launch, which then leaves the "state of
-                                // the last get_rhs call" diagnostic behind (KParams::denit_out)
     h->denit_valid = false;
-    // chains (msed_chain.cuh) cover every step of the call, whatever its parity
     // both fused kernels only work on wet columns, so the tile size that decides between them counts those
     const long long work_cols = h->colmap ? (long long)h->wet_idx.size() : (long long)h->ncol;
-    const bool chain_fit = h->K <= CHAIN_MAX_LAYERS &&
+    const bool chain_fit = h->K <= TU_CHAIN_MAX_LAYERS &&
                            (h->step_fusion == 3 ||
                             (h->step_fusion == 1 && !collective && work_cols <= h->chain_max_cols));
     // (with a collective every rank has to take the same decision, and the tile size is a per-rank fact:
     //  auto mode then stays with pairs; mode 3, set on every rank, selects chains)
-    const bool use_chain = fusable && chain_fit && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 1;
-    int chain_base = 0, chain_extra = 0;
+
+    // the plan: how the steps of this call are predicted to go (see plan_depth)
+    int depth = (method == MSED_ADAPTIVE_EULER) ? h->pred_depth : 0;
+    double dt_acc = dt;
+    long long nq = 1;
+    bool planned = fusable && single_attempt && !diag && nsteps >= 1 && plan_depth(dt, h->cfg.dt_min, depth, dt_acc, nq);
+    const bool use_chain = planned && chain_fit;
+    const int own_rejectable = (method == MSED_ADAPTIVE_EULER && dt_acc > h->cfg.dt_min) ? 1 : 0;
+    std::vector<FusedLaunch> fl;
+    long long fused_planned = 0;  // steps the fused launches hold
+    auto base_commit = [&](long long gate) {
+        PlanCommit pc;
+        std::memset(&pc, 0, sizeof(pc));
+        pc.gate_steps = gate;
+        pc.own_rejectable = own_rejectable;
+        pc.flip = 1;
+        pc.launches = 1;
+        pc.depth = depth;
+        pc.dt_int = 0.0;
+        pc.dt_red = dt;
+        return pc;
+    };
     if (use_chain) {
-        npairs = (nsteps + MSED_CHAIN_MAX_STEPS - 1) / MSED_CHAIN_MAX_STEPS;
-        chain_base = (int)(nsteps / npairs);     // the first chain_extra chains hold one step more
-        chain_extra = (int)(nsteps % npairs);
+        // chains cover every step of the call, whatever its parity; a launch holds at most
+        // TU_CHAIN_MAX_STEPS accepted sub-steps
+        const long long per = std::max<long long>(1, TU_CHAIN_MAX_STEPS / nq);
+        const long long nl = (nsteps + per - 1) / per;
+        const long long base = nsteps / nl, extra = nsteps % nl;   // the first `extra` chains hold one step more
+        long long gate = 0;
+        for (long long q = 0; q < nl; ++q) {
+            FusedLaunch f;
+            f.m = (int)(base + (q < extra ? 1 : 0));
+            f.step = (int)gate;
+            f.pc = base_commit(gate);
+            f.pc.steps = f.m;
+            f.pc.rhs_evals = f.m * (nq + depth);
+            f.pc.subcycles = (long long)f.m * depth;
+            f.pc.up_slots = f.m * depth;
+            fl.push_back(f);
+            gate += f.m;
+        }
         fused_planned = nsteps;
-        last_is_pair = true;
-        if ((rc = ensure_denit(h))) return rc;
-    } else if (fusable && h->pair_cooldown <= 0 && single_attempt && !diag && nsteps >= 2) {
-        npairs = nsteps / 2;
-        fused_planned = 2 * npairs;
-        last_is_pair = (2 * npairs == nsteps);
-        if (last_is_pair && (rc = ensure_denit(h))) return rc;
+    } else if (planned && depth == 0 && nsteps >= 2) {
+        for (long long q = 0; q < nsteps / 2; ++q) {
+            FusedLaunch f;
+            f.kind = PAIR_FULL;
+            f.step = (int)(2 * q);
+            f.pc = base_commit(2 * q);
+            f.pc.steps = 2;
+            f.pc.rhs_evals = 2;
+            fl.push_back(f);
+        }
+        fused_planned = 2 * (nsteps / 2);
+    } else if (planned && depth > 0) {
+        // every step: the pair that holds the planned rejections and the first two sub-steps, inner pairs,
+        // the pair that ends the call (4^depth sub-steps = 4^depth/2 pairs)
+        for (long long st = 0; st < nsteps; ++st) {
+            double di = 0.0;
+            for (long long j = 0; j < nq / 2; ++j) {
+                FusedLaunch f;
+                f.kind = (j == 0) ? PAIR_FIRST : (j == nq / 2 - 1 ? PAIR_LAST : PAIR_MID);
+                f.step = (int)st;
+                f.pc = base_commit(st);
+                di = di + dt_acc;            // :138, twice
+                di = di + dt_acc;
+                f.pc.rhs_evals = 2 + (j == 0 ? depth : 0);
+                f.pc.subcycles = (j == 0) ? depth : 0;
+                f.pc.up_slots = (j == 0) ? depth : 0;
+                if (f.kind == PAIR_LAST) {
+                    f.pc.steps = 1;
+                } else {
+                    f.pc.dt_int = di;
+                    f.pc.dt_red = dt_acc;
+                }
+                fl.push_back(f);
+            }
+        }
+        fused_planned = nsteps;
+    } else {
+        planned = false;
     }
+    const long long nfl = (long long)fl.size();
+    // the call ends with a fused launch, which then leaves the "state of the last get_rhs call" diagnostic
+    // behind (KParams::denit_out)
+    const bool last_is_fused = nfl > 0 && fused_planned == nsteps;
+    if (last_is_fused && (rc = ensure_denit(h))) return rc;
+    p.dt_acc = dt_acc;
+    p.depth = depth;
+
     // export of one chunk of msed_run_exchange while the next chunks are still being computed
     auto export_chunk = [&](int c) -> int {
         const int c0 = plan->c0[c], c1 = plan->c1[c];
@@ -533,20 +547,23 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     // seen the flags of every pair of every chunk, so a rejected step anywhere still costs nothing but the redo.
     const int cur_before = h->cur;
     const bool seq_mode = plan && plan->stage_private && plan->first && plan->last && first_pending && !use_chain &&
-                          npairs >= 2 && fused_planned == nsteps && h->scratch != nullptr;
+                          nfl >= 2 && last_is_fused && h->scratch != nullptr && nsteps * depth <= MAX_UP_SLOTS;
     if (seq_mode) {
         double *A = h->buf[cur_before], *B = h->buf[1 - cur_before], *S = h->scratch;
         for (int c = 0; c < plan->nchunks; ++c) {
             if ((rc = boundary_chunk(c))) return rc;
             const double *in = A;
-            for (long long q = 0; q < npairs; ++q) {
+            for (long long q = 0; q < nfl; ++q) {
                 double *out = (q % 2 == 0) ? B : S;
                 KParams pc = p;
                 pc.col0 = plan->c0[c];
                 pc.col_end = plan->c1[c];
                 pc.in_ovr = in;
                 pc.out_ovr = out;
-                if (q == npairs - 1) pc.denit_out = h->denit;
+                pc.pair_kind = fl[q].kind;
+                pc.gate_steps = 0;                       // nothing is committed before the whole interval
+                pc.up_slot = fl[q].step * depth;
+                if (q == nfl - 1) pc.denit_out = h->denit;
                 CUDA_TRY(h, launch_pair(h, method, pc));
                 launches += 1;
                 in = out;
@@ -555,17 +572,26 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         }
         first_pending = false;
         if (collective)
-            if ((rc = reduce_flags(h))) return rc;
-        // commits all pairs at once (or none): same gate and bookkeeping as a chain of nsteps steps
-        chain_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method, (int)nsteps);
+            if ((rc = reduce_flags(h, depth > 0 ? MSED_NFLAGS : 4))) return rc;
+        // commits all pairs at once (or none)
+        PlanCommit pc = base_commit(0);
+        pc.steps = nsteps;
+        pc.rhs_evals = nsteps * (nq + depth);
+        pc.subcycles = nsteps * depth;
+        pc.up_slots = (int)(nsteps * depth);
+        pc.launches = (int)nfl;
+        plan_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, pc);
         launches += 1;
     }
-    for (long long q = 0; q < (seq_mode ? 0 : npairs); ++q) {
-        const bool last_pair = last_is_pair && q == npairs - 1;
-        const int m = use_chain ? chain_base + (q < chain_extra ? 1 : 0) : 2;  // steps in this launch
-        const bool chunk_last = last_pair && plan && plan->last;
+    for (long long q = 0; q < (seq_mode ? 0 : nfl); ++q) {
+        const bool last_launch = last_is_fused && q == nfl - 1;
+        const bool chunk_last = last_launch && plan && plan->last;
         KParams pq = p;
-        if (last_pair) pq.denit_out = h->denit;
+        pq.pair_kind = fl[q].kind;
+        pq.gate_steps = fl[q].pc.gate_steps;
+        pq.up_slot = 0;                                  // every launch is committed on its own: slots start at 0
+        if (last_launch) pq.denit_out = h->denit;
+        const int m = fl[q].m;
         if (first_pending || chunk_last) {
             for (int c = 0; c < plan->nchunks; ++c) {
                 if (first_pending)
@@ -584,9 +610,8 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
             launches += 1;
         }
         if (collective)
-            if ((rc = reduce_flags(h))) return rc;
-        if (use_chain) chain_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method, m);
-        else pair_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, method);
+            if ((rc = reduce_flags(h, fl[q].pc.up_slots > 0 ? MSED_NFLAGS : 4))) return rc;
+        plan_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, fl[q].pc);
         launches += 1;
     }
     const long long singles_planned = nsteps - fused_planned;
@@ -595,12 +620,15 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     long long remaining = singles_planned, issued = 0;
     const long long max_batch = 256;
     int guard = 0;
-    // with nothing but pairs planned the controller still has to be asked whether all of them were
-    // committed; a failed pair leaves its steps to the single-step loop
-    bool check_pairs = (singles_planned == 0 && npairs > 0);
-    while (remaining > 0 || check_pairs) {
-        check_pairs = false;
-        const long long batch = remaining < max_batch ? remaining : max_batch;
+    // with nothing but fused launches planned the controller still has to be asked whether all of them were
+    // committed; a failed group leaves its steps to the single-attempt loop
+    bool check_fused = (singles_planned == 0 && nfl > 0);
+    // attempts a step is expected to need (sub-cycling: rejected + accepted ones); launches past the end of the
+    // call return at once, so a generous estimate only costs empty launches
+    long long per_step = 1;
+    while (remaining > 0 || check_fused) {
+        check_fused = false;
+        const long long batch = std::min(remaining * per_step, max_batch);
         for (long long s = 0; s < batch; ++s, ++issued) {
             const bool chunk_first = first_pending && issued == 0;
             const bool chunk_last = plan && plan->last && issued == singles_planned - 1;
@@ -653,7 +681,12 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         if (h->ctl_host->stop) break;
         remaining = nsteps - h->ctl_host->steps_done;
-        // sub-cycling needs more attempts than steps: keep going until the controller reports done
+        // sub-cycling needs more attempts than steps: keep going until the controller reports done, and size
+        // the next batch by what the steps have needed so far
+        if (method == MSED_ADAPTIVE_EULER && remaining > 0) {   // (identical on every rank: the flags are reduced)
+            const long long d = h->ctl_host->steps_done > 0 ? h->ctl_host->last_depth : h->ctl_host->step_rej_first;
+            per_step = std::max<long long>(per_step, std::min<long long>(d + (1LL << (2 * std::min<long long>(d, 3))), 70));
+        }
         if (++guard > 1000000) return fail(h, MSED_ERR_STATE, "step loop did not terminate");
     }
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
@@ -667,20 +700,21 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     }
 
     const Ctl &r = *h->ctl_host;
-    if (plan && plan->last) {  // the chunked export is final only if no attempt was rejected
+    const bool fused_ok = nfl > 0 && r.pair_failures == 0;
+    if (plan && plan->last) {  // the chunked export is final only if every attempt went as planned
         CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
-        plan->export_done = single_attempt && !r.stop && r.subcycles == 0 && r.pair_failures == 0 &&
-                            r.steps_done == nsteps && nsteps > 0;
+        // ... i.e. the launch the export rode on produced the final state: the last fused launch of a committed
+        // plan, or the single attempt planned behind it if that was accepted at once
+        plan->export_done = single_attempt && !r.stop && r.steps_done == nsteps && nsteps > 0 && r.pair_failures == 0 &&
+                            (last_is_fused || r.subcycles == fused_planned * depth);
     }
-    // fused pairs only pay off while steps are accepted first time: after a rejection or a failed
-    // pair run single steps for a while (sub-cycling comes in long episodes)
-    if (r.subcycles > 0 || r.pair_failures > 0) h->pair_cooldown = 64;
-    else if (h->pair_cooldown > 0) h->pair_cooldown -= (int)std::min<long long>(nsteps, h->pair_cooldown);
-    h->pairs_committed += (npairs > 0 && r.pair_failures == 0) ? npairs : 0;
-    h->denit_valid = last_is_pair && r.pair_failures == 0 && !r.stop && r.steps_done == nsteps;
+    // the next call is planned the way this call's last step went
+    if (r.steps_done > 0 && method == MSED_ADAPTIVE_EULER) h->pred_depth = r.last_irregular ? -1 : r.last_depth;
+    h->pairs_committed += fused_ok ? nfl : 0;
+    h->denit_valid = last_is_fused && fused_ok && !r.stop && r.steps_done == nsteps;
     // a committed chunk-major sequence with an even number of pairs ends in the staging buffer: it becomes
     // the state buffer the controller's flipped `cur` points at, the intermediate buffer becomes staging
-    if (seq_mode && r.pair_failures == 0 && !r.stop && r.steps_done == nsteps && npairs % 2 == 0) {
+    if (seq_mode && fused_ok && !r.stop && r.steps_done == nsteps && nfl % 2 == 0) {
         std::swap(h->buf[1 - cur_before], h->scratch);
         // the stepping kernels never write land columns, so the buffer rotated in holds whatever last used the
         // staging area there: restore conc = missing_value (driver :464) before anything can read it
@@ -693,12 +727,45 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     }
     h->cur = r.cur;
     if (diag && r.last_min_dt < h->last_min_dt) {
-        long long idx = -1;
-        CUDA_TRY(h, cudaMemcpy(&idx, h->minloc_idx, sizeof(idx), cudaMemcpyDeviceToHost));
-        if (idx >= 0) {  // rows are (n*K+k), columns i + inum*j -> Fortran (i,j,k,n), 1-based
-            const long long row = idx / h->ncol, col = idx % h->ncol;
-            h->last_min_dt_grid_cell[0] = (int)(col % h->cfg.inum) + 1;
-            h->last_min_dt_grid_cell[1] = (int)(col / h->cfg.inum) + 1;
+        // rows are (n*K+k), columns i + inum*j -> Fortran (i,j,k,n), 1-based, in the GLOBAL grid (the tile's
+        // origin is cfg.i_offset, cfg.j_offset)
+        long long row = -1, gi = 0, gj = 0;
+        if (h->comm) {
+            // one domain cut into tiles: the minloc of :133 is over all of them.  The condition above is the
+            // same on every tile (dt_red and last_min_dt are global), so all tiles reach these reductions.
+            // Index = row*2^40 + global column: Fortran array order of the global array for j-slab tiles.
+            NcclApi &api = nccl_api();
+            double *dval = h->red, *dmin = h->red + 1;
+            long long *didx = reinterpret_cast<long long *>(h->red + 2);
+            const long long stride = 1LL << 40;
+            minloc_pack_kernel<<<1, 1, 0, h->stream>>>(dval, didx, h->minloc_val, h->minloc_idx, h->ncol, stride,
+                                                        (long long)h->cfg.j_offset * h->cfg.inum + h->cfg.i_offset);
+            int nrc = api.AllReduce(dval, dmin, 1, kNcclFloat64, kNcclMin, h->comm, h->stream);
+            minloc_select_kernel<<<1, 1, 0, h->stream>>>(didx, dval, dmin);
+            if (nrc == 0) nrc = api.AllReduce(didx, didx, 1, kNcclInt64, kNcclMin, h->comm, h->stream);
+            if (nrc != 0) return fail(h, MSED_ERR_NCCL, "ncclAllReduce (minloc) failed");
+            long long g = -1;
+            CUDA_TRY(h, cudaMemcpyAsync(&g, didx, sizeof(g), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            if (g != 0x7fffffffffffffffLL && g >= 0) {
+                row = g / stride;
+                const long long gcol = g % stride;
+                gi = gcol % h->cfg.inum;
+                gj = gcol / h->cfg.inum;
+            }
+        } else {
+            long long idx = -1;
+            CUDA_TRY(h, cudaMemcpy(&idx, h->minloc_idx, sizeof(idx), cudaMemcpyDeviceToHost));
+            if (idx >= 0) {
+                row = idx / h->ncol;
+                const long long col = idx % h->ncol;
+                gi = col % h->cfg.inum + h->cfg.i_offset;
+                gj = col / h->cfg.inum + h->cfg.j_offset;
+            }
+        }
+        if (row >= 0) {
+            h->last_min_dt_grid_cell[0] = (int)gi + 1;
+            h->last_min_dt_grid_cell[1] = (int)gj + 1;
             h->last_min_dt_grid_cell[2] = (int)(row % h->K) + 1;
             h->last_min_dt_grid_cell[3] = (int)(row / h->K) + 1;
         }
@@ -713,9 +780,9 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         info->nan_detected = r.nan_detected;
         info->kernel_ms = ms;
         info->kernel_launches = launches;
-        info->fused_pairs = (npairs > 0 && r.pair_failures == 0) ? npairs : 0;
-        info->fused_steps = (npairs > 0 && r.pair_failures == 0) ? fused_planned : 0;
-        info->fused_ms = npairs > 0 ? ms_pairs : 0.0;
+        info->fused_pairs = r.fused_launches;
+        info->fused_steps = r.fused_steps;
+        info->fused_ms = nfl > 0 ? ms_pairs : 0.0;
     }
     return r.nan_detected ? MSED_NAN_DETECTED : MSED_OK;
 }
@@ -880,6 +947,7 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     CREATE_TRY(cudaMalloc(&h->ctl, sizeof(Ctl)));
     CREATE_TRY(cudaMalloc(&h->minloc_val, sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->minloc_idx, sizeof(long long)));
+    CREATE_TRY(cudaMalloc(&h->red, 32 * sizeof(double)));
     CREATE_TRY(cudaMallocHost(&h->ctl_host, sizeof(Ctl)));
     CREATE_TRY(cudaMemsetAsync(h->buf[0], 0, state_bytes, h->stream));  // conc = 0.0_rk, component :531
     CREATE_TRY(cudaMemsetAsync(h->buf[1], 0, state_bytes, h->stream));
@@ -910,7 +978,7 @@ int msed_destroy(msed_handle *h)
     cudaFree(h->buf[0]); cudaFree(h->buf[1]); cudaFree(h->aux[0]); cudaFree(h->aux[1]);
     cudaFree(h->por); cudaFree(h->bdys); cudaFree(h->fluxes); cudaFree(h->par_surface);
     cudaFree(h->scratch); cudaFree(h->denit); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->colmap); cudaFree(h->xstage); cudaFree(h->ctl);
-    cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->pel);
+    cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->red); cudaFree(h->pel);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1279,7 +1347,7 @@ int msed_set_step_fusion(msed_handle *h, int enable)
     if (!h) return MSED_ERR_ARG;
     if (enable < 0 || enable > 3) return fail(h, MSED_ERR_ARG, "step fusion mode must be 0..3");
     h->step_fusion = enable;
-    h->pair_cooldown = 0;
+    h->pred_depth = 0;
     return MSED_OK;
 }
 
@@ -1440,6 +1508,130 @@ int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const doubl
     return rc;
 }
 
+namespace {
+void apply_member(msed_config &c, const msed_spinup_member &m)
+{
+    c.rLabile = m.rLabile; c.rSemilabile = m.rSemilabile; c.NCrLdet = m.NCrLdet; c.NCrSdet = m.NCrSdet;
+    c.PAds = m.PAds; c.PAdsODU = m.PAdsODU; c.NH3Ads = m.NH3Ads; c.CprodMax = m.CprodMax; c.rnit = m.rnit;
+    c.ksO2nitri = m.ksO2nitri; c.rODUox = m.rODUox; c.ksO2oduox = m.ksO2oduox; c.ksO2oxic = m.ksO2oxic;
+    c.ksNO3denit = m.ksNO3denit; c.kinO2denit = m.kinO2denit; c.kinNO3anox = m.kinNO3anox; c.kinO2anox = m.kinO2anox;
+    for (int n = 0; n < NV; ++n) c.initial_value[n] = m.initial_value[n];
+}
+}  // namespace
+
+int msed_spinup_batch(const msed_config *cfg, int32_t nmembers, const msed_spinup_member *members,
+                      const double *bdys1d, const double *fluxes1d, int64_t nsteps, int method, double *conc1d,
+                      msed_step_info *info)
+{
+    if (!cfg || !bdys1d || !fluxes1d || !conc1d || nmembers < 1 || nsteps < 0)
+        return fail(nullptr, MSED_ERR_ARG, "bad arguments");
+    if (method < 0 || method > 3) return fail(nullptr, MSED_ERR_ARG, "unknown ode_method");
+    const int K = cfg->knum;
+    const size_t P = (size_t)nmembers;
+    // configurations outside the batch kernel's scope: member by member through msed_spinup_column
+    if (K > TU_CHAIN_MAX_LAYERS || cfg->distributed_pom_flux || cfg->model == MSED_MODEL_TEST_SOLVER) {
+        std::vector<double> bd(NV + 1), fl(NV), col((size_t)NV * K);
+        for (size_t m = 0; m < P; ++m) {
+            msed_config cm = *cfg;
+            if (members) apply_member(cm, members[m]);
+            for (int n = 0; n <= NV; ++n) bd[n] = bdys1d[m + P * n];
+            for (int n = 0; n < NV; ++n) fl[n] = fluxes1d[m + P * n];
+            const int rc = msed_spinup_column(&cm, bd.data(), fl.data(), nsteps, method, col.data(), info ? &info[m] : nullptr);
+            if (rc) return rc;
+            for (size_t q = 0; q < (size_t)NV * K; ++q) conc1d[m + P * q] = col[q];
+        }
+        return MSED_OK;
+    }
+    // sed1d: 1x1xknum clones with Dirichlet boundaries, constant bioturbation and solver diagnostics
+    // (component :557-611), laid out as one nmembers x 1 tile
+    msed_config c1 = *cfg;
+    c1.inum = nmembers;
+    c1.jnum = 1;
+    c1.i_offset = c1.j_offset = 0;
+    c1.bcup_dissolved_variables = 2;
+    c1.adaptive_solver_diagnostics = 1;
+    msed_handle *h = nullptr;
+    int rc = msed_create(&c1, &h);
+    if (rc) return rc;
+    h->cfg.bioturbation_profile = (c1.bioturbation_profile == 3) ? 0 : c1.bioturbation_profile;   // :611
+    OmexDev *d_om = nullptr;
+    double *d_lmd = nullptr;
+    int *d_cell = nullptr;
+    long long *d_cnt = nullptr;
+    auto cleanup = [&](int code) {
+        if (code) g_err = h->err.empty() ? g_err : h->err;
+        cudaFree(d_om); cudaFree(d_lmd); cudaFree(d_cell); cudaFree(d_cnt);
+        msed_destroy(h);
+        return code;
+    };
+#define BATCH_TRY(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess) return cleanup(fail(h, MSED_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(e_))); \
+    } while (0)
+    if ((rc = msed_check_domain(h)) || (rc = msed_init_concentrations(h)) || (rc = msed_set_boundary(h, bdys1d, fluxes1d)))
+        return cleanup(rc);
+    if (members) {   // per-member reaction parameters and initial values (init_concentrations, driver :456)
+        std::vector<OmexDev> om(P);
+        std::vector<double> conc((size_t)NV * K * P);
+        for (size_t m = 0; m < P; ++m) {
+            msed_config cm = *cfg;
+            apply_member(cm, members[m]);
+            om[m] = omex_dev(cm);
+            for (int n = 0; n < NV; ++n)
+                for (int k = 0; k < K; ++k) conc[m + P * (k + (size_t)K * n)] = cm.initial_value[n] / h->por_profile[k];
+        }
+        BATCH_TRY(cudaMalloc(&d_om, P * sizeof(OmexDev)));
+        BATCH_TRY(cudaMemcpy(d_om, om.data(), P * sizeof(OmexDev), cudaMemcpyHostToDevice));
+        if ((rc = msed_set_state(h, conc.data()))) return cleanup(rc);
+    }
+    BATCH_TRY(cudaMalloc(&d_lmd, P * sizeof(double)));
+    BATCH_TRY(cudaMalloc(&d_cell, 4 * P * sizeof(int)));
+    BATCH_TRY(cudaMalloc(&d_cnt, 2 * P * sizeof(long long)));
+    KParams p;
+    fill_params(h, p);
+    p.use_ctl = 0;
+    p.buf[0] = h->buf[h->cur];
+    p.buf[1] = h->buf[1 - h->cur];
+    SpinupArgs a;
+    a.om = d_om;
+    a.last_min_dt = d_lmd;
+    a.grid_cell = d_cell;
+    a.counters = d_cnt;
+    a.nsteps = nsteps;
+    a.dt = 3600.0;                        // dt_spinup, :574
+    a.dt_min = h->cfg.dt_min;
+    a.last_min_dt0 = (double)1.e20f;      // solver_library.F90:44
+    a.method = method;
+    BATCH_TRY(cudaEventRecord(h->ev0, h->stream));
+    BATCH_TRY(tu_launch_spinup(h->cfg.model, p, a, h->stream));
+    BATCH_TRY(cudaEventRecord(h->ev1, h->stream));
+    BATCH_TRY(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    BATCH_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if ((rc = msed_get_state(h, conc1d))) return cleanup(rc);
+    if (info) {
+        std::vector<double> lmd(P);
+        std::vector<int> cell(4 * P);
+        std::vector<long long> cnt(2 * P);
+        BATCH_TRY(cudaMemcpy(lmd.data(), d_lmd, P * sizeof(double), cudaMemcpyDeviceToHost));
+        BATCH_TRY(cudaMemcpy(cell.data(), d_cell, 4 * P * sizeof(int), cudaMemcpyDeviceToHost));
+        BATCH_TRY(cudaMemcpy(cnt.data(), d_cnt, 2 * P * sizeof(long long), cudaMemcpyDeviceToHost));
+        for (size_t m = 0; m < P; ++m) {
+            std::memset(&info[m], 0, sizeof(msed_step_info));
+            info[m].steps_done = nsteps;
+            info[m].rhs_evaluations = cnt[2 * m];
+            info[m].subcycle_warnings = cnt[2 * m + 1];
+            info[m].last_min_dt = lmd[m];
+            for (int q = 0; q < 4; ++q) info[m].last_min_dt_grid_cell[q] = cell[4 * m + q];
+            info[m].kernel_ms = ms;
+            info[m].kernel_launches = 1;
+        }
+    }
+#undef BATCH_TRY
+    return cleanup(MSED_OK);
+}
+
 int msed_pelagic_init(msed_handle *h, const double *conc2d, const double *wz2d, const double *layer_height2d,
                       const double *temperature2d)
 {
@@ -1543,7 +1735,8 @@ int msed_pelagic_benthic_coupler(msed_handle *h, const msed_pelagic_state *st)
         (rc = up(st->DIN, 8, &in.DIN)) || (rc = up(st->DIP, 9, &in.DIP)) || (rc = up(st->temperature, 11, &temp)))
         return rc;
     double *csurf = stage + 12 * ld, *wz = stage + 20 * ld;
-    pelagic_benthic_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(csurf, wz, in, ld, h->ncol);
+    pelagic_benthic_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(csurf, wz, in, ld, h->ncol,
+                                                                    (h->compat & MSED_COMPAT_P2B_OXYGEN_LAST_CELL) ? 1 : 0);
     CUDA_TRY(h, cudaGetLastError());
     BcPtrs bc;
     std::memset(&bc, 0, sizeof(bc));
@@ -1606,6 +1799,178 @@ int msed_soil_pelagic_connector(msed_handle *h, const msed_soil_pelagic_params *
             CUDA_TRY(h, cudaMemcpyAsync(rows[r].dst, h->scratch + (size_t)rows[r].row * h->ld,
                                         (size_t)h->ncol * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_set_compat(msed_handle *h, int flags)
+{
+    if (!h) return MSED_ERR_ARG;
+    if (flags & ~(MSED_COMPAT_P2B_OXYGEN_LAST_CELL | MSED_COMPAT_P2S_HEAD)) return fail(h, MSED_ERR_ARG, "unknown compat flag");
+    h->compat = flags;
+    return MSED_OK;
+}
+
+int msed_pelagic_soil_params_defaults(msed_pelagic_soil_params *par)
+{
+    if (!par) return MSED_ERR_ARG;
+    par->sinking_factor = 0.3;                      // pelagic_soil_connector.F90:38
+    par->NC_ldet = 0.23;                            // :39
+    par->NC_sdet = 0.01;                            // :40
+    par->convertN = 1.0;                            // :41
+    par->convertP = 1.0;                            // :42
+    par->sinking_factor_min = (double)0.02f;        // :43 (default-real literal)
+    par->half_sedimentation_depth = (double)0.1f;   // :44
+    par->half_sedimentation_tke = 1.0e3;            // :45
+    par->critical_detritus = (double)60.0f;         // :46
+    return MSED_OK;
+}
+
+int msed_pelagic_soil_connector(msed_handle *h, const msed_pelagic_soil_state *st, const msed_pelagic_soil_params *par)
+{
+    if (!h || !st || !par) return fail(h, MSED_ERR_ARG, "null argument");
+    if (!st->temperature || !st->detN || !st->detN_z_velocity)
+        return fail(h, MSED_ERR_ARG, "temperature, detN and detN_z_velocity are required");
+    if (!st->nitrate && !st->ammonium && !st->DIN)
+        return fail(h, MSED_ERR_ARG, "one of nitrate, ammonium, DIN is required");   // ESMF_RC_NOT_FOUND, :1846
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    // staging rows (row length ld): [0..14] inputs, [15] temperature, [16..23] csurf, [24..26] wz
+    const size_t ld = h->ld, w = (size_t)h->ncol;
+    double *stage = h->scratch;
+    if ((size_t)NV * h->K < 27) return fail(h, MSED_ERR_STATE, "staging buffer too small");
+    auto up = [&](const double *src, size_t row, const double **dst) -> int {
+        *dst = nullptr;
+        if (!src) return MSED_OK;
+        CUDA_TRY(h, cudaMemcpyAsync(stage + row * ld, src, w * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        *dst = stage + row * ld;
+        return MSED_OK;
+    };
+    P2SIn in;
+    const double *temp = nullptr, *par2d = nullptr;
+    if ((rc = up(st->oxygen, 0, &in.oxygen)) || (rc = up(st->odu, 1, &in.odu)) || (rc = up(st->detN, 2, &in.detN)) ||
+        (rc = up(st->detN_z_velocity, 3, &in.detN_wz)) || (rc = up(st->detC, 4, &in.detC)) ||
+        (rc = up(st->detP, 5, &in.detP)) || (rc = up(st->detP_z_velocity, 6, &in.detP_wz)) ||
+        (rc = up(st->nitrate, 7, &in.nitrate)) || (rc = up(st->ammonium, 8, &in.ammonium)) ||
+        (rc = up(st->DIN, 9, &in.DIN)) || (rc = up(st->DIP, 10, &in.DIP)) || (rc = up(st->water_depth, 11, &in.depth)) ||
+        (rc = up(st->tke, 12, &in.tke)) || (rc = up(st->par, 13, &par2d)) || (rc = up(st->temperature, 15, &temp)))
+        return rc;
+    P2SPar q;
+    q.sinking_factor = par->sinking_factor;
+    q.sinking_factor_min = par->sinking_factor_min;
+    q.NC_ldet = par->NC_ldet;
+    q.NC_sdet = par->NC_sdet;
+    q.half_sedimentation_depth = par->half_sedimentation_depth;
+    q.half_sedimentation_tke = par->half_sedimentation_tke;
+    q.critical_detritus = par->critical_detritus;
+    q.convertN = par->convertN;
+    q.convertP = par->convertP;
+    q.head_compat = (h->compat & MSED_COMPAT_P2S_HEAD) ? 1 : 0;
+    double *csurf = stage + 16 * ld, *wz = stage + 24 * ld;
+    if (q.head_compat)   // the carbon velocity fields keep the 0 the component created them with
+        CUDA_TRY(h, cudaMemsetAsync(wz, 0, 2 * ld * sizeof(double), h->stream));
+    pelagic_soil_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(csurf, wz, nullptr, in, q, ld, h->ncol);
+    CUDA_TRY(h, cudaGetLastError());
+    if (par2d)
+        CUDA_TRY(h, cudaMemcpyAsync(h->par_surface, par2d, w * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    BcPtrs bc;
+    std::memset(&bc, 0, sizeof(bc));
+    bc.temperature = temp;
+    for (int n = 0; n < NV; ++n) {
+        // oxygen / reduced substances stay untouched when neither is imported (:862-900 maps a 2-D field only)
+        if (n >= 6 && !st->oxygen && !st->odu) continue;
+        bc.csurf[n] = csurf + (size_t)n * ld;
+        if (n < NPART) bc.wz[n] = wz + (size_t)n * ld;
+    }
+    boundary_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(
+        h->bdys, h->fluxes, h->buf[h->cur], h->por, bc, h->ld, ld, h->ncol, h->K,
+        h->cfg.bcup_dissolved_variables, h->bioturbation_eff, h->cfg.diffusivity, h->dz[0]);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_diagnostics(msed_handle *h, double *bed_flux_sum, double *inventory, int reduce_over_ranks)
+{
+    if (!h || (!bed_flux_sum && !inventory)) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    KParams p;
+    fill_params(h, p);
+    const int nb = nblocks(h->ncol);
+    diag_partial_kernel<<<nb, 256, 0, h->stream>>>(h->scratch, h->buf[h->cur], h->por, h->fluxes, h->mask, h->ld,
+                                                   h->ncol, h->K, p);
+    diag_final_kernel<<<1, 32, 0, h->stream>>>(h->red, h->scratch, nb);
+    CUDA_TRY(h, cudaGetLastError());
+    if (reduce_over_ranks && h->comm) {
+        NcclApi &api = nccl_api();
+        if (api.AllReduce(h->red, h->red, 2 * NV, kNcclFloat64, kNcclSum, h->comm, h->stream) != 0)
+            return fail(h, MSED_ERR_NCCL, "ncclAllReduce (diagnostics) failed");
+    }
+    double out[2 * NV];
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->red, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int n = 0; n < NV; ++n) {
+        if (bed_flux_sum) bed_flux_sum[n] = out[n];
+        if (inventory) inventory[n] = out[NV + n];
+    }
+    return MSED_OK;
+}
+
+int msed_state_checksum(msed_handle *h, int64_t global_ncol, int64_t col_offset, uint64_t out[2])
+{
+    if (!h || !out) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(h->red);
+    CUDA_TRY(h, cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), h->stream));
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+    checksum_kernel<<<nsm * 8, 256, 0, h->stream>>>(h->buf[h->cur], h->mask, h->ld, h->ncol, NV * h->K,
+                                                    (long long)global_ncol, (long long)col_offset, d);
+    CUDA_TRY(h, cudaGetLastError());
+    unsigned long long r[2];
+    CUDA_TRY(h, cudaMemcpyAsync(r, d, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    out[0] = r[0];
+    out[1] = r[1];
+    return MSED_OK;
+}
+
+int msed_measure_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return MSED_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, MSED_ERR_CUDA, "no CUDA device");
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    double *out = nullptr;
+    CUDA_TRY(nullptr, cudaMalloc(&out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(nullptr, cudaEventCreate(&e0));
+    CUDA_TRY(nullptr, cudaEventCreate(&e1));
+    const int iters = 1 << 15, threads = 256, blocks = nsm * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {   // the first launch warms up
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(out, 0.999999, 1e-9, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fma = (double)blocks * threads * 8.0 * iters;
+        if (rep > 0 && ms > 0.f) best = std::max(best, 2.0 * fma / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    CUDA_TRY(nullptr, cudaGetLastError());
+    *tflops = best;
     return MSED_OK;
 }
 

@@ -19,11 +19,15 @@
 // Semantics are those of nsub ode_solver calls (solver_library.F90:104-140), each followed by the
 // component's check_NaN / minimum clip (fabm_sediment_component.F90:1718-1732): a step's output is
 // clipped before the next step reads it, every step raises the violation / NaN flags, and
-// chain_controller_kernel commits the chain only if no step would have been rejected or stopped.
-// Otherwise nothing is committed (the input buffer is untouched) and the host redoes the same steps
+// plan_controller_kernel commits the chain only if the reference would have taken exactly the planned
+// decisions.  The plan (msed.cu run_steps) may hold sub-cycled steps (SUB): every call then runs at
+// dt_acc = dt/4^depth, i.e. its first sub-step also evaluates -- with the same RHS, the state being unchanged
+// by a rejection -- the attempts at dt, dt/4, .. that the reference rejects (:126-128) and raises "rejection
+// seen" for each, 4^depth sub-steps follow each other without a clip, and the clip comes after the last.
+// Otherwise nothing is committed (the input buffer is untouched) and the host redoes the same attempts
 // with the single-step kernel -- speculation with a free rollback, exactly as for pairs.  The
 // arithmetic is the shared inline code of msed_column.cuh, so a committed chain is bit-identical to
-// nsub single steps.
+// the single attempts.
 //
 // Same scope as pair_kernel: bcup_particulate = 1, bioturbation_profile != 3, closed-form porosity.
 
@@ -39,15 +43,21 @@ constexpr int CHAIN_MAX_LAYERS = 32;
 
 // CLIP: the component wrapper (check_NaN + minimum clip after every step) is on -- a host-side fact
 // (msed_step / msed_run set it, msed_ode_solver does not), mirrored in Ctl::do_clip
-template <int MODEL, bool ADAPTIVE, bool CLIP>
+// SUB: the plan holds sub-cycled steps (KParams::depth > 0); a separate instantiation so that the common
+// chain (every step accepted at dt) keeps its straight step loop
+template <int MODEL, bool ADAPTIVE, bool CLIP, bool SUB>
 __global__ void __launch_bounds__(CHAIN_BLOCK, MSED_CHAIN_MIN_BLOCKS)
 chain_kernel(const __grid_constant__ KParams p, const int nsub)
 {
     const Ctl *ctl = p.ctl;
-    if (ctl->stop || ctl->pairs_disabled || ctl->steps_done + nsub > ctl->steps_target || ctl->dt_int != 0.0)
-        return;
+    // the plan was made for one definite control state (see pair_kernel)
+    if (ctl->stop || ctl->pairs_disabled || ctl->steps_done != p.gate_steps) return;
     const int cur = ctl->cur;
-    const double dt = ctl->dt;
+    const double dt = p.dt_acc;
+    const int depth = SUB ? p.depth : 0;
+    const int nq = 1 << (2 * depth);               // accepted sub-steps per ode_solver call
+    const double dt_up[MAX_PLAN_DEPTH] = {dt * 4.0, dt * 16.0};   // the rejected step sizes, exact (:127)
+    unsigned upmask = 0;                           // bit s*depth + l: step s saw the rejection at dt_up[l]
     // a violation can only be rejected while dt_red > dt_min (solver_library.F90:126); a chain whose
     // violation flag is already up cannot be committed, so warps that start later skip their work
     const bool rejectable = ADAPTIVE && dt > ctl->dt_min;
@@ -107,11 +117,14 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     const double *top_part = p.fluxes + col;
     const double *top_diss = (bc_diss == 2) ? p.bdys + ld + col : p.fluxes + col;
 
+    const int nacc = nsub * nq;
 #ifdef MSED_CHAIN_UNROLL
     MSED_UNROLL_PRAGMA(MSED_CHAIN_UNROLL)
 #endif
-    for (int s = 0; s < nsub; ++s) {
-        const bool last = (s == nsub - 1);
+    for (int a = 0; a < nacc; ++a) {
+        const int s = SUB ? a / nq : a, q = SUB ? a - s * nq : 0;
+        const bool last = (a == nacc - 1);
+        const bool final_sub = !SUB || q == nq - 1;   // this sub-step ends an ode_solver call
 
         // upper-boundary inputs, read by every lane (one address per warp: a broadcast) and not inside a
         // lane-0 branch: they are step-invariant, so the compiler lifts them out of the loop and keeps them in
@@ -180,19 +193,30 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
         }
 
         double raw[NV];  // new state before the clip (check_NaN looks at it first, component :1718)
+        int vup = 0;
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
             const double rhs = layer_rhs(F[n], Fn[n], rpd, r[n]);
             const double c0 = cc[n];
             double newc = euler_update(dt, rhs, c0);
             if (ADAPTIVE) violates_acc(viol, p.fac, c0, newc);
+            if (ADAPTIVE && SUB && q == 0) {   // the planned rejections: tested exactly as a single attempt does
+#pragma unroll
+                for (int l = 0; l < MAX_PLAN_DEPTH; ++l)
+                    if (l < depth && violates(p.fac, c0, euler_update(dt_up[l], rhs, c0))) vup |= 1 << l;
+            }
             raw[n] = newc;
-            if (CLIP) {
+            if (CLIP && final_sub) {
                 if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
                 const double mn = p.om.minimum[n];
                 newc = (newc < mn) ? mn : newc;
             }
             cc[n] = newc;
+        }
+        if (ADAPTIVE && SUB && q == 0) {
+#pragma unroll
+            for (int l = 0; l < MAX_PLAN_DEPTH; ++l)
+                if (l < depth && __any_sync(FULL, (vup & (1 << l)) && active)) upmask |= 1u << (s * depth + l);
         }
         // a rejectable violation anywhere in the column: the chain will not be committed, stop here
         if (rejectable && __any_sync(FULL, viol < 0 && active)) {
@@ -212,25 +236,8 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     if (lane == 0) {
         if (ADAPTIVE && any_viol) atomicOr(&p.ctl->flags[0], 1);
         if (any_nan) atomicOr(&p.ctl->flags[1], 1);
+        for (int b = 0; SUB && upmask; ++b, upmask >>= 1)
+            if (upmask & 1u) atomicOr(&p.ctl->flags[FLAG_UP0 + p.up_slot + b], 1);
     }
 }
 
-// commits a chain of m steps (or disables fused launches so the host falls back to single steps from the
-// same state); the gate is the one chain_kernel evaluated
-__global__ void chain_controller_kernel(Ctl *c, int method, int m)
-{
-    c->step_completed = 0;
-    if (c->stop || c->pairs_disabled || c->steps_done + m > c->steps_target || c->dt_int != 0.0) return;
-    const int v = c->flags[0] | c->flags[2], nn = c->flags[1] | c->flags[3];
-    c->flags[0] = c->flags[1] = c->flags[2] = c->flags[3] = 0;
-    const bool rejectable = (method == MSED_ADAPTIVE_EULER) && (c->dt_red > c->dt_min);
-    if ((rejectable && v) || (c->do_clip && nn)) {
-        c->pairs_disabled = 1;  // a step would be rejected (:126) or stopped (component :1718):
-        c->pair_failures += 1;  // nothing is committed, single steps redo it exactly
-        return;
-    }
-    c->cur ^= 1;
-    c->steps_done += m;
-    c->rhs_evals += m;
-    c->step_completed = 1;
-}

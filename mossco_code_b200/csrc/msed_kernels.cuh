@@ -1,113 +1,21 @@
-// msed_kernels.cuh -- sm_100a device code of the fabm_sediment column solver.
+// msed_kernels.cuh -- sm_100a device code of the fabm_sediment column solver that lives in msed.cu:
+// the step-loop controllers and the small thread-per-column helper kernels.
 //
-// Shared types (control block, kernel parameters), the step-loop controller and the small
-// thread-per-column helper kernels.  The fused RHS + integrator kernel is in msed_column.cuh:
-// diff3d transport + omexdia_p reactions (fabm_sediment_driver.F90:575-717,739-825), the
-// integrator update (solver_library.F90:99-185), the adaptive-step violation test (:121),
-// check_NaN and the minimum clip (fabm_sediment_component.F90:1718-1732) in one pass: per
-// ode_solver attempt the state is read once and written once.
+// The fused RHS + integrator kernels are in msed_column.cuh (one step per launch), msed_pair.cuh (two
+// sub-steps per launch), msed_chain.cuh / msed_strip.cuh (many sub-steps per launch with the column in
+// registers) and msed_rkpair.cuh (two Runge-Kutta stages per launch): diff3d transport + omexdia_p reactions
+// (fabm_sediment_driver.F90:575-717,739-825), the integrator update (solver_library.F90:99-185), the
+// adaptive-step violation test (:121), check_NaN and the minimum clip (fabm_sediment_component.F90:1718-1732)
+// in one pass.
 #pragma once
 
-#include <cstddef>
-#include <cstdint>
-#include <cuda_runtime.h>
-#include <type_traits>
-
-#include "../../include/msed.h"
+#include "msed_types.cuh"
 
 namespace msed {
 
-constexpr int NV = MSED_NVAR;
-constexpr int MAXK = MSED_MAX_LAYERS;
-constexpr int NPART = 3;  // ldetC, sdetC, detP are particulate (main.F90:92-101)
-// tunables of the column kernel (overridable with -D for the sweeps in tools/tune_sweep.sh)
-#ifndef MSED_COL_BLOCK
-#define MSED_COL_BLOCK 128
-#endif
-#ifndef MSED_COL_MIN_BLOCKS
-#define MSED_COL_MIN_BLOCKS 4
-#endif
-#ifndef MSED_RING_STAGES
-#define MSED_RING_STAGES 4
-#endif
-constexpr int COL_BLOCK = MSED_COL_BLOCK;            // threads (= columns) per CTA of the column kernel
-constexpr int COL_MIN_BLOCKS = MSED_COL_MIN_BLOCKS;  // 4 CTAs/SM -> <=128 registers/thread, 16 warps/SM
-
-// integrator stage executed by the column kernel
-enum Op : int {
-    OP_RHS = 0,       // get_rhs only
-    OP_EULER,         // solver_library.F90:99-102
-    OP_ADAPTIVE,      // one attempt of :104-140
-    OP_RK4_S1, OP_RK4_S2, OP_RK4_S3, OP_RK4_S4,         // :142-163
-    OP_RK38_S1, OP_RK38_S2, OP_RK38_S3, OP_RK38_S4      // :164-185
-};
-
-// device-resident control block of the step loop (one per handle)
-struct Ctl {
-    double dt;          // requested ode_solver dt
-    double dt_int;      // integrated time inside the current ode_solver call (:106)
-    double dt_red;      // current reduced sub-step (:107,:127)
-    double dt_min;      // type_rhs_driver%dt_min
-    double last_min_dt; // :44
-    long long steps_done, steps_target;
-    long long rhs_evals, subcycles;
-    int cur;            // which of buf[0..1] is sed%conc
-    int flags[4];       // [0] relative-change violation (:121)  [1] NaN (component :2392);
-                        // [2],[3] the same for the second step of a fused pair (msed_pair.cuh)
-    int pairs_disabled; // a fused pair could not be committed: fall back to single steps
-    int pair_failures;
-    int nan_detected;
-    int stop;
-    int do_clip;        // component wrapper (check_NaN + clip) on/off
-    int diagnostics;    // adaptive_solver_diagnostics
-    int minloc_request; // set when last_min_dt decreased (:131-135)
-    int step_completed; // 1 if the last controller invocation finished an ode_solver call
-};
-
-struct OmexDev {  // hzg_omexdia_p parameters, rates already per second
-    double rLabile, rSemilabile, NCrLdet, NCrSdet, PAds_rS, PAdsODU, rNH3Ads, CprodMax;
-    double rnit, ksO2nitri, rODUox, ksO2oduox, ksO2oxic, ksNO3denit, kinO2denit;
-    double kinNO3anox, kinO2anox, E_a;
-    double minimum[NV];
-};
-
-struct KParams {
-    double *buf[2];          // ping-pong state, [nvar][K][ld]
-    double *aux1, *aux2;     // RK accumulators
-    double *rhs_out;         // OP_RHS target
-    const double *por;       // [K][ld]
-    const double *bdys;      // [nvar+1][ld]
-    double *fluxes;          // [nvar][ld]
-    const unsigned char *mask;  // [ncol]
-    Ctl *ctl;
-    size_t ld;
-    int ncol, K, inum;
-    int col0, col_end;       // column range [col0, col_end) of this launch (chunked launches overlap PCIe)
-    int i_offset, j_offset;
-    int bcup_diss, bcup_part, profile;
-    int use_ctl;             // 0: OP_RHS / plain launch with p.dt and buffer 0
-    int por_mode;            // 0: 3-D porosity field, 1: portab[k], 2: por(:,:,1)*portab[k]
-    double dt;
-    double fac;              // 1 + relative_change_min
-    double bioturbation, diffusivity;
-    double pom_flux_rate;    // pom_flux_max/86400
-    double beta, b, L1, L2, poc_factor[2], cumdepth_last;
-    OmexDev om;
-    double dz[MAXK], rdzc[MAXK], bf[MAXK], e1[MAXK], e2[MAXK], portab[MAXK];
-    double *denit_out;       // [K][ld]: FABM denit diagnostic of the second step of a call's last pair, or null
-    const int *colmap;       // pair_kernel on a masked tile: indices of the wet columns, ascending; col0/col_end
-                             // then count wet columns (null: identity)
-    const double *in_ovr;    // pair_kernel<.., OVR>: explicit input / output state buffers of a launch inside a
-    double *out_ovr;         // chunk-major sequence (msed.cu run_steps), instead of buf[cur] / buf[1-cur]
-};
-
-// loaders, reaction term and the fused column kernel
+// loaders and the reaction term (the helper kernels below evaluate diagnostics with the same inline code);
+// the stepping kernels themselves are instantiated in the msed_tu_*.cu translation units (msed_launch.h)
 #include "msed_column.cuh"
-// two Euler / adaptive-Euler steps per pass over HBM (speculative, rollback-free)
-#include "msed_pair.cuh"
-// a chain of steps with the column in registers: warp per column, lane per layer (knum <= 32)
-#include "msed_chain.cuh"
-#include "msed_rkpair.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // step-loop controller: the scalar part of ode_solver (:108,:126-139) and of the component
@@ -125,6 +33,8 @@ __global__ void controller_kernel(Ctl *c, int method)
         if (viol && c->dt_red > c->dt_min) {  // :126-128
             c->dt_red = c->dt_red * 0.25;
             c->subcycles += 1;
+            if (c->step_accepts == 0) c->step_rej_first += 1;
+            else c->step_rej_later += 1;
             return;
         }
         if (c->diagnostics && c->dt_red < c->last_min_dt) {  // :130-135
@@ -133,6 +43,7 @@ __global__ void controller_kernel(Ctl *c, int method)
         }
         c->cur ^= 1;                      // conc = c1, :137
         c->dt_int = c->dt_int + c->dt_red;  // :138
+        c->step_accepts += 1;
         if (c->dt_int < c->dt) return;    // :108
     } else if (method == MSED_EULER) {
         c->rhs_evals += 1;
@@ -148,6 +59,54 @@ __global__ void controller_kernel(Ctl *c, int method)
     c->step_completed = 1;
     c->dt_int = 0.0;
     c->dt_red = c->dt;
+    c->last_depth = c->step_rej_first;
+    c->last_irregular = c->step_rej_later > 0;
+    c->step_rej_first = c->step_rej_later = c->step_accepts = 0;
+}
+
+// Commits one fused group -- a pair launch, a chain launch, or all pair launches of a chunk-major coupling
+// interval -- or disables fused launches so that the host redoes the same attempts one by one from the
+// untouched state.  The group was planned on the host (msed.cu run_steps) as a definite piece of the
+// reference's attempt sequence (solver_library.F90:104-140): which attempts are rejected, which sub-steps are
+// accepted, where ode_solver calls end.  It is committed only if every flag agrees with that plan:
+//   - every planned rejection was seen (its flag slot is up: some cell violated relative_change_min at the
+//     larger step, :121,:126), otherwise the reference would have accepted the larger step;
+//   - no accepted sub-step violates while it could still be rejected (:126), otherwise the reference would
+//     have gone to a smaller step;
+//   - check_NaN (component :1718) found nothing.
+__global__ void plan_controller_kernel(Ctl *c, PlanCommit pc)
+{
+    c->step_completed = 0;
+    if (c->stop || c->pairs_disabled || c->steps_done != pc.gate_steps) return;
+    const int own = c->flags[0] | c->flags[2], nanf = c->flags[1] | c->flags[3];
+    int up_all = 1;
+    for (int s = 0; s < pc.up_slots; ++s) up_all &= (c->flags[FLAG_UP0 + s] != 0);
+    for (int s = 0; s < MSED_NFLAGS; ++s) c->flags[s] = 0;
+    if ((pc.own_rejectable && own) || (c->do_clip && nanf) || !up_all) {
+        c->pairs_disabled = 1;
+        c->pair_failures += 1;
+        return;
+    }
+    if (pc.flip) c->cur ^= 1;
+    c->steps_done += pc.steps;
+    c->fused_steps += pc.steps;
+    c->fused_launches += pc.launches;
+    c->rhs_evals += pc.rhs_evals;
+    c->subcycles += pc.subcycles;
+    c->dt_int = pc.dt_int;
+    c->dt_red = pc.dt_red;
+    c->step_completed = (pc.steps > 0 && pc.dt_int == 0.0) ? 1 : 0;
+    if (pc.steps > 0) {
+        c->last_depth = pc.depth;
+        c->last_irregular = 0;
+    }
+    if (pc.dt_int == 0.0) {
+        c->step_rej_first = c->step_rej_later = c->step_accepts = 0;
+    } else {   // the group ends inside an ode_solver call: what the single-step controller needs to carry on
+        c->step_rej_first = pc.depth;
+        c->step_rej_later = 0;
+        c->step_accepts = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,17 +255,20 @@ __global__ void boundary_kernel(double *bdys, double *fluxes, const double *conc
 
 // pelagic_benthic_coupler Run (src/mediators/pelagic_benthic_coupler.F90:330-480), one thread per
 // column.  Writes the 8 surface concentrations into csurf rows and the 3 sinking velocities into wz
-// rows of a staging area [..][ld_out]; the per-cell intent of the oxygen/odu split is implemented
-// (the reference assigns the whole array inside its i,j loop, :344-349).
+// rows of a staging area [..][ld_out]; the per-cell intent of the oxygen/odu split is implemented by default
+// (the reference assigns the whole array inside its i,j loop, :344-349: see oxy_last_cell).
 struct P2BIn {
     const double *oxygen, *detN, *detN_wz, *detC, *detP, *detP_wz, *nitrate, *ammonium, *DIN, *DIP;
 };
-__global__ void pelagic_benthic_kernel(double *csurf, double *wz, P2BIn in, size_t ld_out, int ncol)
+__global__ void pelagic_benthic_kernel(double *csurf, double *wz, P2BIn in, size_t ld_out, int ncol,
+                                       int oxy_last_cell)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncol) return;
     const double NC_fdet = 0.20, NC_sdet = 0.04, sinking_factor = 0.3;   // :298,:301-302
-    const double o2 = in.oxygen[col];
+    // MSED_COMPAT_P2B_OXYGEN_LAST_CELL: the reference assigns the whole oxy/odu arrays inside its i,j loop
+    // (:344-349), so every column ends up with the value of the tile's last cell
+    const double o2 = in.oxygen[oxy_last_cell ? ncol - 1 : col];
     const double detN = in.detN[col];
     const double vN = in.detN_wz[col];
     const double CN = in.detC ? __ddiv_rn(in.detC[col], detN) : 106.0 / 16.0;           // :379-394
@@ -518,5 +480,8 @@ __global__ void clip_kernel(Ctl *c, double *b0, double *b1, const unsigned char 
         }
     if (nanf) { c->nan_detected = 1; c->stop = 1; }
 }
+
+// pelagic -> soil connector, whole-domain diagnostics, fp64 micro-benchmark
+#include "msed_aux.cuh"
 
 }  // namespace msed

@@ -1,0 +1,30 @@
+// msed_launch.h -- launchers of the stepping kernels.  Each family of kernel templates is instantiated in a
+// translation unit of its own (msed_tu_*.cu), so that the library builds in parallel; msed.cu (host side,
+// C ABI, controllers, helper kernels) only sees these functions.
+#pragma once
+
+#include "msed_types.cuh"
+
+namespace msed {
+
+// column_kernel<MODEL, OP, PROFILE3, STREAM_POR> (msed_column.cuh): one RHS evaluation / attempt / RK stage
+cudaError_t tu_launch_column(int model, bool profile3, bool stream_por, int op, const KParams &p, cudaStream_t s);
+
+// pair_kernel (msed_pair.cuh): two accepted sub-steps per launch.  DENIT <- p.denit_out, COLMAP <- p.colmap,
+// OVR <- p.in_ovr; the caller has already converted col0/col_end to a range of the wet-column list
+cudaError_t tu_launch_pair(int model, bool adaptive, const KParams &p, cudaStream_t s);
+cudaError_t tu_enable_pair_smem();
+
+// chain_kernel (msed_chain.cuh): nsteps ode_solver calls per launch, warp per column, knum <= 32
+cudaError_t tu_launch_chain(int model, bool adaptive, bool clip, const KParams &p, int nsteps, cudaStream_t s);
+constexpr int TU_CHAIN_MAX_LAYERS = 32;
+constexpr int TU_CHAIN_MAX_STEPS = 16;   // steps per launch: bounds the work a failed speculation throws away
+
+// rk_pair_kernel (msed_rkpair.cuh): which = 0 for stages 1+2, 1 for stages 3+4
+cudaError_t tu_launch_rk_pair(int model, int method, int which, const KParams &p, cudaStream_t s);
+cudaError_t tu_enable_rk_smem();
+
+// spinup_kernel (msed_spinup.cuh): the 1-D pre-simulation of a batch of members, warp per member, knum <= 32
+cudaError_t tu_launch_spinup(int model, const KParams &p, const SpinupArgs &a, cudaStream_t s);
+
+}  // namespace msed

@@ -1,21 +1,29 @@
 // msed_pair.cuh -- included inside namespace msed after msed_column.cuh.
 //
-// Two consecutive Euler / adaptive-Euler steps in one pass over HBM.
+// Two consecutive accepted sub-steps of the Euler / adaptive-Euler integrator in one pass over HBM.
 //
-// The single-step kernel is HBM-bound (state read once, written once per step) with the fp64 pipe
-// only half busy.  Columns are independent and the stencil is one layer wide, so the second step can
-// chase the first one down the column with a lag of one layer: when step 1 has produced layer k,
-// step 2 has everything it needs for layer k-1.  The intermediate state c1 never leaves the SM (a
+// The single-step kernel is HBM-bound (state read once, written once per attempt) with the fp64 pipe
+// only half busy.  Columns are independent and the stencil is one layer wide, so the second sub-step can
+// chase the first one down the column with a lag of one layer: when stage A has produced layer k,
+// stage B has everything it needs for layer k-1.  The intermediate state never leaves the SM (a
 // thread-private 4-layer window in shared memory), so a pair costs one read and one write of the
 // state instead of two.
 //
-// Semantics are exactly those of two ode_solver calls (solver_library.F90:104-140) with the component's
-// check_NaN / minimum clip after each (fabm_sediment_component.F90:1718-1732): step 1's output is
-// clipped before step 2 reads it, each step raises its own violation / NaN flags, and the pair is
-// committed by pair_controller_kernel only if neither step would have been rejected or stopped.
-// Otherwise nothing is committed (the input buffer is untouched) and the host falls back to single
-// steps from the same state -- so a pair is speculation with a free rollback.  The arithmetic is the
-// shared inline code of msed_column.cuh: a committed pair is bit-identical to two single steps.
+// What the two stages are is decided by the host's plan of the reference's attempt sequence
+// (solver_library.F90:104-140; KParams::pair_kind, msed.cu run_steps):
+//   PAIR_FULL   two whole ode_solver calls, each accepted at dt on its first attempt, with the component's
+//               check_NaN / minimum clip after each (fabm_sediment_component.F90:1718-1732);
+//   PAIR_FIRST  the first two sub-steps of a call that runs at dt_acc = dt/4^depth: stage A evaluates the RHS
+//               of the attempts at dt, dt/4, .. that are rejected (:126-128) -- the state is unchanged by a
+//               rejection, so it is the same RHS -- raises "rejection seen" for each of them and advances by
+//               dt_acc; nothing is clipped inside a call;
+//   PAIR_MID    two inner sub-steps;
+//   PAIR_LAST   the last two sub-steps of a call; check_NaN / clip after stage B.
+// Every stage raises its own violation flag at dt_acc.  plan_controller_kernel commits the launch (or the
+// whole group of launches it belongs to) only if the flags say the reference would have taken exactly the
+// planned decisions; otherwise nothing is committed (the input buffer is untouched) and the host redoes the
+// same attempts one by one -- a fused launch is speculation with a free rollback.  The arithmetic is the
+// shared inline code of msed_column.cuh: a committed pair is bit-identical to the single attempts.
 //
 // Restricted to the hot configuration: bcup_particulate = 1 (no distributed POM flux cascade),
 // bioturbation_profile != 3, closed-form porosity (KParams::por_mode 1 or 2).
@@ -41,11 +49,12 @@ pair_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) double ring[];
     const Ctl *ctl = p.ctl;
-    if (ctl->stop || ctl->pairs_disabled || ctl->steps_done + 2 > ctl->steps_target || ctl->dt_int != 0.0)
-        return;
+    // the plan this launch belongs to was made for one definite control state: after a failed group
+    // (pairs_disabled) or anything else unforeseen the launch does nothing
+    if (ctl->stop || ctl->pairs_disabled || ctl->steps_done != p.gate_steps) return;
     const int cur = ctl->cur;
     const bool do_clip = ctl->do_clip != 0;
-    const double dt = ctl->dt;
+    const double dt = p.dt_acc;
     // a pair whose violation flags are already up cannot be committed: later CTAs skip their work
     const volatile int *flags = ctl->flags;
     if (ADAPTIVE && dt > ctl->dt_min && (flags[0] | flags[2])) return;
@@ -155,10 +164,19 @@ pair_kernel(const __grid_constant__ KParams p)
         return lc;
     };
 
-    auto step_layer = [&](auto has_next_tag, auto clip_tag, const LayerCoef &lc, const double (&cc)[NV], auto cn,
-                          double (&F)[NV], int &viol, bool &nanf, auto sink, auto denit) {
+    // planned rejections (PAIR_FIRST, stage A): bit l of viol_up = some relative change at dt_acc*4^(l+1) fell
+    // below relative_change_min.  Tested exactly as the single attempt tests it (violates(): a false alarm
+    // here would commit a sub-cycle the reference never took).
+    int viol_up = 0;
+    static_assert(MAX_PLAN_DEPTH == 2, "dt_up lists the step sizes of the planned rejections");
+    const double dt_up[MAX_PLAN_DEPTH] = {dt * 4.0, dt * 16.0};   // exact: dt_acc = dt_up * 0.25 (:127)
+    const int depth = p.depth;
+
+    auto step_layer = [&](auto has_next_tag, auto clip_tag, auto up_tag, const LayerCoef &lc, const double (&cc)[NV],
+                          auto cn, double (&F)[NV], int &viol, bool &nanf, auto sink, auto denit) {
         constexpr bool HAS_NEXT = decltype(has_next_tag)::value;
         constexpr bool CLIP = decltype(clip_tag)::value;
+        constexpr bool UP = decltype(up_tag)::value;
         double Fn[NV];
         if (HAS_NEXT) {
 #pragma unroll
@@ -188,6 +206,11 @@ pair_kernel(const __grid_constant__ KParams p)
             const double c0 = cc[n];
             double newc = euler_update(dt, rhs, c0);
             if (ADAPTIVE) violates_acc(viol, p.fac, c0, newc);
+            if (ADAPTIVE && UP) {
+#pragma unroll
+                for (int l = 0; l < MAX_PLAN_DEPTH; ++l)
+                    if (l < depth && violates(p.fac, c0, euler_update(dt_up[l], rhs, c0))) viol_up |= 1 << l;
+            }
             raw[n] = newc;
             if (CLIP) {
                 if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
@@ -200,7 +223,7 @@ pair_kernel(const __grid_constant__ KParams p)
 
     LayerCoef coef_prev;  // coefficients of the layer step 2 is about to process (made by step 1)
     // step 1, layer k: state from the ring, result into the c1 window; returns the layer coefficients
-    auto stage_a = [&](auto has_next_tag, auto clip_tag, int k) -> LayerCoef {
+    auto stage_a = [&](auto has_next_tag, auto clip_tag, auto up_tag, int k) -> LayerCoef {
         fetch_next();
         cp_async_wait<RING_STAGES - 2>();
         const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
@@ -210,8 +233,8 @@ pair_kernel(const __grid_constant__ KParams p)
         double cc[NV];
 #pragma unroll
         for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
-        step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA, viol1,
-                   nan1, [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); }, nullptr);
+        step_layer(has_next_tag, clip_tag, up_tag, lc, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA,
+                   viol1, nan1, [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); }, nullptr);
         return lc;
     };
     // step 2, layer j: state from the c1 window, result to HBM
@@ -224,39 +247,52 @@ pair_kernel(const __grid_constant__ KParams p)
         double *go = g_out;
         if (DENIT) {
             double dn = 0.0;
-            step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB,
-                       viol2, nan2, [&](int n, double v) { go[(size_t)n * plane] = v; }, &dn);
+            step_layer(has_next_tag, clip_tag, std::false_type{}, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); },
+                       FB, viol2, nan2, [&](int n, double v) { go[(size_t)n * plane] = v; }, &dn);
             p.denit_out[(size_t)j * ld + col] = dn;
         } else {
-            step_layer(has_next_tag, clip_tag, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); }, FB,
-                       viol2, nan2, [&](int n, double v) { go[(size_t)n * plane] = v; }, nullptr);
+            step_layer(has_next_tag, clip_tag, std::false_type{}, lc, cc, [&](int n) { return lds64(wn + n * ROW_BYTES); },
+                       FB, viol2, nan2, [&](int n, double v) { go[(size_t)n * plane] = v; }, nullptr);
         }
         g_out += ld;
     };
 
-    auto sweep = [&](auto clip_tag) {
+    // clip_a / clip_b: check_NaN + minimum clip after stage A / stage B (the stage ends an ode_solver call and
+    // the component wrapper is on); up_tag: stage A also tests the planned rejections
+    auto sweep = [&](auto clip_a, auto clip_b, auto up_tag) {
         using Y = std::true_type;
         using N = std::false_type;
-        if (K == 1) {  // degenerate column: both steps see a closed bottom right away
-            coef_prev = stage_a(N{}, clip_tag, 0);
+        if (K == 1) {  // degenerate column: both stages see a closed bottom right away
+            coef_prev = stage_a(N{}, clip_a, up_tag, 0);
             top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
-            stage_b(N{}, clip_tag, 0, coef_prev);
+            stage_b(N{}, clip_b, 0, coef_prev);
             return;
         }
-        coef_prev = stage_a(Y{}, clip_tag, 0);
+        coef_prev = stage_a(Y{}, clip_a, up_tag, 0);
         top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
         MSED_PAIR_UNROLL_PRAGMA
-        for (int k = 1; k < K - 1; ++k) {  // steady state: step 1 on layer k, step 2 on layer k-1
-            const LayerCoef lc = stage_a(Y{}, clip_tag, k);
-            stage_b(Y{}, clip_tag, k - 1, coef_prev);
+        for (int k = 1; k < K - 1; ++k) {  // steady state: stage A on layer k, stage B on layer k-1
+            const LayerCoef lc = stage_a(Y{}, clip_a, up_tag, k);
+            stage_b(Y{}, clip_b, k - 1, coef_prev);
             coef_prev = lc;
         }
-        const LayerCoef last = stage_a(N{}, clip_tag, K - 1);
-        stage_b(Y{}, clip_tag, K - 2, coef_prev);
-        stage_b(N{}, clip_tag, K - 1, last);
+        const LayerCoef last = stage_a(N{}, clip_a, up_tag, K - 1);
+        stage_b(Y{}, clip_b, K - 2, coef_prev);
+        stage_b(N{}, clip_b, K - 1, last);
     };
-    if (do_clip) sweep(std::true_type{});
-    else sweep(std::false_type{});
+    {
+        using Y = std::true_type;
+        using N = std::false_type;
+        const int kind = ADAPTIVE ? p.pair_kind : (int)PAIR_FULL;
+        // one call site per instantiation (the lambda body is inlined wherever it is called)
+        const int sel = (kind == PAIR_FULL && do_clip) ? 0 : (kind == PAIR_FIRST) ? 1 : (kind == PAIR_LAST && do_clip) ? 2 : 3;
+        switch (sel) {
+        case 0: sweep(Y{}, Y{}, N{}); break;
+        case 1: sweep(N{}, N{}, Y{}); break;
+        case 2: sweep(N{}, Y{}, N{}); break;
+        default: sweep(N{}, N{}, N{}); break;
+        }
+    }
     cp_async_wait<0>();
 
     int *wf = p.ctl->flags;
@@ -264,23 +300,10 @@ pair_kernel(const __grid_constant__ KParams p)
     if (nan1) atomicOr(&wf[1], 1);
     if (ADAPTIVE && viol2 < 0) atomicOr(&wf[2], 1);
     if (nan2) atomicOr(&wf[3], 1);
+    if (ADAPTIVE && viol_up) {
+#pragma unroll
+        for (int l = 0; l < MAX_PLAN_DEPTH; ++l)
+            if (viol_up & (1 << l)) atomicOr(&wf[FLAG_UP0 + p.up_slot + l], 1);
+    }
 }
 
-// commits a pair (or disables pairs so the host falls back to single steps from the same state)
-__global__ void pair_controller_kernel(Ctl *c, int method)
-{
-    c->step_completed = 0;
-    if (c->stop || c->pairs_disabled || c->steps_done + 2 > c->steps_target || c->dt_int != 0.0) return;
-    const int v1 = c->flags[0], n1 = c->flags[1], v2 = c->flags[2], n2 = c->flags[3];
-    c->flags[0] = c->flags[1] = c->flags[2] = c->flags[3] = 0;
-    const bool rejectable = (method == MSED_ADAPTIVE_EULER) && (c->dt_red > c->dt_min);
-    if ((rejectable && (v1 || v2)) || (c->do_clip && (n1 || n2))) {
-        c->pairs_disabled = 1;  // a step would be rejected (:126) or stopped (component :1718):
-        c->pair_failures += 1;  // nothing is committed, single steps redo it exactly
-        return;
-    }
-    c->cur ^= 1;
-    c->steps_done += 2;
-    c->rhs_evals += 2;
-    c->step_completed = 1;
-}

@@ -9,7 +9,8 @@ branches and the error behaviour of the Fortran, so that the tests read like a c
 States are plain dicts ``name -> numpy array`` as in ``component.py``; pelagic ``*_in_water`` fields may be
 rank 3 (i, j, layer), in which case the bottom layer ``[:, :, 0]`` is taken (``lbnd(3)`` in the Fortran).
 
-    pelagic model --PelagicBenthicCoupler--> sediment --BenthicPelagicCoupler / SoilPelagicConnector--> pelagic model
+    pelagic model --PelagicBenthicCoupler / PelagicSoilConnector--> sediment
+    sediment --BenthicPelagicCoupler / SoilPelagicConnector--> pelagic model
 """
 from __future__ import annotations
 
@@ -78,6 +79,82 @@ class PelagicBenthicCoupler:
         if "DIN" not in fields and not all(k in fields for k in ("nitrate", "ammonium", "DIP")):
             raise ComponentError(ESMF_RC_NOT_FOUND, "pelagic_benthic_coupler: neither DIN nor nitrate+ammonium+DIP")
         self.sed.pelagic_benthic_coupler(**fields)
+        if fill_export and export_state is not None:
+            bdys, fluxes = self.sed.bdys, self.sed.fluxes
+            export_state["temperature_at_soil_surface"] = bdys[:, :, 0].copy()
+            for n, v in enumerate(VARIABLE_NAMES[3:], start=3):
+                export_state[f"{v}_at_soil_surface"] = bdys[:, :, n + 1].copy()
+            for n, v in enumerate(VARIABLE_NAMES[:3]):
+                export_state[f"{v}_sinking_flux_at_soil_surface"] = fluxes[:, :, n].copy()
+        return ESMF_SUCCESS
+
+
+class PelagicSoilConnector:
+    """``pelagic_soil_connector`` (src/mediators/pelagic_soil_connector.F90:176-2122), the generic successor of
+    ``pelagic_benthic_coupler``: the same direction, with a C:N-dependent split of detritus into the labile and
+    semilabile pools (:1082-1095), an environmental sinking factor from water depth, turbulent kinetic energy
+    and the detritus concentration (:1150-1232), and ammonium / nitrate / phosphate assembled from whichever of
+    nitrate, ammonium, DIN, DIP the pelagic model exports (:1775-2110).  Namelist ``/pelagic_soil_connector/``
+    (:146-148): sinking_factor, sinking_factor_min, NC_ldet, NC_sdet, half_sedimentation_depth,
+    critical_detritus, half_sedimentation_tke, convertN, convertP.  ``head_compat`` reproduces the HEAD
+    revision's detritus / phosphate branches (``msed_set_compat``, include/msed.h)."""
+
+    IMPORT_NAMES = {
+        "temperature": ("temperature_in_water",),                                                   # :351
+        "par": ("photosynthetically_active_radiation_in_water",
+                "downwelling_photosynthetic_radiative_flux_in_water"),                              # :331-332
+        "oxygen": ("concentration_of_dissolved_oxygen_in_water", "oxygen_in_water", "dissolved_oxygen_oxy_in_water",
+                   "hzg_ecosmo_oxy_in_water", "dissolved_oxygen_in_water"),                         # :652-656
+        "odu": ("dissolved_reduced_substances_odu_in_water", "dissolved_reduced_substances_in_water"),   # :697-698
+        "detN": ("detritus_at_soil_surface", "detritus_in_water", "detN_at_soil_surface", "detN_in_water",
+                 "Detritus_Nitrogen_detN_at_soil_surface", "Detritus_Nitrogen_detN_in_water",
+                 "hzg_ecosmo_det_at_soil_surface", "hzg_ecosmo_det_in_water"),                      # :923-930
+        "detC": ("Detritus_Carbon_detC_at_soil_surface", "Detritus_Carbon_detC_in_water"),          # :1027-1028
+        "detP": ("detP_in_water", "Detritus_Phosphorus_detP_in_water"),                             # :1530-1531
+        "detP_z_velocity": ("detP_z_velocity_in_water", "Detritus_Phosphorus_detP_z_velocity_in_water"),  # :1604-1605
+        "nitrate": ("nitrate_in_water",),                                                           # :1655
+        "DIN": ("nutrients_in_water", "DIN_in_water", "Dissolved_Inorganic_Nitrogen_DIN_nutN_in_water"),  # :1685-1687
+        "ammonium": ("ammonium_in_water", "dissolved_ammonium_nh3_in_water"),                       # :1725-1726
+        "DIP": ("DIP_in_water", "phosphate_in_water", "Dissolved_Inorganic_Phosphorus_DIP_nutP_in_water"),  # :1988-1990
+    }
+    # looked up in the EXPORT state: the sediment side of the coupling holds them (:1126, :1164-1165)
+    EXPORT_SIDE_NAMES = {
+        "water_depth": ("water_depth_at_soil_surface",),
+        "tke": ("turbulent_kinetic_energy_at_soil_surface", "turbulent_diffusivity_of_momentum_at_soil_surface"),
+    }
+
+    def __init__(self, sed: SedimentDriver, head_compat: bool = False, **namelist):
+        self.sed = sed
+        self.namelist = namelist
+        self.head_compat = head_compat
+
+    def run(self, import_state: State, export_state: Optional[State] = None, fill_export: bool = False) -> int:
+        fields = {}
+        for key, names in self.IMPORT_NAMES.items():
+            n = _first(import_state, names)
+            if n is not None:
+                fields[key] = _bottom(import_state[n])
+        n = _first(import_state, self.IMPORT_NAMES["detN"])
+        if n is None:           # "skip the rest of this routine" (:919-921): nothing is transferred
+            return ESMF_SUCCESS
+        # the velocity field carries the detritus field's name with z_velocity spliced in (:961-972)
+        for suffix in ("_in_water", "_at_soil_surface"):
+            if n.endswith(suffix):
+                vname = n[:-len(suffix)] + "_z_velocity" + suffix
+                break
+        if import_state.get(vname) is None:
+            raise ComponentError(ESMF_RC_NOT_FOUND, f"pelagic_soil_connector: no {vname}")
+        fields["detN_z_velocity"] = _bottom(import_state[vname])
+        if "temperature" not in fields:
+            raise ComponentError(ESMF_RC_NOT_FOUND, "pelagic_soil_connector: no temperature_in_water")
+        if not any(k in fields for k in ("nitrate", "ammonium", "DIN")):        # rc = ESMF_RC_NOT_FOUND, :1846
+            raise ComponentError(ESMF_RC_NOT_FOUND, "pelagic_soil_connector: none of nitrate, ammonium, DIN")
+        for key, names in self.EXPORT_SIDE_NAMES.items():
+            e = _first(export_state or {}, names)
+            if e is not None:
+                fields[key] = _bottom(export_state[e])
+        self.sed.set_compat(p2s_head=self.head_compat)
+        self.sed.pelagic_soil_connector(params=self.namelist, **fields)
         if fill_export and export_state is not None:
             bdys, fluxes = self.sed.bdys, self.sed.fluxes
             export_state["temperature_at_soil_surface"] = bdys[:, :, 0].copy()

@@ -341,6 +341,51 @@ class SedimentDriver:
         self._check(self._lib.msed_soil_pelagic_connector(self._h, C.byref(par), C.byref(out)))
         return res
 
+    def pelagic_soil_connector(self, params=None, **fields):
+        """``pelagic_soil_connector`` Run (src/mediators/pelagic_soil_connector.F90:176-2122) fused with
+        ``get_boundary_conditions``.  Keyword arguments are the bottom-layer pelagic fields (temperature, detN,
+        detN_z_velocity and one of nitrate / ammonium / DIN required; par, oxygen, odu, detC, detP,
+        detP_z_velocity, DIP, water_depth, tke optional); ``params``: namelist entries that differ from the
+        module defaults (:38-46)."""
+        par = _abi.PelagicSoilParams()
+        self._check(self._lib.msed_pelagic_soil_params_defaults(C.byref(par)))
+        for k, v in (params or {}).items():
+            if not hasattr(par, k):
+                raise AttributeError(f"msed_pelagic_soil_params has no field {k!r}")
+            setattr(par, k, float(v))
+        st, keep = _abi.PelagicSoilState(), []
+        for name, arr in fields.items():
+            if not hasattr(st, name):
+                raise AttributeError(f"msed_pelagic_soil_state has no field {name!r}")
+            if arr is not None:
+                a = _f64(arr, self.shape2d, name)
+                keep.append(a)
+                setattr(st, name, _ptr(a))
+        self._check(self._lib.msed_pelagic_soil_connector(self._h, C.byref(st), C.byref(par)))
+
+    def set_compat(self, p2b_oxygen_last_cell: bool = False, p2s_head: bool = False):
+        """Reference quirks that are not reproduced by default (``msed_set_compat``)."""
+        flags = (_abi.COMPAT_P2B_OXYGEN_LAST_CELL if p2b_oxygen_last_cell else 0) | \
+                (_abi.COMPAT_P2S_HEAD if p2s_head else 0)
+        self._check(self._lib.msed_set_compat(self._h, flags))
+
+    # -- whole-domain diagnostics ---------------------------------------------------------------
+    def diagnostics(self, reduce_over_ranks: bool = False):
+        """(bed_flux_sum[nvar], inventory[nvar]) over the wet columns (``msed_diagnostics``)."""
+        b, inv = np.zeros(NVAR), np.zeros(NVAR)
+        self._check(self._lib.msed_diagnostics(self._h, _ptr(b), _ptr(inv), int(bool(reduce_over_ranks))))
+        return b, inv
+
+    def state_checksum(self, global_ncol: int = None, col_offset: int = None):
+        """Tiling-independent checksum of the state: (weighted sum mod 2^64, xor) as Python ints."""
+        if global_ncol is None:
+            global_ncol = self.inum * self.jnum
+        if col_offset is None:
+            col_offset = self.inum * int(self.cfg.j_offset)
+        out = (C.c_uint64 * 2)()
+        self._check(self._lib.msed_state_checksum(self._h, int(global_ncol), int(col_offset), out))
+        return int(out[0]), int(out[1])
+
     # -- execution / multi-GPU ---------------------------------------------------------------
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.msed_set_stream(self._h, C.c_void_p(cuda_stream)))
@@ -401,8 +446,54 @@ def spinup_column(cfg: Config, bdys1d, fluxes1d, nsteps: int, method: int = ADAP
     return out, info
 
 
+def spinup_batch(cfg: Config, bdys1d, fluxes1d, nsteps: int, method: int = ADAPTIVE_EULER, members=None):
+    """1-D pre-simulation of a batch of members in one launch (``msed_spinup_batch``).  ``bdys1d`` is
+    (nmembers, nvar+1), ``fluxes1d`` (nmembers, nvar); ``members``: optional list of dicts overriding the
+    reaction parameters / ``initial_value`` of ``cfg`` per member.  Returns conc(nmembers,1,knum,nvar) and
+    a list of per-member StepInfo."""
+    b = np.asfortranarray(np.asarray(bdys1d, dtype=np.float64))
+    f = np.asfortranarray(np.asarray(fluxes1d, dtype=np.float64))
+    P = b.shape[0]
+    if b.shape != (P, NVAR + 1) or f.shape != (P, NVAR):
+        raise ValueError("spinup_batch: bdys1d must be (nmembers, nvar+1), fluxes1d (nmembers, nvar)")
+    mem = None
+    if members is not None:
+        if len(members) != P:
+            raise ValueError("spinup_batch: one member entry per row of bdys1d")
+        mem = (_abi.SpinupMember * P)()
+        for m, over in enumerate(members):
+            for name, _ in _abi.SpinupMember._fields_:
+                if name == "initial_value":
+                    src = over.get(name, cfg.initial_value)
+                    for n in range(NVAR):
+                        mem[m].initial_value[n] = float(src[n])
+                else:
+                    setattr(mem[m], name, float(over.get(name, getattr(cfg, name))))
+            unknown = set(over) - {n for n, _ in _abi.SpinupMember._fields_}
+            if unknown:
+                raise AttributeError(f"msed_spinup_member has no field(s) {sorted(unknown)}")
+    out = np.zeros((P, 1, cfg.knum, NVAR), order="F")
+    infos = (StepInfo * P)()
+    lib = _abi.load()
+    rc = lib.msed_spinup_batch(C.byref(cfg), P, mem, _ptr(b), _ptr(f), int(nsteps), int(method), _ptr(out), infos)
+    if rc:
+        raise MsedError(rc, (lib.msed_last_error(None) or b"").decode())
+    return out, list(infos)
+
+
+def measure_fp64_peak(device: int = -1) -> float:
+    """fp64 pipe throughput of the device in TFLOP/s (2 x FMA/s), ``msed_measure_fp64_peak``."""
+    v = C.c_double()
+    lib = _abi.load()
+    rc = lib.msed_measure_fp64_peak(int(device), C.byref(v))
+    if rc:
+        raise MsedError(rc, (lib.msed_last_error(None) or b"").decode())
+    return v.value
+
+
 __all__ = [
-    "SedimentDriver", "ode_solver", "default_config", "spinup_column", "nccl_unique_id",
+    "SedimentDriver", "ode_solver", "default_config", "spinup_column", "spinup_batch", "measure_fp64_peak",
+    "nccl_unique_id",
     "STATE_NAMES", "VARIABLE_NAMES", "PARTICULATE", "EULER", "RUNGE_KUTTA_4", "ADAPTIVE_EULER",
     "RUNGE_KUTTA_4_38", "MODEL_OMEXDIA_P", "MODEL_NONE", "MODEL_TEST_SOLVER",
 ]

@@ -381,11 +381,11 @@ void osed_get_rhs(osed_rhs_driver *self, double *rhs)
 
     /* environmental properties :593-605 */
     for (int k = 0; k < K; ++k) {
-        for (size_t c = 0; c < n2; ++c) {
-            double sum = 0.0;               /* sum(dz(:,:,1:k-1),dim=3) ; 0 for k==1 */
-            for (int m = 0; m < k; ++m) sum += s->dz[c + n2 * m];
-            cumdepth[c] = sum;
-        }
+        /* sum(dz(:,:,1:k-1),dim=3) ; 0 for k==1.  Layers outermost, columns unit-stride -- the order
+         * gfortran gives the intrinsic; per column the terms are still added for m = 1..k-1 */
+        for (size_t c = 0; c < n2; ++c) cumdepth[c] = 0.0;
+        for (int m = 0; m < k; ++m)
+            for (size_t c = 0; c < n2; ++c) cumdepth[c] += s->dz[c + n2 * m];
         for (size_t c = 0; c < n2; ++c)
             if (!(s->base.mask[c + n2 * k] > 0)) {
                 s->temp3d[c + n2 * k] = s->bdys[c];
@@ -742,6 +742,220 @@ double osed_bench_tiled(int inum, int jnum, int knum, double dzmin, const osed_s
     return err ? -1.0 : (t1 - t0);
 }
 
+/* ---- fused-loop CPU variant ------------------------------------ */
+
+/* One attempt of the adaptive-Euler / Euler step for the columns [c0, c0+nb) of a tile, walking each
+ * column once: boundary flux, interface fluxes, omexdia_p rates, dC, c1 = c + dt*rhs and the
+ * relative-change test in a single pass (the reference needs >= 40 whole-array passes for the same
+ * arithmetic, get_rhs :575-717 + ode_solver :104-140).  Same formulas as osed_get_rhs / osed_diff3d,
+ * per column instead of per array; columns are the innermost (SIMD) index.  Hot configuration only:
+ * bioturbation_profile != 3, BcUp(particulate) = 1, BcUp(dissolved) in {1,2,3}, BcDown = 3.
+ * Returns 1 if some cell violates relative_change_min. */
+#define FB 8   /* columns per block: one AVX-512 / two AVX2 vectors of doubles */
+static int fused_attempt_block(const osed_sed *s, const double *cin, double *cout, size_t c0, int nb,
+                               double dt, double fac, double *flux_out)
+{
+    const int K = s->base.knum;
+    const size_t n2 = N2(s), n3 = N3(s);
+    const osed_omexdia_params *p = &s->p;
+    const double relaxO2 = 0.04, T0 = 288.15;
+    const double E_a = 0.1 * log(1.5) * T0 * (T0 + 10.0);
+    const double rLabile = p->rLabile / 86400.0, rSemilabile = p->rSemilabile / 86400.0;
+    const double rnit = p->rnit / 86400.0, rODUox = p->rODUox / 86400.0, cmax = p->CprodMax / 86400.0;
+    double cpart[FB], cdiss[FB], fT[FB], F[8][FB], Fn[8][FB], cc[8][FB], cn[8][FB], porc[FB], porn[FB];
+    int viol = 0;
+    for (int b = 0; b < nb; ++b) {
+        const double temp = s->bdys[c0 + b];
+        const double f_T = exp(-4500.0 * (1.0 / (temp + 273.0) - (1.0 / 288.0)));      /* :648 */
+        cpart[b] = s->bioturbation * f_T / 86400.0 / 10000.0;                           /* :652 */
+        cdiss[b] = (s->diffusivity + temp * 0.035) / 86400.0 / 10000.0;                 /* :682 */
+        fT[b] = exp(-E_a * (1.0 / (temp + 273.15) - 1.0 / T0));
+    }
+    for (int b = nb; b < FB; ++b) { cpart[b] = cdiss[b] = 0.0; fT[b] = 1.0; }
+    /* layer 1 and the upper boundary (diff3d :782-789) */
+    for (int b = 0; b < FB; ++b) {
+        const size_t c = c0 + (b < nb ? b : 0);
+        porc[b] = s->porosity[c];
+        for (int n = 0; n < 8; ++n) cc[n][b] = cin[c + n3 * n];
+        const double Dp = cpart[b] * (1.0 - porc[b]) * s->bioturbation_factor[c];
+        const double Dd = Dp + cdiss[b] * porc[b];
+        for (int n = 0; n < 8; ++n) {
+            const int part = s->particulate[n];
+            const int bc = part ? 1 : s->bcup_dissolved_variables;
+            double f = 0.0;
+            if (bc == 1) f = s->fluxes[c + n2 * n];
+            else if (bc == 2) {
+                const double C1 = part ? cc[n][b] * porc[b] : cc[n][b];
+                f = -(part ? Dp : Dd) * (C1 - s->bdys[c + n2 * (n + 1)]) / s->dz[c];
+            }
+            F[n][b] = f;
+            if (!part && b < nb) flux_out[c + n2 * n] = f;                              /* :692 */
+        }
+    }
+    for (int k = 0; k < K; ++k) {
+        const int has_next = k + 1 < K;
+        if (has_next) {
+#pragma omp simd
+            for (int b = 0; b < FB; ++b) {
+                const size_t c = c0 + (b < nb ? b : 0);
+                porn[b] = s->porosity[c + n2 * (k + 1)];
+                const double intf = 0.5 * (porc[b] + porn[b]);
+                const double Dp = cpart[b] * (1.0 - intf) * s->bioturbation_factor[c + n2 * (k + 1)];
+                const double Dd = Dp + cdiss[b] * intf;
+                const double rdzc = 1.0 / s->dzc[c + n2 * k];
+                for (int n = 0; n < 8; ++n) cn[n][b] = cin[c + n2 * (k + 1) + n3 * n];
+                for (int n = 0; n < 3; ++n) Fn[n][b] = -Dp * (cn[n][b] * porn[b] - cc[n][b] * porc[b]) * rdzc;
+                for (int n = 3; n < 8; ++n) Fn[n][b] = -Dd * (cn[n][b] - cc[n][b]) * rdzc;
+            }
+        } else {
+            for (int n = 0; n < 8; ++n)
+                for (int b = 0; b < FB; ++b) Fn[n][b] = 0.0;
+        }
+#pragma omp simd reduction(| : viol)
+        for (int b = 0; b < FB; ++b) {
+            const size_t c = c0 + (b < nb ? b : 0);
+            const double ldetC = cc[0][b], sdetC = cc[1][b], detP = cc[2][b], po4 = cc[3][b];
+            const double no3 = cc[4][b], nh3 = cc[5][b], oxy = cc[6][b], odu = cc[7][b];
+            const double Oxicminlim = oxy / (oxy + p->ksO2oxic + relaxO2 * (nh3 + odu));
+            const double Denitrilim = (1.0 - oxy / (oxy + p->kinO2denit)) * no3 / (no3 + p->ksNO3denit);
+            const double Anoxiclim = (1.0 - oxy / (oxy + p->kinO2anox)) * (1.0 - no3 / (no3 + p->kinNO3anox));
+            const double Rescale = 1.0 / (Oxicminlim + Denitrilim + Anoxiclim);
+            const double CprodL = rLabile * ldetC, CprodS = rSemilabile * sdetC;
+            double Cprod = CprodL + CprodS;
+            Cprod = Cprod > cmax ? cmax : Cprod;
+            const double Nprod = CprodL * p->NCrLdet + CprodS * p->NCrSdet;
+            const double radsP = p->PAds * rSemilabile * po4 * (odu > p->PAdsODU ? odu : p->PAdsODU);
+            const double Pprod = rLabile * (1.0 - Oxicminlim) * detP;
+            const double OxicMin = Cprod * Oxicminlim * Rescale, Denitrific = Cprod * Denitrilim * Rescale;
+            const double AnoxicMin = Cprod * Anoxiclim * Rescale;
+            const double Nitri = fT[b] * rnit * nh3 * oxy / (oxy + p->ksO2nitri + relaxO2 * (ldetC + odu));
+            const double OduOx = fT[b] * rODUox * odu * oxy / (oxy + p->ksO2oduox + relaxO2 * (nh3 + ldetC));
+            double r[8];
+            r[0] = -fT[b] * CprodL;  r[1] = -fT[b] * CprodS;
+            r[2] = fT[b] * (radsP - Pprod);  r[3] = fT[b] * (Pprod - radsP);
+            r[4] = -0.8 * Denitrific + Nitri;  r[5] = (Nprod - Nitri) / (1.0 + p->NH3Ads);
+            r[6] = -OxicMin - 2.0 * Nitri - OduOx;  r[7] = AnoxicMin - OduOx;
+            const double rpd = 1.0 / (porc[b] * s->dz[c + n2 * k]);     /* dC*(1-por)/por == dF/(por*dz) */
+            for (int n = 0; n < 8; ++n) {
+                const double rhs = (F[n][b] - Fn[n][b]) * rpd + r[n];
+                const double c1 = cc[n][b] + dt * rhs;
+                viol |= (c1 - fac * cc[n][b]) < 0.0;
+                if (b < nb) cout[c + n2 * k + n3 * n] = c1;
+                F[n][b] = Fn[n][b];
+                cc[n][b] = cn[n][b];
+            }
+            porc[b] = porn[b];
+        }
+    }
+    return viol;
+}
+
+/* Same contract as osed_bench_tiled, fused loop structure: every attempt reads the state once and writes
+ * it once; per tile the accept decision is the reference's whole-tile any() (solver_library.F90:121). */
+double osed_bench_fused(int inum, int jnum, int knum, double dzmin, const osed_sed_nml *nml,
+                        const osed_omexdia_params *p, const int *mask2d, double *conc,
+                        const double *bdys, const double *fluxes_in, double dt, int method,
+                        int nsteps, double dt_min, double relative_change_min,
+                        int bcup_dissolved, int nthreads, long *subcycles)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > jnum) nthreads = jnum;
+    if (method != OSED_EULER && method != OSED_ADAPTIVE_EULER) return -1.0;
+    if (nml->bioturbation_profile == 3 || nml->distributed_pom_flux) return -1.0;
+    const int nvar = OSED_NVAR_OMEXDIA;
+    osed_sed *tiles = (osed_sed *)calloc(nthreads, sizeof(osed_sed));
+    double **ta = (double **)calloc(nthreads, sizeof(double *)), **tb = (double **)calloc(nthreads, sizeof(double *));
+    int *j0 = (int *)calloc(nthreads + 1, sizeof(int));
+    long *subs = (long *)calloc(nthreads, sizeof(long));
+    for (int t = 0; t <= nthreads; ++t) j0[t] = (int)((long)jnum * t / nthreads);
+    const size_t n2 = (size_t)inum * jnum;
+    for (int t = 0; t < nthreads; ++t) {
+        osed_sed *s = &tiles[t];
+        const int jl = j0[t + 1] - j0[t];
+        const size_t n2l = (size_t)inum * jl, n3l = n2l * knum;
+        osed_init_grid(s, inum, jl, knum, dzmin);
+        int *mask3 = (int *)calloc(n3l ? n3l : 1, sizeof(int));
+        if (mask2d)
+            for (int k = 0; k < knum; ++k)
+                for (size_t c = 0; c < n2l; ++c) mask3[c + n2l * k] = mask2d[c + (size_t)inum * j0[t]];
+        osed_initialize(s, nml, OSED_MODEL_OMEXDIA_P, p, mask3);
+        free(mask3);
+        s->bcup_dissolved_variables = bcup_dissolved;
+        ta[t] = dalloc(n3l * nvar, 0.0);
+        tb[t] = dalloc(n3l * nvar, 0.0);
+        s->bdys = dalloc(n2l * (nvar + 1), 0.0);
+        s->fluxes = dalloc(n2l * nvar, 0.0);
+        for (int n = 0; n < nvar; ++n)
+            for (int k = 0; k < knum; ++k)
+                memcpy(ta[t] + n2l * (k + (size_t)knum * n),
+                       conc + (size_t)inum * j0[t] + n2 * (k + (size_t)knum * n), n2l * sizeof(double));
+        memcpy(tb[t], ta[t], n3l * nvar * sizeof(double));   /* masked columns stay put in both buffers */
+        for (int n = 0; n < nvar + 1; ++n)
+            memcpy(s->bdys + n2l * n, bdys + (size_t)inum * j0[t] + n2 * n, n2l * sizeof(double));
+        for (int n = 0; n < nvar; ++n)
+            memcpy(s->fluxes + n2l * n, fluxes_in + (size_t)inum * j0[t] + n2 * n, n2l * sizeof(double));
+    }
+    const double fac = 1.0 + relative_change_min;
+    double t0 = wall_seconds();
+#pragma omp parallel for num_threads(nthreads) schedule(static, 1)
+    for (int t = 0; t < nthreads; ++t) {
+        osed_sed *s = &tiles[t];
+        const size_t n2l = N2(s), n3l = N3(s);
+        double *a = ta[t], *b = tb[t];
+        for (int st = 0; st < nsteps; ++st) {
+            double dt_int = 0.0, dt_red = dt;
+            while (dt_int < dt) {
+                int viol = 0;
+                for (size_t c0 = 0; c0 < n2l; c0 += FB) {
+                    int nb = (int)(n2l - c0 < FB ? n2l - c0 : FB), wet = 0;
+                    for (int q = 0; q < nb; ++q) wet |= !(s->base.mask[c0 + q] > 0);
+                    if (!wet) continue;
+                    if (nb == FB) {
+                        int all = 1;
+                        for (int q = 0; q < nb; ++q) all &= !(s->base.mask[c0 + q] > 0);
+                        if (all) { viol |= fused_attempt_block(s, a, b, c0, nb, dt_red, fac, s->fluxes); continue; }
+                    }
+                    for (int q = 0; q < nb; ++q)    /* ragged or partly masked block: column by column */
+                        if (!(s->base.mask[c0 + q] > 0))
+                            viol |= fused_attempt_block(s, a, b, c0 + q, 1, dt_red, fac, s->fluxes);
+                }
+                if (method == OSED_ADAPTIVE_EULER && viol && dt_red > dt_min) {
+                    dt_red *= 0.25;
+                    subs[t]++;
+                } else {
+                    double *tmp = a; a = b; b = tmp;
+                    dt_int += (method == OSED_ADAPTIVE_EULER) ? dt_red : dt;
+                }
+            }
+            /* check_NaN + clip (component :1718-1732) in the same sweep over the accepted state */
+            for (int n = 0; n < nvar; ++n)
+                for (size_t q = 0; q < n3l; ++q) {
+                    if (s->base.mask[q] > 0) continue;
+                    double *v = &a[q + n3l * n];
+                    if (*v < s->p.minimum[n]) *v = s->p.minimum[n];
+                }
+        }
+        ta[t] = a; tb[t] = b;
+    }
+    double t1 = wall_seconds();
+    long sub = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        osed_sed *s = &tiles[t];
+        const int jl = j0[t + 1] - j0[t];
+        const size_t n2l = (size_t)inum * jl;
+        for (int n = 0; n < nvar; ++n)
+            for (int k = 0; k < knum; ++k)
+                memcpy(conc + (size_t)inum * j0[t] + n2 * (k + (size_t)knum * n),
+                       ta[t] + n2l * (k + (size_t)knum * n), n2l * sizeof(double));
+        sub += subs[t];
+        free(s->bdys); free(s->fluxes); free(ta[t]); free(tb[t]);
+        osed_finalize(s);
+    }
+    if (subcycles) *subcycles = sub;
+    free(tiles); free(ta); free(tb); free(j0); free(subs);
+    return t1 - t0;
+}
+
 /* ---- flat handle API for the Python test harness ------------------------------------------ */
 
 typedef struct {
@@ -862,11 +1076,14 @@ void osedpy_test_solver(int inum, int jnum, int knum, int nvar, double *conc, do
  * in[]: 0 oxygen 1 detN 2 detN_wz 3 detC 4 detP 5 detP_wz 6 nitrate 7 ammonium 8 DIN 9 DIP (NULL = absent)
  * csurf(n2,8), wz(n2,3) out.  The oxygen/odu split follows the per-cell intent of :344-349 (the
  * reference assigns the whole arrays inside the i,j loop). */
-void osed_pelagic_benthic_coupler(size_t n2, const double *const in[10], double *csurf, double *wz)
+void osed_pelagic_benthic_coupler_ex(size_t n2, const double *const in[10], double *csurf, double *wz,
+                                     int oxy_last_cell)
 {
     const double NC_fdet = 0.20, NC_sdet = 0.04, sinking_factor = 0.3;   /* :298,:301-302 */
     for (size_t c = 0; c < n2; ++c) {
-        double o2 = in[0][c], detN = in[1][c], vN = in[2][c];
+        /* oxy_last_cell: the reference assigns the WHOLE oxy/odu arrays inside its i,j loop (:344-349), which
+         * leaves every cell with the value of the last one */
+        double o2 = in[0][oxy_last_cell ? n2 - 1 : c], detN = in[1][c], vN = in[2][c];
         double CN_det = in[3] ? in[3][c] / detN : 106.0 / 16.0;                     /* :379-394 */
         double fac_fdet = (1.0 - NC_sdet * CN_det) / (NC_fdet - NC_sdet);           /* :395 */
         double fac_sdet = (1.0 - NC_fdet * CN_det) / (NC_sdet - NC_fdet);           /* :396 */
@@ -883,6 +1100,11 @@ void osed_pelagic_benthic_coupler(size_t n2, const double *const in[10], double 
         wz[c + n2 * 1] = sinking_factor * vN;                                       /* :408 */
         wz[c + n2 * 2] = sinking_factor * (in[5] ? in[5][c] : vN);                  /* :427-431 */
     }
+}
+
+void osed_pelagic_benthic_coupler(size_t n2, const double *const in[10], double *csurf, double *wz)
+{
+    osed_pelagic_benthic_coupler_ex(n2, in, csurf, wz, 0);
 }
 
 /* benthic_pelagic_coupler Run, src/mediators/benthic_pelagic_coupler.F90:211-282.
@@ -940,3 +1162,83 @@ void osed_soil_pelagic_connector(size_t n2, const double *up, double dinflux_con
         out[c + n2 * 8] = detP;
     }
 }
+
+/* pelagic_soil_connector Run, src/mediators/pelagic_soil_connector.F90:176-2122 (2-D export fields, bottom layer
+ * of the pelagic fields).  in[]: 0 oxygen 1 odu 2 detN 3 detN_z_velocity 4 detC 5 detP 6 detP_z_velocity 7 nitrate
+ * 8 ammonium 9 DIN 10 DIP 11 water_depth 12 tke (NULL = absent).  par[]: sinking_factor sinking_factor_min NC_ldet
+ * NC_sdet half_sedimentation_depth half_sedimentation_tke critical_detritus convertN convertP.
+ * csurf(n2,8) in the sediment's variable order, wz(n2,3); rows the connector does not write are left alone
+ * (oxygen/odu without either import field; the carbon velocities in head_compat mode).
+ * head_compat = 0: what the file is written to compute (each export field its own expression, the velocity
+ * fields sinking_factor*fac_env*velocity); 1: what the HEAD revision computes where that is defined -- the
+ * "velocity" blocks fetch fieldList(1), the CONCENTRATION field, a second time and overwrite it with
+ * sinking_factor*fac_env*detN (:1291-1295, :1351-1355); the phosphorus velocity gets the same expression
+ * (:1595-1597) unless a detP velocity is imported (:1626-1630); phosphate is recomputed from DIN although DIP
+ * was imported (:2092-2094). */
+void osed_pelagic_soil_connector(size_t n2, const double *const in[13], const double par[9], int head_compat,
+                                 double *csurf, double *wz)
+{
+    const double sinking_factor = par[0], sinking_factor_min = par[1], NC_ldet = par[2], NC_sdet = par[3];
+    const double hsd = par[4], hst = par[5], crit = par[6], convertN = par[7], convertP = par[8];
+    const double *oxy = in[0], *odu = in[1], *detN = in[2], *vdetN = in[3], *detC = in[4], *detP = in[5];
+    const double *vdetP = in[6], *nit = in[7], *amm = in[8], *din = in[9], *dip = in[10], *depth = in[11], *tke = in[12];
+    const int hasN = nit != NULL, hasA = amm != NULL, hasD = din != NULL;
+    for (size_t c = 0; c < n2; ++c) {
+        double CN_det = 106.0 / 16.0;                                                   /* :1022 */
+        if (detC) CN_det = detC[c] / (1E-5f + detN[c]);                                 /* :1063 */
+        double fac_ldet = (1.0 - NC_sdet * CN_det) / (NC_ldet - NC_sdet);               /* :1082 */
+        if (fac_ldet > CN_det) fac_ldet = CN_det;                                       /* :1084-1087 */
+        if (fac_ldet < 0.0) fac_ldet = 0.0;                                             /* :1088-1091 */
+        double fac_sdet = CN_det - fac_ldet;                                            /* :1095 */
+        double fac_env = 1.0;                                                           /* :1097 */
+        if (depth && hsd > 1E-3f)                                                       /* :1150-1155 */
+            fac_env = fac_env * (depth[c] * depth[c]) / (depth[c] * depth[c] + hsd * hsd);
+        if (tke && hst < 9E9f) fac_env = fac_env * hst / (tke[c] + hst);                /* :1189-1191 */
+        fac_env = fac_env + sinking_factor_min / sinking_factor;                        /* :1204 */
+        if (detC && crit > 1E-3f && crit < 9E9f) {                                      /* :1215-1227 */
+            double x = detC[c] / crit, x2 = x * x;
+            fac_env = fac_env * 1.0 / (1.0 + x2 * x2);
+        }
+        if (!head_compat) {
+            csurf[c + n2 * 0] = fac_ldet * convertN * detN[c];                          /* :1282-1284 */
+            csurf[c + n2 * 1] = fac_sdet * convertN * detN[c];                          /* :1342-1344 */
+            wz[c + n2 * 0] = sinking_factor * fac_env * vdetN[c];
+            wz[c + n2 * 1] = sinking_factor * fac_env * vdetN[c];
+            wz[c + n2 * 2] = sinking_factor * fac_env * (vdetP ? vdetP[c] : vdetN[c]);
+        } else {
+            csurf[c + n2 * 0] = sinking_factor * fac_env * detN[c];                     /* :1293-1295 */
+            csurf[c + n2 * 1] = sinking_factor * fac_env * detN[c];                     /* :1353-1355 */
+            wz[c + n2 * 2] = sinking_factor * fac_env * (vdetP ? vdetP[c] : detN[c]);   /* :1595-1597, :1628-1630 */
+        }
+        csurf[c + n2 * 2] = detP ? detP[c] : 1.0 / 16.0 * convertN * detN[c];           /* :1521-1523, :1557-1559 */
+        double a_out, n_out;
+        if (hasA) a_out = convertN * amm[c];                                            /* :1816-1818 */
+        else if (hasD && hasN) a_out = convertN * (din[c] - nit[c]);                    /* :1821-1823 */
+        else if (hasD) a_out = convertN * 0.5 * din[c];                                 /* :1832-1834 */
+        else a_out = convertN * nit[c];                                                 /* :1843-1845 */
+        if (hasN) n_out = convertN * nit[c];                                            /* :1930-1932 */
+        else if (hasA && hasD) n_out = convertN * (din[c] - amm[c]);                    /* :1939-1943 */
+        else if (hasD) n_out = convertN * 0.5 * din[c];                                 /* :1952-1954 */
+        else n_out = convertN * amm[c];                                                 /* :1963-1965 */
+        csurf[c + n2 * 4] = n_out;
+        csurf[c + n2 * 5] = a_out;
+        double din_eff;                                                                 /* :2040-2070 */
+        if (hasD) din_eff = din[c];
+        else if (hasA && hasN) din_eff = nit[c] + amm[c];
+        else if (hasA) din_eff = 2 * amm[c];
+        else din_eff = 2 * nit[c];
+        if (dip && !(head_compat && (hasD || hasA || hasN))) csurf[c + n2 * 3] = convertP * dip[c];
+        else csurf[c + n2 * 3] = convertP * (1.0 / 16.0 * convertN * din_eff);          /* :2092-2094 */
+        if (oxy && odu) {                                                               /* :806-807 */
+            csurf[c + n2 * 6] = oxy[c];
+            csurf[c + n2 * 7] = odu[c];
+        } else if (odu) {                                                               /* :827-828 */
+            csurf[c + n2 * 6] = fmax(0.0, -odu[c]);
+            csurf[c + n2 * 7] = fmax(0.0, odu[c]);
+        } else if (oxy) {                                                               /* intent of :849-850 */
+            csurf[c + n2 * 6] = fmax(0.0, oxy[c]);
+            csurf[c + n2 * 7] = fmax(0.0, -oxy[c]);
+        }
+    }
+}
+

@@ -147,8 +147,23 @@ double osed_bench_tiled(int inum, int jnum, int knum, double dzmin, const osed_s
                         int nsteps, double dt_min, double relative_change_min,
                         int bcup_dissolved, int nthreads, long *subcycles);
 
+/* fused-loop CPU variant of the same step: one pass over the state per attempt
+ * instead of the reference's whole-array passes; same contract and arguments as osed_bench_tiled.
+ * Euler / adaptive Euler, bioturbation_profile != 3, no distributed POM flux; <0 otherwise. */
+double osed_bench_fused(int inum, int jnum, int knum, double dzmin, const osed_sed_nml *nml,
+                        const osed_omexdia_params *p, const int *mask2d, double *conc,
+                        const double *bdys, const double *fluxes_in, double dt, int method,
+                        int nsteps, double dt_min, double relative_change_min,
+                        int bcup_dissolved, int nthreads, long *subcycles);
+
 /* pelagic <-> soil couplers (src/mediators/pelagic_benthic_coupler.F90, benthic_pelagic_coupler.F90) */
 void osed_pelagic_benthic_coupler(size_t n2, const double *const in[10], double *csurf, double *wz);
+/* oxy_last_cell != 0: the whole-array assignment of :344-349 as written (every cell = the last cell's value) */
+void osed_pelagic_benthic_coupler_ex(size_t n2, const double *const in[10], double *csurf, double *wz,
+                                     int oxy_last_cell);
+/* pelagic_soil_connector Run (src/mediators/pelagic_soil_connector.F90:176-2122); see msed_oracle.c */
+void osed_pelagic_soil_connector(size_t n2, const double *const in[13], const double par[9], int head_compat,
+                                 double *csurf, double *wz);
 void osed_benthic_pelagic_coupler(size_t n2, const double *up, double dinflux_const, double dipflux_const,
                                   double convertN, double NC_fdet, double NC_sdet, double *out);
 /* soil_pelagic_connector Run (src/mediators/soil_pelagic_connector.F90:179-981); out(n2,9) */

@@ -90,7 +90,12 @@ def load(fast: bool = False):
                                      C.POINTER(OmexdiaParams), C.POINTER(C.c_int), dp, dp, dp,
                                      C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                      C.c_int, C.POINTER(C.c_long)]
+    lib.osed_bench_fused.restype = C.c_double
+    lib.osed_bench_fused.argtypes = lib.osed_bench_tiled.argtypes
     lib.osed_pelagic_benthic_coupler.argtypes = [C.c_size_t, C.POINTER(dp), dp, dp]
+    lib.osed_pelagic_benthic_coupler_ex.argtypes = [C.c_size_t, C.POINTER(dp), dp, dp, C.c_int]
+    lib.osed_pelagic_soil_connector.argtypes = [C.c_size_t, C.POINTER(dp), dp, C.c_int, dp, dp]
+    lib.osed_pelagic_soil_connector.restype = None
     lib.osed_soil_pelagic_connector.argtypes = [C.c_size_t, dp, C.c_double, C.c_double, C.c_double, C.c_double,
                                                 C.c_int, C.c_int, dp]
     lib.osed_soil_pelagic_connector.restype = None
@@ -142,6 +147,24 @@ def from_config(cfg):
         init=[cfg.initial_value[n] for n in range(NVAR)],
         minimum=[cfg.minimum[n] for n in range(NVAR)])
     return nml, par
+
+
+def default_config(**kw):
+    """A plain-Python stand-in for the product's ``msed_config`` holding the reference defaults
+    (fabm_sediment_driver.F90:217-231, component :59-67, fabm_sed.nml:51-77), taken from THIS library --
+    for callers that must not load the product (bench.py --impl reference)."""
+    from types import SimpleNamespace
+    nml, par = sed_nml(), omexdia_params()
+    d = {n: getattr(nml, n) for n, _ in SedNml._fields_}
+    d.update({n: getattr(par, n) for n, _ in OmexdiaParams._fields_ if n not in ("init", "minimum")})
+    d.update(inum=1, jnum=1, knum=10, dzmin=0.005, model=MODEL_OMEXDIA_P, dt_min=1.0e-8,
+             relative_change_min=-0.9, bcup_dissolved_variables=2, adaptive_solver_diagnostics=0,
+             initial_value=[par.init[n] for n in range(NVAR)], minimum=[par.minimum[n] for n in range(NVAR)])
+    for k, v in kw.items():
+        if k not in d:
+            raise AttributeError(k)
+        d[k] = v
+    return SimpleNamespace(**d)
 
 
 class OracleSediment:
@@ -300,14 +323,20 @@ def spinup_column(nml, par, knum, dzmin, dt_min, rcm, bdys1d, fluxes1d, nsteps, 
     return out
 
 
-def bench_tiled(cfg, mask2d, conc, bdys, fluxes, dt, method, nsteps, nthreads, native=True):
-    """Times the restated reference CPU path (j-slab tiles, one OpenMP thread per tile)."""
-    if native:
+_native_built = False
+
+
+def bench_tiled(cfg, mask2d, conc, bdys, fluxes, dt, method, nsteps, nthreads, native=True, fused=False):
+    """Times the restated reference CPU path (j-slab tiles, one OpenMP thread per tile).  ``fused``: the
+    fused-loop variant of the same step (one pass over the state per attempt)."""
+    global _native_built
+    if native and not _native_built:
         try:
             build(fast=True, native=True)
         except Exception:
             build(fast=True)
-    _libs.pop("fast", None)
+        _native_built = True
+        _libs.pop("fast", None)
     lib = load(fast=True)
     nml, par = from_config(cfg)
     m = None if mask2d is None else np.asfortranarray(np.asarray(mask2d, dtype=np.int32))
@@ -315,7 +344,8 @@ def bench_tiled(cfg, mask2d, conc, bdys, fluxes, dt, method, nsteps, nthreads, n
     conc = np.asfortranarray(conc, dtype=np.float64)
     b = np.asfortranarray(bdys, dtype=np.float64)
     f = np.asfortranarray(fluxes, dtype=np.float64)
-    secs = lib.osed_bench_tiled(cfg.inum, cfg.jnum, cfg.knum, cfg.dzmin, C.byref(nml), C.byref(par),
+    fn = lib.osed_bench_fused if fused else lib.osed_bench_tiled
+    secs = fn(cfg.inum, cfg.jnum, cfg.knum, cfg.dzmin, C.byref(nml), C.byref(par),
                                 None if m is None else m.ctypes.data_as(C.POINTER(C.c_int)),
                                 _p(conc), _p(b), _p(f), float(dt), int(method), int(nsteps),
                                 cfg.dt_min, cfg.relative_change_min, cfg.bcup_dissolved_variables,
@@ -328,7 +358,38 @@ P2B_FIELDS = ("oxygen", "detN", "detN_z_velocity", "detC", "detP", "detP_z_veloc
 B2P_FIELDS = ("nitrate", "ammonium", "DIN", "DIP", "detN", "detC", "detP", "oxygen")
 
 
-def pelagic_benthic_coupler(shape2d, **fields):
+P2S_FIELDS = ("oxygen", "odu", "detN", "detN_z_velocity", "detC", "detP", "detP_z_velocity", "nitrate", "ammonium",
+              "DIN", "DIP", "water_depth", "tke")
+P2S_PARAMS = ("sinking_factor", "sinking_factor_min", "NC_ldet", "NC_sdet", "half_sedimentation_depth",
+              "half_sedimentation_tke", "critical_detritus", "convertN", "convertP")
+# module defaults, pelagic_soil_connector.F90:38-46 (three of them are default-real literals)
+P2S_DEFAULTS = dict(sinking_factor=0.3, sinking_factor_min=float(np.float32(0.02)), NC_ldet=0.23, NC_sdet=0.01,
+                    half_sedimentation_depth=float(np.float32(0.1)), half_sedimentation_tke=1.0e3,
+                    critical_detritus=60.0, convertN=1.0, convertP=1.0)
+
+
+def pelagic_soil_connector(shape2d, params=None, head_compat=False, csurf0=None, wz0=None, **fields):
+    """Restated pelagic_soil_connector Run: returns (csurf list of 8, wz list of 3 + 5 None).  ``csurf0`` /
+    ``wz0``: previous contents of the export fields (rows the connector leaves alone keep them)."""
+    dp = C.POINTER(C.c_double)
+    n2 = int(np.prod(shape2d))
+    arr, keep = (dp * 13)(), []
+    for i, name in enumerate(P2S_FIELDS):
+        a = fields.get(name)
+        if a is not None:
+            a = np.asfortranarray(np.asarray(a, dtype=np.float64))
+            keep.append(a)
+            arr[i] = _p(a)
+    par = dict(P2S_DEFAULTS)
+    par.update(params or {})
+    pv = np.array([par[k] for k in P2S_PARAMS], dtype=np.float64)
+    cs = np.zeros(tuple(shape2d) + (8,), order="F") if csurf0 is None else np.asfortranarray(csurf0, dtype=np.float64).copy(order="F")
+    wz = np.zeros(tuple(shape2d) + (3,), order="F") if wz0 is None else np.asfortranarray(wz0, dtype=np.float64).copy(order="F")
+    load().osed_pelagic_soil_connector(n2, arr, _p(pv), int(head_compat), _p(cs), _p(wz))
+    return [cs[..., n] for n in range(8)], [wz[..., n] for n in range(3)] + [None] * 5
+
+
+def pelagic_benthic_coupler(shape2d, oxy_last_cell=False, **fields):
     """Restated pelagic_benthic_coupler Run: returns (csurf list of 8, wz list of 3 + 5 None)."""
     dp = C.POINTER(C.c_double)
     n2 = int(np.prod(shape2d))
@@ -341,7 +402,7 @@ def pelagic_benthic_coupler(shape2d, **fields):
             arr[i] = _p(a)
     cs = np.zeros(tuple(shape2d) + (8,), order="F")
     wz = np.zeros(tuple(shape2d) + (3,), order="F")
-    load().osed_pelagic_benthic_coupler(n2, arr, _p(cs), _p(wz))
+    load().osed_pelagic_benthic_coupler_ex(n2, arr, _p(cs), _p(wz), int(oxy_last_cell))
     return [cs[..., n] for n in range(8)], [wz[..., n] for n in range(3)] + [None] * 5
 
 

@@ -327,3 +327,119 @@ def test_check_domain_flags_bad_porosity(gpu):
             with pytest.raises(MsedError) as e:
                 sed.check_domain()
             assert e.value.code == 2 and text in str(e.value)
+
+
+P2S_CASES = [
+    # which pelagic fields exist -> which of the connector's branches run
+    dict(detC=True, detP=True, detP_z_velocity=True, nitrate=True, ammonium=True, DIN=True, DIP=True, oxygen=True,
+         odu=True, water_depth=True, tke=True),                                  # every field
+    dict(DIN=True, oxygen=True),                                                 # NPZD-like: DIN only, oxygen only
+    dict(nitrate=True, DIN=True, odu=True, detC=True, water_depth=True),         # ammonium = DIN - nitrate; odu only
+    dict(ammonium=True, detP=True, tke=True),                                    # nitrate = ammonium; DIN = 2*ammonium
+    dict(nitrate=True, ammonium=True, DIP=True),                                 # neither oxygen nor odu: rows untouched
+]
+
+
+@pytest.mark.parametrize("head", [False, True])
+@pytest.mark.parametrize("present", P2S_CASES)
+def test_pelagic_soil_connector(gpu, oracle, present, head):
+    """pelagic_soil_connector (src/mediators/pelagic_soil_connector.F90:176-2122) fused with
+    get_boundary_conditions against the restatement, for the default (intended) algebra and for what the HEAD
+    revision computes (msed_set_compat), with non-default namelist values."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    from mossco_code_b200.sediment import PARTICULATE
+    case = make_case("p2s", 9, 7, 15, 0.004, seed=67)
+    rng = np.random.default_rng(4)
+    sh = (9, 7)
+    allf = dict(temperature=4 + 8 * rng.random(sh), par=30 * rng.random(sh), oxygen=250 * (rng.random(sh) - 0.2),
+                odu=40 * (rng.random(sh) - 0.5), detN=2 + rng.random(sh), detN_z_velocity=-1e-5 * (1 + rng.random(sh)),
+                detC=(2 + 60 * rng.random(sh)), detP=0.1 + 0.1 * rng.random(sh),
+                detP_z_velocity=-2e-5 * (1 + rng.random(sh)), nitrate=8 + rng.random(sh), ammonium=3 + rng.random(sh),
+                DIN=12 + 5 * rng.random(sh), DIP=0.5 + rng.random(sh), water_depth=0.05 + 30 * rng.random(sh) ** 3,
+                tke=2.0e3 * rng.random(sh))
+    f = {k: v for k, v in allf.items() if k in ("temperature", "par", "detN", "detN_z_velocity") or present.get(k)}
+    params = dict(sinking_factor=0.25, NC_ldet=0.21, convertN=1.5, convertP=0.8, critical_detritus=45.0)
+    cfg = default_config(inum=9, jnum=7, knum=15, dzmin=0.004, dt_min=1.0)
+    with SedimentDriver(cfg) as sed:
+        sed.init_concentrations()
+        sed.set_boundary(case.bdys, case.fluxes)
+        ref = oracle.OracleSediment.from_config(cfg)
+        ref.init_concentrations()
+        ref.set_boundary(case.bdys, case.fluxes)
+        sed.set_compat(p2s_head=head)
+        sed.pelagic_soil_connector(params=params, **f)
+        cs, wz = oracle.pelagic_soil_connector(sh, params=params, head_compat=head,
+                                               **{k: v for k, v in f.items() if k not in ("temperature", "par")})
+        if not (present.get("oxygen") or present.get("odu")):
+            cs[6] = cs[7] = None                      # not in the transfer: the sediment keeps its boundary values
+        ref.get_boundary_conditions(f["temperature"], cs, wz)
+        assert np.array_equal(sed.bdys, ref.bdys)            # same IEEE operation sequence
+        assert np.array_equal(sed.fluxes, ref.fluxes)
+        assert np.array_equal(sed.field("photosynthetically_active_radiation")[:, :, 0], f["par"])
+        if not head:   # the split conserves detritus carbon: fac_ldet + fac_sdet = C:N
+            cn = f["detC"] / (np.float64(np.float32(1e-5)) + f["detN"]) if "detC" in f else 106.0 / 16.0
+            total = (cs[0] + cs[1]) / (params["convertN"] * f["detN"])
+            assert np.allclose(total, cn, rtol=1e-14)
+        else:
+            assert np.all(sed.fluxes[:, :, :2] == 0.0)       # HEAD never writes the carbon velocities
+        assert sed.step(360.0, 2, 2) == 0 and ref.step(360.0, 2, 2) == 0
+        assert scaled_err(sed.conc, ref.conc) <= 1e-11
+    assert sum(PARTICULATE) == 3
+
+
+def test_pelagic_benthic_coupler_oxygen_quirk_switch(gpu, oracle):
+    """MSED_COMPAT_P2B_OXYGEN_LAST_CELL: the whole-array assignment of pelagic_benthic_coupler.F90:344-349 as
+    written (every column gets the last cell's oxygen split) against the per-column default."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    rng = np.random.default_rng(8)
+    sh = (6, 5)
+    f = dict(temperature=4 + 8 * rng.random(sh), oxygen=250 * (rng.random(sh) - 0.3), detN=2 + rng.random(sh),
+             detN_z_velocity=-1e-5 * (1 + rng.random(sh)), DIN=10 + 5 * rng.random(sh))
+    cfg = default_config(inum=6, jnum=5, knum=12, dzmin=0.004, dt_min=1.0)
+    for quirk in (False, True):
+        with SedimentDriver(cfg) as sed:
+            sed.init_concentrations()
+            sed.set_compat(p2b_oxygen_last_cell=quirk)
+            sed.pelagic_benthic_coupler(**f)
+            cs, wz = oracle.pelagic_benthic_coupler(sh, oxy_last_cell=quirk, **{k: v for k, v in f.items() if k != "temperature"})
+            assert np.array_equal(sed.bdys[:, :, 7], cs[6]) and np.array_equal(sed.bdys[:, :, 8], cs[7])
+            if quirk:
+                last = f["oxygen"][-1, -1]
+                assert np.all(sed.bdys[:, :, 7] == max(0.0, last)) and np.all(sed.bdys[:, :, 8] == max(0.0, -last))
+            else:
+                assert len(np.unique(sed.bdys[:, :, 7])) > 2
+
+
+def test_diagnostics_and_checksum(gpu, oracle):
+    """msed_diagnostics (bed-flux sums, inventories over the wet columns) against numpy on the downloaded
+    state, and msed_state_checksum: two half tiles reproduce the whole tile's pair."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    case = make_case("diag", 12, 10, 15, 0.004, seed=71, land_fraction=0.25)
+
+    def tile(j0, j1):
+        cfg = default_config(inum=12, jnum=j1 - j0, knum=15, dzmin=0.004, dt_min=1.0, j_offset=j0)
+        sed = SedimentDriver(cfg)
+        sed.set_mask(np.asfortranarray(case.mask[:, j0:j1]))
+        sed.init_concentrations()
+        sed.set_boundary(np.asfortranarray(case.bdys[:, j0:j1]), np.asfortranarray(case.fluxes[:, j0:j1]))
+        assert sed.step(360.0, 0, 4) == 0          # Euler: no whole-domain decision, tiles are independent
+        return sed
+
+    whole = tile(0, 10)
+    b, inv = whole.diagnostics()
+    wet = case.mask == 0
+    conc, por, fl = whole.conc, whole.field("porosity"), whole.fluxes
+    _, _, dz, _ = whole.grid()
+    for n in range(8):
+        assert np.isclose(b[n], fl[:, :, n][wet].sum(), rtol=1e-12, atol=1e-300)
+        assert np.isclose(inv[n], (conc[:, :, :, n] * por * dz)[wet].sum(), rtol=1e-12)
+    want = whole.state_checksum(global_ncol=120, col_offset=0)
+    parts = [tile(0, 4), tile(4, 10)]
+    got = [p.state_checksum(global_ncol=120) for p in parts]
+    assert ((got[0][0] + got[1][0]) % 2 ** 64, got[0][1] ^ got[1][1]) == want
+    c = conc.copy(); c[3, 2, 5, 1] = np.nextafter(c[3, 2, 5, 1], 1e30)
+    assert wet[3, 2]
+    whole.conc = c
+    assert whole.state_checksum(global_ncol=120, col_offset=0) != want     # one ulp in one cell shows
+    for s in [whole] + parts:
+        s.finalize()

@@ -23,18 +23,19 @@ def _run(case, fusion, method, nsteps, calls=1, mutate=None, **cfgkw):
         sed.set_boundary(case.bdys, case.fluxes)
         if mutate:
             mutate(sed)
-        launches = sub = rhs = done = 0
+        launches = sub = rhs = done = fused = 0
         rc = 0
         for _ in range(calls):
             rc = sed.step(DT, method, nsteps)
             launches += sed.info.kernel_launches
+            fused += sed.info.fused_steps
             sub += sed.info.subcycle_warnings
             rhs += sed.info.rhs_evaluations
             done += sed.info.steps_done
             if rc:
                 break
         return dict(conc=sed.conc, fluxes=sed.fluxes, denit=sed.field("denit"), launches=launches, sub=sub,
-                    rhs=rhs, done=done, rc=rc)
+                    rhs=rhs, done=done, rc=rc, fused=fused)
 
 
 def _same(a, b):
@@ -113,6 +114,49 @@ def test_fusion_falls_back_when_a_step_is_rejected(gpu, mode):
     off = _run(case, False, 2, 7, calls=3, **kw)
     assert off["sub"] > 0
     _same(on, off)
+
+
+# per-step rejection counts of these regimes on this tile (oracle, 60 steps):
+#   rnit=rODUox=600     110111111111...           steady sub-cycling at dt/4
+#   rnit=rODUox=4000    2222222222222222100100200120...   steady dt/16, then a mix
+#   rnit=rODUox=2000    2111111111111111111110000000010101000100...   an episode that ends
+#   rLabile=0.6         0000000111212221212121212...   period-2 pattern: every prediction fails
+#   rnit=rODUox=2e4     3333003000300030...        deeper than the fused kernels plan (dt/64)
+SUBCYCLING = [dict(rnit=600., rODUox=600.), dict(rnit=4000., rODUox=4000.), dict(rnit=2000., rODUox=2000.),
+              dict(rLabile=0.6), dict(rnit=2.0e4, rODUox=2.0e4)]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("nsteps,calls", [(10, 5), (3, 9), (1, 12)])
+@pytest.mark.parametrize("kw", SUBCYCLING)
+def test_subcycling_regime_is_fused_and_bit_identical(gpu, kw, nsteps, calls, mode):
+    """Sub-cycled steps (solver_library.F90:126-128) go through the fused kernels too: a call is planned the way
+    the last step went -- rejected attempts at dt, dt/4 with the RHS of the first accepted sub-step, then 4 or 16
+    sub-steps without a clip in between -- and committed only if the reference would have taken exactly those
+    decisions.  State, bed fluxes, diagnostics and the attempt / sub-cycle counters must be those of the
+    single-attempt path in every regime, including the ones where the prediction keeps failing."""
+    case = make_case("fuser", 12, 8, 15, 0.004, seed=2)
+    on = _run(case, mode, 2, nsteps, calls=calls, **kw)
+    off = _run(case, False, 2, nsteps, calls=calls, **kw)
+    assert off["sub"] > 0
+    _same(on, off)
+    if kw.get("rnit") == 600. and nsteps * calls >= 27:
+        # the steady regime: once a call has been planned from a sub-cycled step everything is fused
+        assert on["fused"] >= nsteps * (calls - 2)
+        assert on["launches"] < off["launches"]
+    if kw.get("rnit") == 4000. and nsteps == 3:
+        assert on["fused"] >= 9                      # steps 3..14 run at dt/16, planned from step 2
+
+
+def test_subcycling_fused_on_a_k40_masked_tile(gpu):
+    """The pair path proper (knum = 40 > 32) on a tile with land, in the steady dt/4 regime."""
+    case = make_case("fusek", 23, 11, 40, 0.0015, seed=12, land_fraction=0.3)
+    kw = dict(rnit=600., rODUox=600.)
+    on = _run(case, "auto", 2, 10, calls=4, **kw)
+    off = _run(case, False, 2, 10, calls=4, **kw)
+    assert off["sub"] >= 30
+    _same(on, off)
+    assert on["fused"] >= 20 and on["launches"] < off["launches"]
 
 
 @pytest.mark.parametrize("mode", MODES)

@@ -126,14 +126,68 @@ def _lockstep(sed, ref, method, nsteps, chunk):
     return err_agree, agreed, scaled_err(sed.conc, ref.conc)
 
 
+def _perturbed_twins(oracle, cfg, case, ref, n=3, eps=1e-13):
+    """Oracle twins of ``ref`` whose initial state is perturbed by a relative ``eps`` (a few hundred ulp: the size
+    of the kernel's own rounding differences -- FMA contraction, 2-ulp reciprocals -- after one step).  Once the
+    accept/reject histories of two adaptive runs part, the distance between them is set by the dynamics, not by
+    the size of what parted them; the twins measure that distance for the oracle against itself."""
+    twins = []
+    for t in range(n):
+        tw = oracle.OracleSediment.from_config(cfg, mask2d=case.mask)
+        tw.init_concentrations()
+        tw.set_boundary(case.bdys, case.fluxes)
+        tw.par_surface[...] = case.par_surface
+        c = ref.conc.copy()
+        wet = c < 1e19
+        c[wet] *= 1.0 + eps * np.random.default_rng(100 + t).uniform(-1, 1, size=c.shape)[wet]
+        tw.conc[...] = c
+        twins.append(tw)
+    return twins
+
+
+def _ten_days_adaptive(oracle, cfg, case, sed, ref, nsteps=2400, chunk=10, advance=None, min_agreed=1):
+    """Lock-step run of ``sed`` (GPU), ``ref`` (oracle) and perturbed oracle twins.  While the GPU and the
+    oracle take identical accept/reject decisions the north-star bar (1e-8) is asserted outright; after they part
+    the GPU must stay inside the envelope the oracle spans against its own perturbed twins -- no fixed looser
+    number.  ``advance(obj, n)`` steps one of them by n steps (default: .step)."""
+    wet = case.mask == 0
+    twins = _perturbed_twins(oracle, cfg, case, ref)
+    advance = advance or (lambda o, n: o.step(DT, 2, n))
+    agreed, err_agree, sub_gpu, diverged = 0, 0.0, 0, False
+    for s0 in range(0, nsteps, chunk):
+        n = min(chunk, nsteps - s0)
+        assert advance(sed, n) == 0
+        assert advance(ref, n) == 0
+        for tw in twins:
+            assert advance(tw, n) == 0
+        sub_gpu += sed.info.subcycle_warnings
+        if not diverged and sub_gpu == ref.solver_diag()["subcycles"]:
+            agreed = s0 + n
+            if (s0 // chunk) % 10 == 9 or s0 + n == nsteps:
+                err_agree = max(err_agree, scaled_err(sed.conc[wet], ref.conc[wet]))
+        else:
+            diverged = True
+    gap_gpu = scaled_err(sed.conc[wet], ref.conc[wet])
+    gap_twins = max(scaled_err(tw.conc[wet], ref.conc[wet]) for tw in twins)
+    print(f"{case.name}: identical accept/reject history for {agreed} of {nsteps} steps, err while agreed "
+          f"{err_agree:.2e}; final GPU-oracle gap {gap_gpu:.2e}, oracle-twin gap {gap_twins:.2e}")
+    assert agreed >= min_agreed
+    assert err_agree <= TOL_10D
+    if agreed == nsteps:
+        assert gap_gpu <= TOL_10D
+    else:
+        # decision-chaotic tail: the GPU is one more member of the oracle's own ensemble
+        assert gap_gpu <= max(TOL_10D, 4.0 * gap_twins)
+    for tw in twins:
+        tw.finalize()
+    return agreed
+
+
 def test_c1_ten_days_adaptive(gpu, oracle):
     """C1, 10 simulated days (2400 steps of 360 s), ode_method=2, from the raw namelist state."""
     case = config_case("C1")
     cfg, sed, ref = _pair(oracle, case)
-    err_agree, agreed, err_final = _lockstep(sed, ref, 2, 2400, 10)
-    assert agreed >= 1000                 # identical accept/reject history for at least 1000 steps
-    assert err_agree <= TOL_10D
-    assert err_final <= (TOL_10D if agreed == 2400 else 1e-6)
+    _ten_days_adaptive(oracle, cfg, case, sed, ref, min_agreed=1000)
     sed.finalize()
 
 
@@ -171,26 +225,122 @@ def test_c2_ten_days_reduced(gpu, oracle):
     (msed_run: 10 ode_solver calls each, component :1700-1769)."""
     case = config_case("C2", 0.24)
     cfg, sed, ref = _pair(oracle, case)
-    agreed, err_agree, sub_gpu, diverged = 0, 0.0, 0, False
-    for it in range(240):
-        assert sed.run(DT, 2, 3600.0) == 0
-        assert sed.info.steps_done == 10
-        assert ref.step(DT, 2, 10) == 0
-        sub_gpu += sed.info.subcycle_warnings
-        if not diverged and sub_gpu == ref.solver_diag()["subcycles"]:
-            agreed = (it + 1) * 10
-            if it % 20 == 19 or it == 239:
-                err_agree = max(err_agree, scaled_err(sed.conc, ref.conc))
-        else:
-            diverged = True
-    print(f"C2 reduced: identical accept/reject history for {agreed} of 2400 steps, "
-          f"err while agreed {err_agree:.2e}, final {scaled_err(sed.conc, ref.conc):.2e}")
-    assert agreed >= 500
-    assert err_agree <= TOL_10D
-    assert scaled_err(sed.conc, ref.conc) <= (TOL_10D if agreed == 2400 else 1e-5)
+
+    def advance(o, n):
+        if o is sed:
+            rc = sed.run(DT, 2, 3600.0)
+            assert sed.info.steps_done == 10
+            return rc
+        return o.step(DT, 2, n)
+
+    agreed = _ten_days_adaptive(oracle, cfg, case, sed, ref, advance=advance, min_agreed=500)
     if agreed == 2400:   # sed%fluxes is the bed flux of the LAST get_rhs call: only comparable when
         assert scaled_err(sed.fluxes, ref.fluxes) <= TOL_10D   # both sides ended on the same sub-step
     sed.finalize()
+
+
+# ---- 10 simulated days on tiles shaped like BASELINE configs 3, 4 and 5 (the loop being matched is the Run
+# ---- loop, fabm_sediment_component.F90:1700-1769) ------------------------------------------------------------
+def _shaped_case(which):
+    if which == "C3":     # land mask, smooth temperature 2..18 degC, PAR, K = 30
+        return make_case("C3tile", 10, 8, 30, 0.002, seed=2024, land_fraction=0.45, smooth_temperature=True,
+                         par_max=50.0), "auto"
+    if which == "C4":     # K = 40: the thread-per-column pair path
+        return make_case("C4tile", 7, 5, 40, 0.0015, seed=4096), "pairs"
+    raise KeyError(which)
+
+
+@pytest.mark.parametrize("method", [0, 1, 3])
+@pytest.mark.parametrize("which", ["C3", "C4"])
+def test_ten_days_shaped_tiles_fixed_step(gpu, oracle, which, method):
+    case, fusion = _shaped_case(which)
+    cfg, sed, ref = _pair(oracle, case)
+    sed.set_step_fusion(fusion)
+    wet = case.mask == 0
+    for _ in range(24):                       # 24 x 100 steps; Runs of different lengths exercise odd/even plans
+        assert sed.step(DT, method, 100) == 0
+        assert ref.step(DT, method, 100) == 0
+    assert sed.info.fused_steps > 0 or method in (1, 3)
+    assert scaled_err(sed.conc[wet], ref.conc[wet]) <= TOL_10D
+    assert scaled_err(sed.fluxes[wet], ref.fluxes[wet]) <= TOL_10D
+    assert np.all(sed.conc[~wet] == 1e20)
+    sed.finalize()
+
+
+@pytest.mark.parametrize("which", ["C3", "C4"])
+def test_ten_days_shaped_tiles_adaptive(gpu, oracle, which):
+    case, fusion = _shaped_case(which)
+    cfg, sed, ref = _pair(oracle, case)
+    sed.set_step_fusion(fusion)
+    _ten_days_adaptive(oracle, cfg, case, sed, ref, min_agreed=100)
+    assert np.all(sed.conc[case.mask > 0] == 1e20)
+    sed.finalize()
+
+
+@pytest.mark.parametrize("method", [2, 1])
+def test_ten_days_coupled_c5_shaped(gpu, oracle, method):
+    """Config 5 at test size for 10 simulated days: 240 coupling intervals of msed_coupled_run (pelagic boxes ->
+    get_boundary_conditions -> 10 steps -> bed flux into the boxes, all on the device) against the same sequence
+    on the oracle (+ numpy for the boxes, fabm_pelagic_component.F90:2100-2105)."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    case = make_case("C5tile", 8, 6, 30, 0.002, seed=2048, land_fraction=0.15)
+    rng = np.random.default_rng(11)
+    sh = case.mask.shape
+    base = np.array([30.0, 300.0, 1.0, 0.6, 14.0, 4.0, 250.0, 0.5])
+    pel0 = np.empty(sh + (8,), order="F")
+    for n in range(8):
+        pel0[:, :, n] = base[n] * (1.0 + 0.1 * rng.uniform(-1, 1, sh))
+    wz = np.zeros(sh + (8,), order="F")
+    wz[:, :, :3] = -(1.0 + rng.random(sh + (3,))) * 1e-6
+    height = np.asfortranarray(5.0 + 10.0 * rng.random(sh))
+    temp = np.asfortranarray(4.0 + 8.0 * rng.random(sh))
+    cfg = default_config(inum=sh[0], jnum=sh[1], knum=30, dzmin=0.002, dt_min=1.0)
+    wet = case.mask == 0
+
+    class Coupled:                                   # the oracle side of msed_coupled_run
+        def __init__(self, conc_scale=None):
+            self.o = oracle.OracleSediment.from_config(cfg, mask2d=case.mask)
+            self.o.init_concentrations()
+            if conc_scale is not None:
+                c = self.o.conc.copy(); m = c < 1e19; c[m] *= conc_scale[m]; self.o.conc[...] = c
+            self.pel = pel0.copy(order="F")
+
+        def couple(self):
+            self.o.get_boundary_conditions(temp, [self.pel[:, :, n] for n in range(8)],
+                                           [wz[:, :, n] if n < 3 else None for n in range(8)])
+            assert self.o.step(DT, method, 10) == 0
+            up = -self.o.fluxes
+            for n in range(8):
+                self.pel[:, :, n][wet] = self.pel[:, :, n][wet] + up[:, :, n][wet] * 3600.0 / height[wet]
+
+    ref = Coupled()
+    twins = [Coupled(1.0 + 1e-13 * np.random.default_rng(200 + t).uniform(-1, 1, size=ref.o.conc.shape))
+             for t in range(3)] if method == 2 else []
+    with SedimentDriver(cfg) as sed:
+        sed.set_mask(case.mask)
+        sed.init_concentrations()
+        sed.pelagic_init(pel0, wz, height, temp)
+        sub_gpu, agreed, diverged, err_agree = 0, 0, False, 0.0
+        for it in range(240):
+            assert sed.coupled_run(DT, method, 3600.0, 1) == 0
+            ref.couple()
+            for tw in twins:
+                tw.couple()
+            sub_gpu += sed.info.subcycle_warnings
+            if not diverged and sub_gpu == ref.o.solver_diag()["subcycles"]:
+                agreed = it + 1
+                if it % 20 == 19:
+                    err_agree = max(err_agree, scaled_err(sed.conc[wet], ref.o.conc[wet]))
+            else:
+                diverged = True
+        gap = max(scaled_err(sed.conc[wet], ref.o.conc[wet]), scaled_err(sed.pelagic_conc[wet], ref.pel[wet]))
+        gap_tw = max([max(scaled_err(t.o.conc[wet], ref.o.conc[wet]), scaled_err(t.pel[wet], ref.pel[wet]))
+                      for t in twins] or [0.0])
+        print(f"C5tile method {method}: {agreed} of 240 couplings with identical decisions, err while agreed "
+              f"{err_agree:.2e}, final gap {gap:.2e}, oracle-twin gap {gap_tw:.2e}")
+        assert err_agree <= TOL_10D
+        assert gap <= (TOL_10D if agreed == 240 else max(TOL_10D, 4.0 * gap_tw))
+        assert np.array_equal(sed.pelagic_conc[~wet], pel0[~wet])
 
 
 @pytest.mark.parametrize("method", [1, 3])
