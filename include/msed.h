@@ -168,6 +168,16 @@ int msed_get_upward_fluxes(msed_handle *h, double *upward_fluxes);
 /* export_states(n)%data / diagnostics for <name>_in_soil, component :1773-1822 */
 int msed_get_field(msed_handle *h, int which, double *out3d);
 
+/* The <var>_in_soil write-back of the component (fabm_sediment_component.F90:1773-1822 copies every export
+ * state to its ESMF field every Run; consumers -- output, restart -- read it at their own cadence) as an
+ * asynchronous export: _begin snapshots the state on the device (a device-to-device copy in stream order) and
+ * starts the PCIe copy of the snapshot into conc_host(inum,jnum,knum,nvar) -- pinned memory for a truly
+ * asynchronous copy -- on the library's copy stream, so that stepping calls issued afterwards overlap it;
+ * _wait blocks until conc_host is complete.  The snapshot buffer (state-sized) is allocated at the first call;
+ * if the device has no room for it the copy reads the state directly and the next stepping call waits. */
+int msed_export_state_begin(msed_handle *h, double *conc_host);
+int msed_export_state_wait(msed_handle *h);
+
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* type_sed%get_rhs, driver :575-717 (one RHS evaluation incl. its side effect on sed%fluxes) */
 int msed_get_rhs(msed_handle *h, double *rhs);

@@ -148,6 +148,8 @@ SYMBOLS = {
     "msed_get_fluxes": (C.c_int, [_h, _dp]),
     "msed_get_upward_fluxes": (C.c_int, [_h, _dp]),
     "msed_get_field": (C.c_int, [_h, C.c_int, _dp]),
+    "msed_export_state_begin": (C.c_int, [_h, _dp]),
+    "msed_export_state_wait": (C.c_int, [_h]),
     "msed_get_rhs": (C.c_int, [_h, _dp]),
     "msed_ode_solver": (C.c_int, [_h, C.c_double, C.c_int, C.POINTER(StepInfo)]),
     "msed_step": (C.c_int, [_h, C.c_double, C.c_int, C.c_int64, C.POINTER(StepInfo)]),

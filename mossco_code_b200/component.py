@@ -62,6 +62,14 @@ class FabmSedimentComponent:
         self.clock_seconds = 0.0
         self.last_info = None
         self.export_3d_every_run = True
+        # <name>_in_soil write-back at an output cadence instead of every Run: every export_cadence-th Run starts
+        # an asynchronous export of the state into export_buffer (caller-owned, ideally pinned, shape
+        # (inum,jnum,knum,nvar)) that overlaps the following Runs; export_ready() completes it and refreshes the
+        # <var>_in_soil entries of the export state (views of export_buffer).  0 = off.
+        self.export_cadence = 0
+        self.export_buffer = None
+        self._export_started = False
+        self._runs = 0
         self.flux_buffer = None   # optional caller-owned (pinned) (inum,jnum,nvar) export buffer
         self._out = None          # output.dat handle (run_nml output > 0, component :266-269)
         self.advance_count = 0    # ESMF clock advanceCount
@@ -282,7 +290,24 @@ class FabmSedimentComponent:
         if rc == _abi.NAN_DETECTED:                          # :1718-1723
             raise ComponentError(ESMF_RC_VAL_OUTOFRANGE, "NaN detected applying ode_solver")
         self._fill_exports(export_state, with_3d=self.export_3d_every_run, up=up)   # :1773-1822
+        self._runs += 1
+        if self.export_cadence > 0 and self._runs % self.export_cadence == 0:
+            if self.export_buffer is None:
+                self.export_buffer = np.zeros(sed.shape4d, order="F")
+            sed.export_state_begin(self.export_buffer)
+            self._export_started = True
         return ESMF_SUCCESS
+
+    def export_ready(self, export_state: State) -> bool:
+        """Complete the export started by the last cadence Run (if any): waits for the copy and points the
+        ``<var>_in_soil`` entries of ``export_state`` at it.  Returns whether an export was pending."""
+        if not self._export_started:
+            return False
+        self.sed.export_state_wait()
+        self._export_started = False
+        for n, v in enumerate(VARIABLE_NAMES):
+            export_state[f"{v}_in_soil"] = self._export(self.export_buffer[:, :, :, n])
+        return True
 
     # ---- output.dat (:677-685 header, :1734-1759 rows) ---------------------------------------------
     @staticmethod

@@ -84,6 +84,10 @@ struct msed_handle {
     double *minloc_val = nullptr;
     long long *minloc_idx = nullptr;
     double *red = nullptr;      // 32 doubles of device scratch for the small cross-tile reductions
+    double *snap = nullptr;     // [nvar][K][ld] snapshot of the state an asynchronous export reads (msed_export_state_begin)
+    cudaEvent_t ev_snap = nullptr, ev_export = nullptr;
+    cudaStream_t export_stream = nullptr;   // its own stream: the per-Run flux copies on copy_stream must not queue behind it
+    bool export_pending = false, export_direct = false;
     int compat = 0;             // MSED_COMPAT_* (msed_set_compat)
     int cur = 0;
     int por_mode = 1;           // how the column kernel obtains porosity (see KParams::por_mode)
@@ -978,7 +982,10 @@ int msed_destroy(msed_handle *h)
     cudaFree(h->buf[0]); cudaFree(h->buf[1]); cudaFree(h->aux[0]); cudaFree(h->aux[1]);
     cudaFree(h->por); cudaFree(h->bdys); cudaFree(h->fluxes); cudaFree(h->par_surface);
     cudaFree(h->scratch); cudaFree(h->denit); cudaFree(h->tables); cudaFree(h->mask); cudaFree(h->colmap); cudaFree(h->xstage); cudaFree(h->ctl);
-    cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->red); cudaFree(h->pel);
+    cudaFree(h->minloc_val); cudaFree(h->minloc_idx); cudaFree(h->red); cudaFree(h->pel); cudaFree(h->snap);
+    if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+    if (h->ev_export) cudaEventDestroy(h->ev_export);
+    if (h->export_stream) cudaStreamDestroy(h->export_stream);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1290,7 +1297,9 @@ int msed_get_rhs(msed_handle *h, double *rhs)
     CUDA_TRY(h, launch_column(h, OP_RHS, p));
     rc = download_rows(h, rhs, h->scratch, (size_t)NV * h->K);
     if (rc) return rc;
-    // diagnostics now describe the current state: mirror it into the "last rhs state" buffer
+    // diagnostics now describe the current state: mirror it into the "last rhs state" buffer (and drop the
+    // diagnostic a fused launch may have left behind for the state before)
+    h->denit_valid = false;
     copy_state_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->buf[1 - h->cur], h->buf[h->cur], h->ld,
                                                                h->ncol, NV * h->K);
     CUDA_TRY(h, cudaGetLastError());
@@ -1799,6 +1808,55 @@ int msed_soil_pelagic_connector(msed_handle *h, const msed_soil_pelagic_params *
             CUDA_TRY(h, cudaMemcpyAsync(rows[r].dst, h->scratch + (size_t)rows[r].row * h->ld,
                                         (size_t)h->ncol * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MSED_OK;
+}
+
+int msed_export_state_begin(msed_handle *h, double *conc_host)
+{
+    if (!h || !conc_host) return fail(h, MSED_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->export_pending) {
+        const int rc = msed_export_state_wait(h);
+        if (rc) return rc;
+    }
+    if (!h->ev_snap) {
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_export, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->export_stream, cudaStreamNonBlocking));
+    }
+    const size_t bytes = (size_t)NV * h->K * h->ld * sizeof(double);
+    if (!h->snap && !h->export_direct) {
+        // a state-sized snapshot lets the PCIe copy run under the following Runs (it takes several of them);
+        // without the memory for it the copy reads the state itself and the next stepping call waits for it
+        if (cudaMalloc(&h->snap, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            h->snap = nullptr;
+            h->export_direct = true;
+        }
+    }
+    const double *src = h->buf[h->cur];
+    if (h->snap) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->snap, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        src = h->snap;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_snap, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->export_stream, h->ev_snap, 0));
+    CUDA_TRY(h, cudaMemcpy2DAsync(conc_host, (size_t)h->ncol * sizeof(double), src, h->ld * sizeof(double),
+                                  (size_t)h->ncol * sizeof(double), (size_t)NV * h->K, cudaMemcpyDeviceToHost,
+                                  h->export_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_export, h->export_stream));
+    if (!h->snap) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_export, 0));   // the state must stay put
+    h->export_pending = true;
+    return MSED_OK;
+}
+
+int msed_export_state_wait(msed_handle *h)
+{
+    if (!h) return MSED_ERR_ARG;
+    if (!h->export_pending) return MSED_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_export));
+    h->export_pending = false;
     return MSED_OK;
 }
 

@@ -211,6 +211,17 @@ class SedimentDriver:
         self._check(self._lib.msed_get_field(self._h, _abi.FIELDS[name], _ptr(out)))
         return out
 
+    def export_state_begin(self, out: np.ndarray):
+        """Start the asynchronous export of ``conc`` into ``out`` (fp64, Fortran order, shape
+        (inum,jnum,knum,nvar); pinned memory overlaps the copy with later stepping calls)."""
+        if out.shape != self.shape4d or not out.flags.f_contiguous or out.dtype != np.float64:
+            raise ValueError("export_state_begin: out must be fp64, Fortran order, shape (inum,jnum,knum,nvar)")
+        self._export_ref = out
+        self._check(self._lib.msed_export_state_begin(self._h, _ptr(out)))
+
+    def export_state_wait(self):
+        self._check(self._lib.msed_export_state_wait(self._h))
+
     # -- hot path -------------------------------------------------------------------------
     def get_rhs(self) -> np.ndarray:
         """``type_sed%get_rhs`` (fabm_sediment_driver.F90:575-717)."""

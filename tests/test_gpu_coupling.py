@@ -437,8 +437,8 @@ def test_diagnostics_and_checksum(gpu, oracle):
     parts = [tile(0, 4), tile(4, 10)]
     got = [p.state_checksum(global_ncol=120) for p in parts]
     assert ((got[0][0] + got[1][0]) % 2 ** 64, got[0][1] ^ got[1][1]) == want
-    c = conc.copy(); c[3, 2, 5, 1] = np.nextafter(c[3, 2, 5, 1], 1e30)
-    assert wet[3, 2]
+    i, j = np.argwhere(wet)[7]
+    c = conc.copy(); c[i, j, 5, 1] = np.nextafter(c[i, j, 5, 1], 1e30)
     whole.conc = c
     assert whole.state_checksum(global_ncol=120, col_offset=0) != want     # one ulp in one cell shows
     for s in [whole] + parts:

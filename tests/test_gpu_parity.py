@@ -253,13 +253,19 @@ def _shaped_case(which):
 @pytest.mark.parametrize("method", [0, 1, 3])
 @pytest.mark.parametrize("which", ["C3", "C4"])
 def test_ten_days_shaped_tiles_fixed_step(gpu, oracle, which, method):
+    """Fixed-step integrators: 1e-8 on state and bed fluxes after 10 simulated days.  dt = 360 s everywhere except
+    for the Runge-Kutta schemes on the C3 tile: its warm columns (up to 18 degC) put explicit RK beyond its
+    stability limit at 360 s, the clipped oscillation (:1726-1732) amplifies rounding differences to O(1) -- the
+    ORACLE moves by 6.0 (scaled) under a 1e-13 perturbation of its initial state there, and by 6e-14 at
+    dt = 120 s -- so that case runs its 10 days in 7200 steps of 120 s."""
     case, fusion = _shaped_case(which)
     cfg, sed, ref = _pair(oracle, case)
     sed.set_step_fusion(fusion)
     wet = case.mask == 0
-    for _ in range(24):                       # 24 x 100 steps; Runs of different lengths exercise odd/even plans
-        assert sed.step(DT, method, 100) == 0
-        assert ref.step(DT, method, 100) == 0
+    dt, n = (120.0, 300) if (which == "C3" and method != 0) else (DT, 100)
+    for _ in range(24):
+        assert sed.step(dt, method, n) == 0
+        assert ref.step(dt, method, n) == 0
     assert sed.info.fused_steps > 0 or method in (1, 3)
     assert scaled_err(sed.conc[wet], ref.conc[wet]) <= TOL_10D
     assert scaled_err(sed.fluxes[wet], ref.fluxes[wet]) <= TOL_10D
@@ -308,11 +314,13 @@ def test_ten_days_coupled_c5_shaped(gpu, oracle, method):
         def couple(self):
             self.o.get_boundary_conditions(temp, [self.pel[:, :, n] for n in range(8)],
                                            [wz[:, :, n] if n < 3 else None for n in range(8)])
-            assert self.o.step(DT, method, 10) == 0
+            assert self.o.step(dt, method, nper) == 0
             up = -self.o.fluxes
             for n in range(8):
                 self.pel[:, :, n][wet] = self.pel[:, :, n][wet] + up[:, :, n][wet] * 3600.0 / height[wet]
 
+    # RK4 at dt = 360 s is beyond its stability limit here (see test_ten_days_shaped_tiles_fixed_step): 120 s
+    dt, nper = (DT, 10) if method == 2 else (120.0, 30)
     ref = Coupled()
     twins = [Coupled(1.0 + 1e-13 * np.random.default_rng(200 + t).uniform(-1, 1, size=ref.o.conc.shape))
              for t in range(3)] if method == 2 else []
@@ -322,7 +330,7 @@ def test_ten_days_coupled_c5_shaped(gpu, oracle, method):
         sed.pelagic_init(pel0, wz, height, temp)
         sub_gpu, agreed, diverged, err_agree = 0, 0, False, 0.0
         for it in range(240):
-            assert sed.coupled_run(DT, method, 3600.0, 1) == 0
+            assert sed.coupled_run(dt, method, 3600.0, 1) == 0
             ref.couple()
             for tw in twins:
                 tw.couple()
@@ -339,7 +347,7 @@ def test_ten_days_coupled_c5_shaped(gpu, oracle, method):
         print(f"C5tile method {method}: {agreed} of 240 couplings with identical decisions, err while agreed "
               f"{err_agree:.2e}, final gap {gap:.2e}, oracle-twin gap {gap_tw:.2e}")
         assert err_agree <= TOL_10D
-        assert gap <= (TOL_10D if agreed == 240 else max(TOL_10D, 4.0 * gap_tw))
+        assert gap <= (TOL_10D if (agreed == 240 and method == 2) else max(TOL_10D, 4.0 * gap_tw))
         assert np.array_equal(sed.pelagic_conc[~wet], pel0[~wet])
 
 

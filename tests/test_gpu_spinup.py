@@ -49,7 +49,7 @@ def test_spinup_batch_equals_single_columns(gpu, method, knum, dzmin):
             assert list(infos[m].last_min_dt_grid_cell) == list(wi.last_min_dt_grid_cell), m
         subs.append(infos[m].subcycle_warnings)
     if method == 2:
-        assert max(subs) > 0 and min(subs) == 0        # members really decide for themselves
+        assert min(subs) > 0 and max(subs) > 1.5 * min(subs)     # members really decide for themselves
 
 
 def test_spinup_batch_matches_oracle_and_shared_parameters(gpu, oracle):
