@@ -35,7 +35,14 @@
 constexpr int PAIR_WIN = 4;  // c1 window slots (3 live layers: j, j+1 and the one being written)
 constexpr uint32_t PAIR_STAGE_BYTES = NV * ROW_BYTES;                    // input ring: 8 rows per layer
 constexpr uint32_t PAIR_RING_BYTES = RING_STAGES * PAIR_STAGE_BYTES;
-constexpr size_t PAIR_SMEM_BYTES = (size_t)PAIR_RING_BYTES + (size_t)PAIR_WIN * NV * ROW_BYTES;
+constexpr uint32_t PAIR_WIN_BYTES = PAIR_WIN * NV * ROW_BYTES;
+constexpr int PAIR_COLROWS = NV + 2;  // per-column scalars: temperature, surface porosity, one upper-boundary value per variable
+static_assert(PAIR_COLROWS <= 2 * NV, "the column scalars borrow window slots 2 and 3");
+#ifdef MSED_PAIR_PAD_SMEM   // experiment: the same kernel with a smaller L1 (profiles/r02_summary.md)
+constexpr size_t PAIR_SMEM_BYTES = (size_t)PAIR_RING_BYTES + PAIR_WIN_BYTES + MSED_PAIR_PAD_SMEM;
+#else
+constexpr size_t PAIR_SMEM_BYTES = (size_t)PAIR_RING_BYTES + PAIR_WIN_BYTES;
+#endif
 constexpr int PAIR_MIN_BLOCKS = 3;
 
 __device__ __forceinline__ void sts64(uint32_t addr, double v)
@@ -80,6 +87,23 @@ pair_kernel(const __grid_constant__ KParams p)
     // ---- input ring (cp.async, as in column_kernel) and the c1 window --------------------------
     const uint32_t sbase = smem_u32(ring) + threadIdx.x * 8u;
     const uint32_t wbase = sbase + PAIR_RING_BYTES;
+    // The per-column scalars (temperature, surface porosity, the upper-boundary value of every variable) travel
+    // with layer 0 through cp.async as well: as plain loads they were ten dependent trips to HBM at the head
+    // of every column (the asm statements of the ring pin their order), a seventh of every warp's life
+    // (profiles/r02_summary.md).  They land in slots 2 and 3 of the c1 window, which stage A does not write
+    // before layer 2, when both upper boundaries have long been evaluated: no shared memory of their own (a
+    // larger carve-out leaves the L1 too small for the cp.async lines in flight, same file).
+    const uint32_t cbase = wbase + 2 * (NV * ROW_BYTES);
+    {
+        cp_async8(cbase, p.bdys + col);                                   // temp3d(:,:,k) = bdys(:,:,1), driver :602
+        if (p.por_mode == 2) cp_async8(cbase + ROW_BYTES, p.por + col);   // porosity(:,:,1), driver :411
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const int bc = (n < NPART) ? p.bcup_part : p.bcup_diss;
+            if (bc == 1 || bc == 4) cp_async8(cbase + (2 + n) * ROW_BYTES, p.fluxes + (size_t)n * ld + col);   // :783,:792
+            else if (bc == 2) cp_async8(cbase + (2 + n) * ROW_BYTES, p.bdys + (size_t)(n + 1) * ld + col);    // :786
+        }
+    }
     const double *g_in = in;
     int k_fetch = 0;
     auto fetch_next = [&]() {
@@ -99,12 +123,8 @@ pair_kernel(const __grid_constant__ KParams p)
 #pragma unroll
     for (int s = 0; s < RING_STAGES - 1; ++s) fetch_next();
 
-    const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
+    double por_surf = 1.0, cpart, cdiss, fT, temp;
     auto por_at = [&](int kk) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
-
-    const double temp = ld_ro(p.bdys + col);
-    double cpart, cdiss, fT;
-    column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
 
     // upper boundary of one step: F[n] = Flux(1) (diff3d :782-803), c0(n) = state of layer 1
     auto top_boundary = [&](auto c0, double por0, double (&F)[NV], bool write_fluxes) {
@@ -117,9 +137,9 @@ pair_kernel(const __grid_constant__ KParams p)
             const int bc = part ? p.bcup_part : p.bcup_diss;
             double f = 0.0;
             if (bc == 1 || bc == 4) {
-                f = ld_ro(p.fluxes + (size_t)n * ld + col);
+                f = lds64(cbase + (2 + n) * ROW_BYTES);
             } else if (bc == 2) {
-                const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
+                const double Cup = lds64(cbase + (2 + n) * ROW_BYTES);
                 const double c1 = c0(n);
                 const double C1 = part ? MSED_MUL(c1, por0) : c1;
                 f = top_flux_dirichlet(part ? Dp : Dd, C1, Cup, rdz0);
@@ -131,7 +151,10 @@ pair_kernel(const __grid_constant__ KParams p)
         }
     };
 
-    cp_async_wait<RING_STAGES - 2>();  // layer 0 has landed
+    cp_async_wait<RING_STAGES - 2>();  // layer 0 and the column's scalars have landed
+    if (p.por_mode == 2) por_surf = lds64(cbase + ROW_BYTES);
+    temp = lds64(cbase);
+    column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
     double FA[NV], FB[NV];
     // Step 1 reads the particulate input fluxes BEFORE step 2 may overwrite the dissolved entries of
     // the same array; with bcup_dissolved = 1 the dissolved input fluxes are read here as well and
