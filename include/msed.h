@@ -93,7 +93,7 @@ typedef struct msed_config {
     double rnit, ksO2nitri, rODUox, ksO2oduox, ksO2oxic, ksNO3denit, kinO2denit;
     double kinNO3anox, kinO2anox;
     double initial_value[MSED_NVAR]; /* ldetC sdetC detP po4 no3 nh3 oxy odu */
-    double minimum[MSED_NVAR];
+    double minimum[MSED_NVAR];   /* state_variables(n)%minimum, each >= 0 (msed_create returns MSED_ERR_ARG otherwise) */
     /* tile origin in the global grid (only used by MSED_MODEL_TEST_SOLVER and minloc reporting) */
     int32_t i_offset, j_offset;
 } msed_config;

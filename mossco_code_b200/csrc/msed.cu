@@ -112,6 +112,8 @@ struct msed_handle {
     int nranks = 1, rank = 0;
     msed_allreduce_hook hook = nullptr;
     void *hook_user = nullptr;
+    // TMA descriptors of the state-sized buffers pair_kernel reads (launch_pair), keyed by base pointer
+    std::vector<std::pair<const void *, CUtensorMap>> tmaps;
     std::string err;
 };
 
@@ -194,6 +196,7 @@ void fill_params(const msed_handle *h, KParams &p)
     p.fluxes = h->fluxes;
     p.mask = h->mask;
     p.colmap = nullptr;
+    p.feed_bulk = 0;
     p.ctl = h->ctl;
     p.ld = h->ld;
     p.ncol = h->ncol;
@@ -267,7 +270,45 @@ int ensure_denit(msed_handle *h)
     return MSED_OK;
 }
 
-cudaError_t launch_pair(const msed_handle *h, int method, const KParams &pin)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &st) != cudaSuccess ||
+            st != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// descriptor of one state buffer [nvar][K][ld] for pair_kernel's box copies; false if it cannot be made
+bool state_tmap(msed_handle *h, const double *base, CUtensorMap *out)
+{
+    for (const auto &e : h->tmaps)
+        if (e.first == base) { *out = e.second; return true; }
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)h->ld, (cuuint64_t)h->K, (cuuint64_t)NV};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->ld * 8, (cuuint64_t)h->ld * 8 * (cuuint64_t)h->K};
+    const cuuint32_t box[3] = {32, 1, (cuuint32_t)NV};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (h->tmaps.size() >= 8) h->tmaps.erase(h->tmaps.begin());
+    h->tmaps.emplace_back(base, m);
+    *out = m;
+    return true;
+}
+
+cudaError_t launch_pair(msed_handle *h, int method, const KParams &pin)
 {
     KParams p = pin;
     if (h->colmap) {  // masked tile: run over the wet columns of [col0, col_end) only
@@ -277,6 +318,14 @@ cudaError_t launch_pair(const msed_handle *h, int method, const KParams &pin)
         p.col_end = (int)(hi - h->wet_idx.begin());
         p.colmap = h->colmap;
         if (p.col_end <= p.col0) return cudaSuccess;  // all land: nothing to launch
+    }
+    p.feed_bulk = 0;
+    if (!h->has_land && !h->colmap) {
+        // opt-in: measured slower than the per-thread cp.async ring on B200 (profiles/r02_summary.md)
+        static const bool off = !(std::getenv("MSED_PAIR_FEED") && !std::strcmp(std::getenv("MSED_PAIR_FEED"), "bulk"));
+        if (!off && state_tmap(h, p.buf[0], &p.tmap[0]) && state_tmap(h, p.buf[1], &p.tmap[1]) &&
+            (!p.in_ovr || state_tmap(h, p.in_ovr, &p.tmap[2])))
+            p.feed_bulk = 1;
     }
     return tu_launch_pair(h->cfg.model, method == MSED_ADAPTIVE_EULER, p, h->stream);
 }
@@ -868,6 +917,8 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     if ((long long)cfg->inum * cfg->jnum > 0x7fffffffLL / 2)
         return fail(nullptr, MSED_ERR_ARG, "tile too large (inum*jnum)");
     if (cfg->model < 0 || cfg->model > 2) return fail(nullptr, MSED_ERR_ARG, "unknown model");
+    for (int n = 0; n < NV; ++n)   // the clip compares bit patterns (clip_min, msed_column.cuh); concentrations have no negative floor
+        if (!(cfg->minimum[n] >= 0.0)) return fail(nullptr, MSED_ERR_ARG, "state variable minimum must be >= 0");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -877,6 +928,7 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     msed_handle *h = new (std::nothrow) msed_handle();
     if (!h) return fail(nullptr, MSED_ERR_ALLOC, "host allocation failed");
     h->cfg = *cfg;
+    for (int n = 0; n < NV; ++n) h->cfg.minimum[n] += 0.0;   // -0.0 -> +0.0
     // auto fusion mode: tiles up to this many columns take the warp-per-column chain kernel when knum <= 32
     // measured on B200 (profiles/r01_chain_kernel.md): chains win below ~60k columns, where the thread-per-
     // column pair kernel cannot fill the machine (one wave = 148 SMs x 3 CTAs x 128 columns), and lose 5-10 % above

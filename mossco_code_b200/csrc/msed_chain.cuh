@@ -209,7 +209,7 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
             if (CLIP && final_sub) {
                 if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
                 const double mn = p.om.minimum[n];
-                newc = (newc < mn) ? mn : newc;
+                newc = clip_min(newc, mn);
             }
             cc[n] = newc;
         }

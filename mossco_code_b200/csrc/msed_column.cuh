@@ -190,6 +190,16 @@ __device__ __forceinline__ void violates_acc(int &acc, double fac, double c0, do
 {
     acc |= __double2hiint(fma(-fac, c0, newc));
 }
+// The component's clip, conc = max(conc, minimum) (fabm_sediment_component.F90:1728-1730), on the integer pipe: for a
+// minimum >= +0 "v < mn" is the signed comparison of the two bit patterns (non-negative doubles are ordered like
+// their bits, every negative double has the sign bit set and compares below) -- two ISETP instead of a DSETP on
+// the fp64 pipe, which bounds the fused kernels.  msed_create rejects a negative minimum and turns -0 into +0.
+// Where it differs from the floating-point test nothing observable changes: -0.0 becomes +0.0 under a zero
+// minimum, and a NaN with the sign bit set is replaced -- check_NaN looks at the value BEFORE the clip (:1718).
+__device__ __forceinline__ double clip_min(double v, double mn)
+{
+    return __double_as_longlong(v) < __double_as_longlong(mn) ? mn : v;
+}
 // per-column Arrhenius factors and diffusivity prefactors (driver :648,:652,:682; omexdia_p f_T)
 template <int MODEL, bool PROFILE3>
 __device__ __forceinline__ void column_constants(const KParams &p, double temp, double &cpart, double &cdiss,
@@ -530,7 +540,7 @@ column_kernel(const __grid_constant__ KParams p)
                     if (CLIP) {
                         if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);  // component :2392
                         const double mn = p.om.minimum[n];                  // :1728-1730
-                        newc = (newc < mn) ? mn : newc;
+                        newc = clip_min(newc, mn);
                     }
                     *go = newc;
                 }

@@ -476,7 +476,7 @@ __global__ void clip_kernel(Ctl *c, double *b0, double *b1, const unsigned char 
             const size_t q = (size_t)(n * K + k) * ld + col;
             const double v = s[q];
             nanf |= (v != v);
-            if (v < minimum.v[n]) s[q] = minimum.v[n];
+            if (__double_as_longlong(v) < __double_as_longlong(minimum.v[n])) s[q] = minimum.v[n];   // clip_min
         }
     if (nanf) { c->nan_detected = 1; c->stop = 1; }
 }

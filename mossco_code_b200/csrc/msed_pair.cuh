@@ -50,11 +50,55 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
-template <int MODEL, bool ADAPTIVE, bool DENIT, bool COLMAP = false, bool OVR = false>
+// ---- bulk asynchronous copies (TMA engine, no tensor map: the rows of the state are contiguous) -----------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "MSED_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra MSED_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// one box of a 3-D tensor, global -> shared, completion counted in bytes on an mbarrier (UTMALDG)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+// How the input state reaches shared memory:
+enum PairFeed : int {
+    FEED_CPASYNC = 0,  // every thread copies its own column, 8 bytes per row (LDGSTS through the L1)
+    FEED_COLMAP,       // the same over the wet-column list of a tile with land (columns of a warp are not contiguous)
+    FEED_BULK          // TMA: a warp's 32 columns x 8 variables of one layer are one box of the state tensor
+                       // [nvar][K][ld]; one cp.async.bulk.tensor per layer and warp, issued by lane 0, completion on a
+                       // warp-private mbarrier per ring slot; the data never passes through the L1
+};
+// FEED_BULK keeps the ring per warp: [warp][slot][variable][32 columns]
+constexpr uint32_t BULK_ROW_BYTES = 32 * 8;
+constexpr uint32_t BULK_STAGE_BYTES = NV * BULK_ROW_BYTES;
+static_assert(BULK_STAGE_BYTES * (COL_BLOCK / 32) == PAIR_STAGE_BYTES, "both ring layouts fill the same shared memory");
+
+template <int MODEL, bool ADAPTIVE, bool DENIT, int FEED = FEED_CPASYNC, bool OVR = false>
 __global__ void __launch_bounds__(COL_BLOCK, PAIR_MIN_BLOCKS)
 pair_kernel(const __grid_constant__ KParams p)
 {
+    constexpr bool COLMAP = FEED == FEED_COLMAP;
+    constexpr bool BULK = FEED == FEED_BULK;
     extern __shared__ __align__(16) double ring[];
+    __shared__ __align__(8) unsigned long long bars[(COL_BLOCK / 32) * RING_STAGES];
     const Ctl *ctl = p.ctl;
     // the plan this launch belongs to was made for one definite control state: after a failed group
     // (pairs_disabled) or anything else unforeseen the launch does nothing
@@ -64,17 +108,32 @@ pair_kernel(const __grid_constant__ KParams p)
     const double dt = p.dt_acc;
     // a pair whose violation flags are already up cannot be committed: later CTAs skip their work
     const volatile int *flags = ctl->flags;
-    if (ADAPTIVE && dt > ctl->dt_min && (flags[0] | flags[2])) return;
+    {
+        bool quit = ADAPTIVE && dt > ctl->dt_min && (flags[0] | flags[2]);
+        if (FEED == FEED_BULK) quit = __any_sync(0xffffffffu, quit);   // the warp is fed as a team: it leaves as one
+        if (quit) return;
+    }
 
     // On a tile with land the launch runs over the list of wet columns, so that every lane of a warp has
     // a column to integrate (a land lane idles for the whole walk down its neighbours' columns, and a CTA
     // with one wet warp holds a full CTA's registers and shared memory).  Wet neighbours stay neighbours:
     // accesses remain coalesced except where a run of land is skipped.
-    const int t = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
-    if (t >= p.col_end) return;
+    const int cta_col0 = p.col0 + blockIdx.x * COL_BLOCK;
+    const int lane = threadIdx.x & 31;
+    const int warp_col0 = cta_col0 + (int)(threadIdx.x & ~31u);
+    int t = cta_col0 + threadIdx.x;
+    if (BULK) {
+        // the warp is fed as a team: it stays whole, and a lane past the ragged end of the range walks the last
+        // column once more (same values to the same addresses).  The host picks this feed only for a tile
+        // without land.
+        if (warp_col0 >= p.col_end) return;
+        t = min(t, p.col_end - 1);
+    } else if (t >= p.col_end) {
+        return;
+    }
     const int col = COLMAP ? p.colmap[t] : t;   // COLMAP: the tile has land (a separate instantiation, so the
                                                 // land-free kernel keeps its register allocation)
-    if (p.mask[col] != 0) return;  // conc stays missing_value in both buffers
+    if (!BULK && p.mask[col] != 0) return;  // conc stays missing_value in both buffers
 
     const int K = p.K;
     const size_t ld = p.ld;
@@ -85,8 +144,11 @@ pair_kernel(const __grid_constant__ KParams p)
     double *out = (OVR ? p.out_ovr : p.buf[1 - cur]) + col;
 
     // ---- input ring (cp.async, as in column_kernel) and the c1 window --------------------------
-    const uint32_t sbase = smem_u32(ring) + threadIdx.x * 8u;
-    const uint32_t wbase = sbase + PAIR_RING_BYTES;
+    constexpr uint32_t SROW = BULK ? BULK_ROW_BYTES : ROW_BYTES;              // ring: distance between two variables
+    constexpr uint32_t SSTAGE = BULK ? BULK_STAGE_BYTES : PAIR_STAGE_BYTES;   // ... and between two slots
+    const uint32_t warp_ring = smem_u32(ring) + (threadIdx.x >> 5) * (RING_STAGES * BULK_STAGE_BYTES);
+    const uint32_t sbase = BULK ? warp_ring + (uint32_t)(t - warp_col0) * 8u : smem_u32(ring) + threadIdx.x * 8u;
+    const uint32_t wbase = smem_u32(ring) + threadIdx.x * 8u + PAIR_RING_BYTES;   // thread-private in every feed
     // The per-column scalars (temperature, surface porosity, the upper-boundary value of every variable) travel
     // with layer 0 through cp.async as well: as plain loads they were ten dependent trips to HBM at the head
     // of every column (the asm statements of the ring pin their order), a seventh of every warp's life
@@ -94,6 +156,17 @@ pair_kernel(const __grid_constant__ KParams p)
     // before layer 2, when both upper boundaries have long been evaluated: no shared memory of their own (a
     // larger carve-out leaves the L1 too small for the cp.async lines in flight, same file).
     const uint32_t cbase = wbase + 2 * (NV * ROW_BYTES);
+    // FEED_BULK: the warp's ring-slot barriers and the descriptor of the input buffer
+    const uint32_t bar0 = smem_u32(bars) + (threadIdx.x >> 5) * (RING_STAGES * 8u);
+    const CUtensorMap *tmap = OVR ? &p.tmap[2] : &p.tmap[cur];
+    if (BULK) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < RING_STAGES; ++s) mbar_init(bar0 + s * 8u, 1);
+            mbar_init_fence();
+        }
+        __syncwarp();
+    }
     {
         cp_async8(cbase, p.bdys + col);                                   // temp3d(:,:,k) = bdys(:,:,1), driver :602
         if (p.por_mode == 2) cp_async8(cbase + ROW_BYTES, p.por + col);   // porosity(:,:,1), driver :411
@@ -107,8 +180,20 @@ pair_kernel(const __grid_constant__ KParams p)
     const double *g_in = in;
     int k_fetch = 0;
     auto fetch_next = [&]() {
+        if (BULK) {
+            if (k_fetch < K) {
+                const uint32_t slot = (uint32_t)(k_fetch & (RING_STAGES - 1));
+                __syncwarp();   // every lane has finished with the layer that lived in this slot
+                if (lane == 0) {
+                    mbar_expect_tx(bar0 + slot * 8u, BULK_STAGE_BYTES);   // the whole box counts, clipped or not
+                    tma_load_3d(warp_ring + slot * BULK_STAGE_BYTES, tmap, warp_col0, k_fetch, 0, bar0 + slot * 8u);
+                }
+            }
+            ++k_fetch;
+            return;
+        }
         if (k_fetch < K) {
-            const uint32_t sa = sbase + (uint32_t)(k_fetch & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
+            const uint32_t sa = sbase + (uint32_t)(k_fetch & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;  // (not BULK)
             const double *g = g_in;
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
@@ -122,6 +207,7 @@ pair_kernel(const __grid_constant__ KParams p)
     };
 #pragma unroll
     for (int s = 0; s < RING_STAGES - 1; ++s) fetch_next();
+    if (BULK) cp_async_commit();  // the column's scalars
 
     double por_surf = 1.0, cpart, cdiss, fT, temp;
     auto por_at = [&](int kk) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
@@ -151,7 +237,13 @@ pair_kernel(const __grid_constant__ KParams p)
         }
     };
 
-    cp_async_wait<RING_STAGES - 2>();  // layer 0 and the column's scalars have landed
+    // layer kk has landed (kk < K)
+    auto wait_layer = [&](int kk) {
+        if (BULK) mbar_wait(bar0 + (uint32_t)(kk & (RING_STAGES - 1)) * 8u, (uint32_t)(kk / RING_STAGES) & 1u);
+        else cp_async_wait<RING_STAGES - 2>();
+    };
+    if (BULK) cp_async_wait<0>();
+    wait_layer(0);  // ... and the column's scalars
     if (p.por_mode == 2) por_surf = lds64(cbase + ROW_BYTES);
     temp = lds64(cbase);
     column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
@@ -159,7 +251,7 @@ pair_kernel(const __grid_constant__ KParams p)
     // Step 1 reads the particulate input fluxes BEFORE step 2 may overwrite the dissolved entries of
     // the same array; with bcup_dissolved = 1 the dissolved input fluxes are read here as well and
     // rewritten unchanged by step 2 (:692).
-    top_boundary([&](int n) { return lds64(sbase + n * ROW_BYTES); }, por_at(0), FA, false);
+    top_boundary([&](int n) { return lds64(sbase + n * SROW); }, por_at(0), FA, false);
 
     int viol1 = 0, viol2 = 0;  // sign bit = some relative change fell below relative_change_min (violates_acc)
     bool nan1 = false, nan2 = false;
@@ -238,7 +330,7 @@ pair_kernel(const __grid_constant__ KParams p)
             if (CLIP) {
                 if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
                 const double mn = p.om.minimum[n];
-                newc = (newc < mn) ? mn : newc;
+                newc = clip_min(newc, mn);
             }
             sink(n, newc);
         }
@@ -248,15 +340,15 @@ pair_kernel(const __grid_constant__ KParams p)
     // step 1, layer k: state from the ring, result into the c1 window; returns the layer coefficients
     auto stage_a = [&](auto has_next_tag, auto clip_tag, auto up_tag, int k) -> LayerCoef {
         fetch_next();
-        cp_async_wait<RING_STAGES - 2>();
-        const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
-        const uint32_t sn = sbase + (uint32_t)((k + 1) & (RING_STAGES - 1)) * PAIR_STAGE_BYTES;
+        if (!BULK || decltype(has_next_tag)::value) wait_layer(k + 1);
+        const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * SSTAGE;
+        const uint32_t sn = sbase + (uint32_t)((k + 1) & (RING_STAGES - 1)) * SSTAGE;
         const uint32_t wk = wbase + (uint32_t)(k & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
         const LayerCoef lc = make_coef(has_next_tag, k);
         double cc[NV];
 #pragma unroll
-        for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * ROW_BYTES);
-        step_layer(has_next_tag, clip_tag, up_tag, lc, cc, [&](int n) { return lds64(sn + n * ROW_BYTES); }, FA,
+        for (int n = 0; n < NV; ++n) cc[n] = lds64(sc + n * SROW);
+        step_layer(has_next_tag, clip_tag, up_tag, lc, cc, [&](int n) { return lds64(sn + n * SROW); }, FA,
                    viol1, nan1, [&](int n, double v) { sts64(wk + n * ROW_BYTES, v); }, nullptr);
         return lc;
     };
@@ -316,7 +408,7 @@ pair_kernel(const __grid_constant__ KParams p)
         default: sweep(N{}, N{}, N{}); break;
         }
     }
-    cp_async_wait<0>();
+    if (!BULK) cp_async_wait<0>();
 
     int *wf = p.ctl->flags;
     if (ADAPTIVE && viol1 < 0) atomicOr(&wf[0], 1);

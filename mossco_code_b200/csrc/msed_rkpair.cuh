@@ -254,7 +254,7 @@ rk_pair_kernel(const __grid_constant__ KParams p)
             if (!FIRST && decltype(clip_tag)::value) {  // final stage: check_NaN + clip (component :1718-1732)
                 if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
                 const double mn = p.om.minimum[n];
-                newc = (newc < mn) ? mn : newc;
+                newc = clip_min(newc, mn);
             }
             *go = newc;
             go += plane; gw1 += plane; gw2 += plane;

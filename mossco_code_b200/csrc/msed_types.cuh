@@ -5,6 +5,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cuda.h>   // CUtensorMap only: the driver entry point is looked up at run time, nothing links libcuda
 #include <cuda_runtime.h>
 #include <type_traits>
 
@@ -107,6 +108,11 @@ struct KParams {
     double *denit_out;       // [K][ld]: FABM denit diagnostic of the second step of a call's last pair, or null
     const int *colmap;       // pair_kernel on a masked tile: indices of the wet columns, ascending; col0/col_end
                              // then count wet columns (null: identity)
+    int feed_bulk;           // pair_kernel: the tensor maps below are valid and the tile has no masked column, so the
+                             // state may be fed to shared memory by TMA box copies (msed_pair.cuh, FEED_BULK)
+    // TMA descriptors of the state buffers as 3-D tensors [nvar][K][ld] of fp64, box = 32 columns x 1 layer x
+    // 8 variables: of buf[0], buf[1] and of in_ovr
+    alignas(64) CUtensorMap tmap[3];
     const double *in_ovr;    // pair_kernel<.., OVR>: explicit input / output state buffers of a launch inside a
     double *out_ovr;         // chunk-major sequence (msed.cu run_steps), instead of buf[cur] / buf[1-cur]
     // ---- the plan of a fused launch (msed.cu run_steps): which accepted sub-steps of the reference's attempt
