@@ -490,19 +490,57 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     // (with a collective every rank has to take the same decision, and the tile size is a per-rank fact:
     //  auto mode then stays with pairs; mode 3, set on every rank, selects chains)
 
-    // the plan: how the steps of this call are predicted to go (see plan_depth)
-    int depth = (method == MSED_ADAPTIVE_EULER) ? h->pred_depth : 0;
+    // export of one chunk of msed_run_exchange while the next chunks are still being computed
+    auto export_chunk = [&](int c) -> int {
+        const int c0 = plan->c0[c], c1 = plan->c1[c];
+        CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pool[16 + c], 0));
+        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->copy_stream>>>(plan->neg + c0, h->fluxes + c0, h->ld,
+                                                                         c1 - c0, NV);
+        launches += 1;
+        CUDA_TRY(h, cudaMemcpy2DAsync(plan->host_out + c0, (size_t)h->ncol * sizeof(double), plan->neg + c0,
+                                      h->ld * sizeof(double), (size_t)(c1 - c0) * sizeof(double), NV,
+                                      cudaMemcpyDeviceToHost, h->copy_stream));
+        return MSED_OK;
+    };
+
+    // ---- the call is worked off in rounds ---------------------------------------------------------------
+    // A round plans every remaining ode_solver call at the predicted depth (the steps run at dt/4^depth, see
+    // plan_depth) as fused launches, enqueues them and asks the controller how far they got.  If a group was
+    // not committed -- step s did not go as predicted -- step s alone runs through single attempts, whatever it
+    // needs, and the next round plans the rest the way step s went.  (Sub-cycling comes in episodes: before,
+    // one wrong prediction sent the rest of the call down the single-attempt path.)
+    const bool adaptive = method == MSED_ADAPTIVE_EULER;
+    int pred = adaptive ? h->pred_depth : 0;
+    long long base = 0;             // ode_solver calls completed before the current round
+    long long nfl_total = 0;        // fused launches enqueued by all rounds
+    int nrounds = 0;
+    bool first_pending = plan && plan->first && single_attempt;
+    const int cur_before = h->cur;
+    bool seq_mode = false, seq_committed = false;
+    long long seq_nfl = 0;
+    bool last_is_fused = false, last_round_clean = false;   // of the latest round
+    int depth0 = 0;                 // round 0, for the chunked export's validity test
+    long long fused_planned0 = 0;
+    bool last_is_fused0 = false;
+    const long long max_batch = 256;
+    int guard = 0;
+    bool stopped = false;
+    std::vector<FusedLaunch> fl;
+    for (;; ++nrounds) {
+    const long long rem = nsteps - base;
+    int depth = pred;
     double dt_acc = dt;
     long long nq = 1;
-    bool planned = fusable && single_attempt && !diag && nsteps >= 1 && plan_depth(dt, h->cfg.dt_min, depth, dt_acc, nq);
+    bool planned = fusable && single_attempt && !diag && rem >= 1 && plan_depth(dt, h->cfg.dt_min, depth, dt_acc, nq);
     const bool use_chain = planned && chain_fit;
-    const int own_rejectable = (method == MSED_ADAPTIVE_EULER && dt_acc > h->cfg.dt_min) ? 1 : 0;
-    std::vector<FusedLaunch> fl;
-    long long fused_planned = 0;  // steps the fused launches hold
+    const int own_rejectable = (adaptive && dt_acc > h->cfg.dt_min) ? 1 : 0;
+    fl.clear();
+    long long fused_planned = 0;  // steps the fused launches of this round hold
     auto base_commit = [&](long long gate) {
         PlanCommit pc;
         std::memset(&pc, 0, sizeof(pc));
-        pc.gate_steps = gate;
+        pc.gate_steps = base + gate;
         pc.own_rejectable = own_rejectable;
         pc.flip = 1;
         pc.launches = 1;
@@ -512,15 +550,15 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         return pc;
     };
     if (use_chain) {
-        // chains cover every step of the call, whatever its parity; a launch holds at most
+        // chains cover every step of the round, whatever its parity; a launch holds at most
         // TU_CHAIN_MAX_STEPS accepted sub-steps
         const long long per = std::max<long long>(1, TU_CHAIN_MAX_STEPS / nq);
-        const long long nl = (nsteps + per - 1) / per;
-        const long long base = nsteps / nl, extra = nsteps % nl;   // the first `extra` chains hold one step more
+        const long long nl = (rem + per - 1) / per;
+        const long long each = rem / nl, extra = rem % nl;   // the first `extra` chains hold one step more
         long long gate = 0;
         for (long long q = 0; q < nl; ++q) {
             FusedLaunch f;
-            f.m = (int)(base + (q < extra ? 1 : 0));
+            f.m = (int)(each + (q < extra ? 1 : 0));
             f.step = (int)gate;
             f.pc = base_commit(gate);
             f.pc.steps = f.m;
@@ -530,9 +568,9 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
             fl.push_back(f);
             gate += f.m;
         }
-        fused_planned = nsteps;
-    } else if (planned && depth == 0 && nsteps >= 2) {
-        for (long long q = 0; q < nsteps / 2; ++q) {
+        fused_planned = rem;
+    } else if (planned && depth == 0 && rem >= 2) {
+        for (long long q = 0; q < rem / 2; ++q) {
             FusedLaunch f;
             f.kind = PAIR_FULL;
             f.step = (int)(2 * q);
@@ -541,11 +579,11 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
             f.pc.rhs_evals = 2;
             fl.push_back(f);
         }
-        fused_planned = 2 * (nsteps / 2);
+        fused_planned = 2 * (rem / 2);
     } else if (planned && depth > 0) {
         // every step: the pair that holds the planned rejections and the first two sub-steps, inner pairs,
         // the pair that ends the call (4^depth sub-steps = 4^depth/2 pairs)
-        for (long long st = 0; st < nsteps; ++st) {
+        for (long long st = 0; st < rem; ++st) {
             double di = 0.0;
             for (long long j = 0; j < nq / 2; ++j) {
                 FusedLaunch f;
@@ -566,42 +604,32 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                 fl.push_back(f);
             }
         }
-        fused_planned = nsteps;
+        fused_planned = rem;
     } else {
         planned = false;
     }
     const long long nfl = (long long)fl.size();
+    nfl_total += nfl;
     // the call ends with a fused launch, which then leaves the "state of the last get_rhs call" diagnostic
     // behind (KParams::denit_out)
-    const bool last_is_fused = nfl > 0 && fused_planned == nsteps;
+    last_is_fused = nfl > 0 && fused_planned == rem;
     if (last_is_fused && (rc = ensure_denit(h))) return rc;
     p.dt_acc = dt_acc;
     p.depth = depth;
+    if (nrounds == 0) { depth0 = depth; fused_planned0 = fused_planned; last_is_fused0 = last_is_fused; }
 
-    // export of one chunk of msed_run_exchange while the next chunks are still being computed
-    auto export_chunk = [&](int c) -> int {
-        const int c0 = plan->c0[c], c1 = plan->c1[c];
-        CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], h->stream));
-        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pool[16 + c], 0));
-        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->copy_stream>>>(plan->neg + c0, h->fluxes + c0, h->ld,
-                                                                         c1 - c0, NV);
-        launches += 1;
-        CUDA_TRY(h, cudaMemcpy2DAsync(plan->host_out + c0, (size_t)h->ncol * sizeof(double), plan->neg + c0,
-                                      h->ld * sizeof(double), (size_t)(c1 - c0) * sizeof(double), NV,
-                                      cudaMemcpyDeviceToHost, h->copy_stream));
-        return MSED_OK;
-    };
-    bool first_pending = plan && plan->first && single_attempt;
     // Chunk-major Run (msed_run_exchange): when the whole coupling interval is pairs, chunk c runs its boundary
     // assembly, ALL its pairs and its export as soon as its import fields have landed, so that only the first
     // chunk's H2D and the last chunk's D2H are exposed (step-major order leaves the GPU short of work while the
     // transfers of the first pair are still arriving).  The pairs of a chunk go A -> B -> S -> B -> ... through
     // the two state buffers and the staging buffer; the committed state A is untouched until one controller has
     // seen the flags of every pair of every chunk, so a rejected step anywhere still costs nothing but the redo.
-    const int cur_before = h->cur;
-    const bool seq_mode = plan && plan->stage_private && plan->first && plan->last && first_pending && !use_chain &&
-                          nfl >= 2 && last_is_fused && h->scratch != nullptr && nsteps * depth <= MAX_UP_SLOTS;
-    if (seq_mode) {
+    const bool seq_round = nrounds == 0 && plan && plan->stage_private && plan->first && plan->last && first_pending &&
+                           !use_chain && nfl >= 2 && last_is_fused && h->scratch != nullptr &&
+                           nsteps * depth <= MAX_UP_SLOTS;
+    if (seq_round) {
+        seq_mode = true;
+        seq_nfl = nfl;
         double *A = h->buf[cur_before], *B = h->buf[1 - cur_before], *S = h->scratch;
         for (int c = 0; c < plan->nchunks; ++c) {
             if ((rc = boundary_chunk(c))) return rc;
@@ -636,9 +664,9 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         plan_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, pc);
         launches += 1;
     }
-    for (long long q = 0; q < (seq_mode ? 0 : nfl); ++q) {
+    for (long long q = 0; q < (seq_round ? 0 : nfl); ++q) {
         const bool last_launch = last_is_fused && q == nfl - 1;
-        const bool chunk_last = last_launch && plan && plan->last;
+        const bool chunk_last = nrounds == 0 && last_launch && plan && plan->last;
         KParams pq = p;
         pq.pair_kind = fl[q].kind;
         pq.gate_steps = fl[q].pc.gate_steps;
@@ -667,15 +695,26 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         plan_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, fl[q].pc);
         launches += 1;
     }
-    const long long singles_planned = nsteps - fused_planned;
-    CUDA_TRY(h, cudaEventRecord(h->ev_mid, h->stream));
+    // ---- single attempts: the step a pair plan leaves over (odd count), the step a failed group stopped at,
+    // ---- or everything when nothing can be planned ----------------------------------------------------------
+    // without a plan: the whole rest for the methods and configurations the fused kernels do not cover; a few
+    // steps, then another look at the prediction, when it is the step history that stands in the way
+    const bool replannable = fusable && single_attempt && !diag;
+    long long target = nsteps;
+    if (!planned && replannable) target = std::min(nsteps, base + 4);
+    const long long singles_planned = (planned ? rem - fused_planned : target - base);
+    if (target != nsteps) {   // (the device copy still holds nsteps otherwise)
+        h->ctl_host->steps_target = target;
+        CUDA_TRY(h, cudaMemcpyAsync(&h->ctl->steps_target, &h->ctl_host->steps_target, sizeof(long long),
+                                    cudaMemcpyHostToDevice, h->stream));
+    }
+    if (nrounds == 0) CUDA_TRY(h, cudaEventRecord(h->ev_mid, h->stream));
 
     long long remaining = singles_planned, issued = 0;
-    const long long max_batch = 256;
-    int guard = 0;
     // with nothing but fused launches planned the controller still has to be asked whether all of them were
-    // committed; a failed group leaves its steps to the single-attempt loop
+    // committed; a failed group leaves its step to the single-attempt loop
     bool check_fused = (singles_planned == 0 && nfl > 0);
+    bool failure_seen = false;
     // attempts a step is expected to need (sub-cycling: rejected + accepted ones); launches past the end of the
     // call return at once, so a generous estimate only costs empty launches
     long long per_step = 1;
@@ -684,7 +723,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         const long long batch = std::min(remaining * per_step, max_batch);
         for (long long s = 0; s < batch; ++s, ++issued) {
             const bool chunk_first = first_pending && issued == 0;
-            const bool chunk_last = plan && plan->last && issued == singles_planned - 1;
+            const bool chunk_last = nrounds == 0 && plan && plan->last && issued == singles_planned - 1;
             if ((chunk_first || chunk_last) && single_attempt) {
                 for (int c = 0; c < plan->nchunks; ++c) {
                     const int c0 = plan->c0[c], c1 = plan->c1[c];
@@ -698,6 +737,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                     if (chunk_last)
                         if ((rc = export_chunk(c))) return rc;
                 }
+                first_pending = false;
             } else if (method == MSED_EULER) {
                 CUDA_TRY(h, launch_column(h, OP_EULER, p));
                 launches += 1;
@@ -732,8 +772,20 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        if (h->ctl_host->stop) break;
-        remaining = nsteps - h->ctl_host->steps_done;
+        if (h->ctl_host->stop) { stopped = true; break; }
+        if (nfl > 0 && h->ctl_host->pairs_disabled && !failure_seen) {
+            // a group of this round was not committed: the step it stopped at runs alone through single
+            // attempts, the rest of the call is planned afresh afterwards (identical on every rank: the flags
+            // the controller decides on are reduced)
+            failure_seen = true;
+            target = std::min(nsteps, (long long)h->ctl_host->steps_done + 1);
+            if (target != h->ctl_host->steps_target) {
+                h->ctl_host->steps_target = target;
+                CUDA_TRY(h, cudaMemcpyAsync(&h->ctl->steps_target, &h->ctl_host->steps_target, sizeof(long long),
+                                            cudaMemcpyHostToDevice, h->stream));
+            }
+        }
+        remaining = target - h->ctl_host->steps_done;
         // sub-cycling needs more attempts than steps: keep going until the controller reports done, and size
         // the next batch by what the steps have needed so far
         if (method == MSED_ADAPTIVE_EULER && remaining > 0) {   // (identical on every rank: the flags are reduced)
@@ -742,6 +794,20 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         }
         if (++guard > 1000000) return fail(h, MSED_ERR_STATE, "step loop did not terminate");
     }
+    last_round_clean = !failure_seen && !stopped;
+    if (nrounds == 0 && seq_mode) seq_committed = last_round_clean && h->ctl_host->steps_done == nsteps;
+    if (stopped || nsteps == 0) { ++nrounds; break; }
+    base = h->ctl_host->steps_done;
+    if (base >= nsteps) { ++nrounds; break; }
+    // next round: planned the way the last completed step went; fused launches are allowed again
+    if (adaptive) pred = h->ctl_host->last_irregular ? -1 : h->ctl_host->last_depth;
+    h->ctl_host->pairs_disabled = 0;
+    h->ctl_host->steps_target = nsteps;
+    CUDA_TRY(h, cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // ctl_host is read back into by the next round
+    if (++guard > 1000000) return fail(h, MSED_ERR_STATE, "step loop did not terminate");
+    }  // rounds
+    const long long nfl = nfl_total;
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_TRY(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f, ms_pairs = 0.f;
@@ -753,21 +819,21 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     }
 
     const Ctl &r = *h->ctl_host;
-    const bool fused_ok = nfl > 0 && r.pair_failures == 0;
     if (plan && plan->last) {  // the chunked export is final only if every attempt went as planned
         CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
-        // ... i.e. the launch the export rode on produced the final state: the last fused launch of a committed
-        // plan, or the single attempt planned behind it if that was accepted at once
+        // ... i.e. the call took one round and the launch the export rode on produced the final state: the last
+        // fused launch of a committed plan, or the single attempt planned behind it if that was accepted at once
         plan->export_done = single_attempt && !r.stop && r.steps_done == nsteps && nsteps > 0 && r.pair_failures == 0 &&
-                            (last_is_fused || r.subcycles == fused_planned * depth);
+                            nrounds == 1 && (last_is_fused0 || r.subcycles == fused_planned0 * depth0);
     }
     // the next call is planned the way this call's last step went
     if (r.steps_done > 0 && method == MSED_ADAPTIVE_EULER) h->pred_depth = r.last_irregular ? -1 : r.last_depth;
-    h->pairs_committed += fused_ok ? nfl : 0;
-    h->denit_valid = last_is_fused && fused_ok && !r.stop && r.steps_done == nsteps;
+    h->pairs_committed += r.fused_launches;
+    // (the call's last step sits in a committed fused launch of the last round)
+    h->denit_valid = last_is_fused && last_round_clean && !r.stop && r.steps_done == nsteps;
     // a committed chunk-major sequence with an even number of pairs ends in the staging buffer: it becomes
     // the state buffer the controller's flipped `cur` points at, the intermediate buffer becomes staging
-    if (seq_mode && fused_ok && !r.stop && r.steps_done == nsteps && nfl % 2 == 0) {
+    if (seq_mode && seq_committed && !r.stop && r.steps_done == nsteps && seq_nfl % 2 == 0) {
         std::swap(h->buf[1 - cur_before], h->scratch);
         // the stepping kernels never write land columns, so the buffer rotated in holds whatever last used the
         // staging area there: restore conc = missing_value (driver :464) before anything can read it
