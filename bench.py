@@ -152,6 +152,31 @@ class ClockSampler:
                 "power_w_max": float(max(power)), "samples": len(sm)}
 
 
+def pin_rank_to_gpu_numa(local_rank):
+    """Keep this rank -- and with it the pinned host buffers it is about to touch first -- on the NUMA node its GPU
+    hangs off, when the box has more than one: eight ranks that all allocate on node 0 push every import and
+    export field of a Run through one socket's memory (VERDICT r1 weak #5).  Returns what was done."""
+    import torch
+    try:
+        nodes = [n for n in os.listdir("/sys/devices/system/node") if n.startswith("node") and n[4:].isdigit()]
+        p = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(path + "/numa_node").read().strip())
+        if len(nodes) < 2 or node < 0:
+            return {"numa_nodes": len(nodes), "gpu_numa_node": node, "pinned": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_nodes": len(nodes), "gpu_numa_node": node, "pinned": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_nodes": len(nodes), "gpu_numa_node": node, "pinned": True, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001  (sysfs layout differs between hosts: measuring must not depend on it)
+        return {"pinned": False, "error": repr(e)[:80]}
+
+
 def pinned_fortran(shape):
     """Pinned host buffer viewed as a Fortran-ordered numpy array of ``shape``."""
     import torch
@@ -290,6 +315,7 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local_rank)
+    numa_info = pin_rank_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -482,10 +508,25 @@ def main():
         to_subcycling_episode()
     else:
         sed.init_concentrations()
+    # The three sinking velocities are constants of the synthetic pelagic side, as they are in most pelagic
+    # models: the coupler declares them static (component.static_import_suffixes -> msed_set_import_generations)
+    # and they cross PCIe once, in the warm-up Run; the other nine fields are uploaded every Run.
+    # e2e_all_fields below is the same measurement with every field uploaded every Run.
+    static_suffix = "_z_velocity_at_soil_surface"
+    h2d_static = sum(a.nbytes for k, a in imp.items() if k.endswith(static_suffix))
+    comp.static_import_suffixes = (static_suffix,)
     comp.run(imp, exp, run_seconds=COUPLING_SECONDS)        # warm-up Run
     e2e_s = timed_runs(nruns)
     d2h = sum(exp[f"{v}_upward_flux_at_soil_surface"].nbytes for v in VARIABLE_NAMES)
     e2e_value = cells_total * nruns * steps_per_run / e2e_s
+    comp.static_import_suffixes = ()
+    sed.set_import_generations(None)
+    if subcyc:
+        to_subcycling_episode()
+    else:
+        sed.init_concentrations()
+    comp.run(imp, exp, run_seconds=COUPLING_SECONDS)
+    e2e_all_value = cells_total * nruns * steps_per_run / timed_runs(nruns)
 
     # ---- the same with the <name>_in_soil write-back at an output cadence ---------------------------------
     # The reference copies all nvar 3-D states to their fields every Run (:1773-1822); consumers read them at the
@@ -600,16 +641,22 @@ def main():
                        "state_checksum": {"sum_mod_2_64": f"{cs_sum:016x}", "xor": f"{cs_xor:016x}",
                                           "of": "state after the timed steps, msed_state_checksum over all tiles: "
                                                 "identical for every N"},
-                       "e2e_call": f"FabmSedimentComponent.run({int(COUPLING_SECONDS)} s) -> msed_run_exchange: H2D of 12 "
-                                   f"pinned import fields + get_boundary_conditions + {steps_per_run} ode_solver "
+                       "host_numa": numa_info,
+                       "e2e_call": f"FabmSedimentComponent.run({int(COUPLING_SECONDS)} s) -> msed_run_exchange: H2D of 9 "
+                                   f"pinned import fields (12 in e2e_all_fields) + get_boundary_conditions + {steps_per_run} ode_solver "
                                    f"steps + D2H of 8 upward-flux fields (chunk-major: every chunk runs the whole "
                                    f"interval as soon as its fields have landed); {nruns} timed Run(s); WITHOUT the "
                                    f"3-D <name>_in_soil write-back, which e2e_with_export adds at its cadence"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "cell-updates/s",
-                    "h2d_bytes_per_step": h2d / steps_per_run, "d2h_bytes_per_step": d2h / steps_per_run,
-                    "h2d_bytes_per_run": h2d, "d2h_bytes_per_run": d2h, "steps_per_run": steps_per_run,
-                    "includes_3d_export": False},
+                    "h2d_bytes_per_step": (h2d - h2d_static) / steps_per_run, "d2h_bytes_per_step": d2h / steps_per_run,
+                    "h2d_bytes_per_run": h2d - h2d_static, "d2h_bytes_per_run": d2h, "steps_per_run": steps_per_run,
+                    "includes_3d_export": False,
+                    "static_import_fields": "the 3 *_z_velocity_at_soil_surface fields (constant sinking speeds) are "
+                                            "declared static and uploaded once, outside the timed Runs"},
+            "e2e_all_fields": {"value": e2e_all_value, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d / steps_per_run,
+                               "d2h_bytes_per_step": d2h / steps_per_run,
+                               "note": "every one of the 12 import fields uploaded every Run"},
             "e2e_with_export": e2e_export,
             "gpu_launches": launches,
             "roofline": roof,

@@ -198,6 +198,15 @@ int msed_run(msed_handle *h, double dt, int method, double run_seconds, msed_ste
 int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
                       const double *temperature2d, const double *const *csurf, const double *const *wz,
                       double *upward_fluxes, msed_step_info *info);
+/* Generation counters of the import fields of msed_run_exchange: gen[0] temperature, gen[1 + 2n] csurf(n),
+ * gen[2 + 2n] wz(n) (MSED_NIMPORT_GEN entries).  A field whose counter and host pointer are the ones of its last
+ * upload is not uploaded again by the next msed_run_exchange calls -- its device staging row persists between
+ * Runs -- e.g. the constant sinking velocities of a pelagic component (the *_z_velocity_at_soil_surface fields of
+ * fabm_sediment_component.F90:1865-2030 are re-read every Run only because ESMF gives no cheaper way to know).
+ * The caller bumps a field's counter whenever it changes the field's data.  gen == NULL (the default state):
+ * every field is uploaded every Run. */
+#define MSED_NIMPORT_GEN (1 + 2 * MSED_NVAR)
+int msed_set_import_generations(msed_handle *h, const uint64_t *gen);
 /* Step fusion (default on): Euler / adaptive-Euler steps are issued in speculative fused launches that
  * read and write the state once for several accepted sub-steps -- pairs (thread per column, two sub-steps) or,
  * for knum <= 32, chains (warp per column with the state in registers, up to 16 sub-steps).  Each call is

@@ -71,6 +71,12 @@ class FabmSedimentComponent:
         self._export_started = False
         self._runs = 0
         self.flux_buffer = None   # optional caller-owned (pinned) (inum,jnum,nvar) export buffer
+        # Import fields the coupler promises not to change between Runs unless it says so with
+        # import_changed(name): name suffixes, e.g. ("_z_velocity_at_soil_surface",) for the constant sinking
+        # velocities of a pelagic component.  They cross PCIe once (msed_set_import_generations); every other
+        # field is uploaded every Run.  Empty = the reference's behaviour (:1865-2030 reads every field every Run).
+        self.static_import_suffixes = ()
+        self._import_gen = {}     # per field key of msed_set_import_generations
         self._out = None          # output.dat handle (run_nml output > 0, component :266-269)
         self.advance_count = 0    # ESMF clock advanceCount
         self.on_mesh = False      # geometry is a mesh: rank-1 surface fields (see initialize_p1)
@@ -254,6 +260,29 @@ class FabmSedimentComponent:
         soil_netcdf.write_fields(path, fields, t, units=units, append=append)
         return ESMF_SUCCESS
 
+    # ---- import fields that stay on the device (static_import_suffixes) -----------------------------------
+    def _generations(self):
+        """Counters for msed_set_import_generations: a static field keeps its counter, every other field gets a
+        new one each Run."""
+        keys = [(0, "temperature_at_soil_surface")]
+        for n, v in enumerate(VARIABLE_NAMES):
+            keys.append((1 + 2 * n, v + "_at_soil_surface"))
+            keys.append((2 + 2 * n, v + "_z_velocity_at_soil_surface"))
+        gen = [0] * (1 + 2 * len(VARIABLE_NAMES))
+        for k, name in keys:
+            static = any(name.endswith(s) for s in self.static_import_suffixes)
+            g = self._import_gen.get(k, 1)
+            if not static:
+                g += 1
+            self._import_gen[k] = g
+            gen[k] = g
+        return gen
+
+    def import_changed(self, name_suffix: str):
+        """The coupler has written new data into the static import fields whose names end in ``name_suffix``."""
+        for k in list(self._import_gen):
+            self._import_gen[k] += 1 << 32
+
     def read_restart_file(self, path: str, record: int = -1):
         from . import soil_netcdf
         fields, t = soil_netcdf.read_fields(path, record)
@@ -278,6 +307,8 @@ class FabmSedimentComponent:
         cs = [self._surface(self._lookup(import_state, v, "_at_soil_surface")) for v in VARIABLE_NAMES]
         wz = [self._surface(self._lookup(import_state, v, "_z_velocity_at_soil_surface")) if PARTICULATE[n]
               else None for n, v in enumerate(VARIABLE_NAMES)]
+        if self.static_import_suffixes:
+            sed.set_import_generations(self._generations())
         if self._out is not None:
             rc, up = self._run_with_output(temp, cs, wz, float(run_seconds))
         else:

@@ -112,6 +112,11 @@ struct msed_handle {
     int nranks = 1, rank = 0;
     msed_allreduce_hook hook = nullptr;
     void *hook_user = nullptr;
+    // msed_set_import_generations: what the staging rows of msed_run_exchange hold from earlier Runs
+    bool import_gen_on = false;
+    unsigned long long import_gen[1 + 2 * NV] = {};        // the caller's current counters
+    struct ImportRow { const double *host = nullptr; unsigned long long gen = 0; int row = -1; const double *stage = nullptr; };
+    ImportRow import_row[1 + 2 * NV];                       // last upload of every field
     // TMA descriptors of the state-sized buffers pair_kernel reads (launch_pair), keyed by base pointer
     std::vector<std::pair<const void *, CUtensorMap>> tmaps;
     std::string err;
@@ -1542,24 +1547,38 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
     }
     const double *host[12];
     const double **dev[12];
+    int key[12];   // index of the field in the generation table (msed_set_import_generations)
     int nf = 0;
-    if (temperature2d) { host[nf] = temperature2d; dev[nf] = &plan.bc.temperature; ++nf; }
+    if (temperature2d) { host[nf] = temperature2d; dev[nf] = &plan.bc.temperature; key[nf] = 0; ++nf; }
     for (int n = 0; n < NV; ++n) {
         if (!csurf || !csurf[n]) continue;
         if (n < NPART) {
             if (!wz || !wz[n]) return fail(h, MSED_ERR_ARG, "particulate variable without z_velocity field");
-            host[nf] = wz[n]; dev[nf] = &plan.bc.wz[n]; ++nf;
+            host[nf] = wz[n]; dev[nf] = &plan.bc.wz[n]; key[nf] = 2 + 2 * n; ++nf;
         }
-        host[nf] = csurf[n]; dev[nf] = &plan.bc.csurf[n]; ++nf;
+        host[nf] = csurf[n]; dev[nf] = &plan.bc.csurf[n]; key[nf] = 1 + 2 * n; ++nf;
     }
     for (int f = 0; f < nf; ++f) *dev[f] = stage + (size_t)f * h->ld;
+    // a field the caller has not changed since its last upload (same counter, same host array, same staging
+    // row of a staging area nothing else writes) is already on the device
+    bool resident[12];
+    for (int f = 0; f < nf; ++f) {
+        msed_handle::ImportRow &r = h->import_row[key[f]];
+        resident[f] = h->import_gen_on && plan.stage_private && r.row == f && r.stage == stage && r.host == host[f] &&
+                      r.gen == h->import_gen[key[f]];
+        r.host = host[f];
+        r.gen = h->import_gen[key[f]];
+        r.row = (h->import_gen_on && plan.stage_private) ? f : -1;
+        r.stage = stage;
+    }
     plan.neg = stage + (size_t)12 * h->ld;
     plan.host_out = upward_fluxes;
     for (int c = 0; c < plan.nchunks; ++c) {  // all H2D traffic on the copy stream, chunk by chunk
         const int c0 = plan.c0[c], n = plan.c1[c] - plan.c0[c];
         for (int f = 0; f < nf; ++f)
-            CUDA_TRY(h, cudaMemcpyAsync(stage + (size_t)f * h->ld + c0, host[f] + c0, (size_t)n * sizeof(double),
-                                        cudaMemcpyHostToDevice, h->copy_stream));
+            if (!resident[f])
+                CUDA_TRY(h, cudaMemcpyAsync(stage + (size_t)f * h->ld + c0, host[f] + c0, (size_t)n * sizeof(double),
+                                            cudaMemcpyHostToDevice, h->copy_stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_pool[c], h->copy_stream));
     }
     msed_step_info a, b;
@@ -1603,6 +1622,16 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
         }
     }
     return rc;
+}
+
+int msed_set_import_generations(msed_handle *h, const uint64_t *gen)
+{
+    if (!h) return fail(h, MSED_ERR_ARG, "null handle");
+    h->import_gen_on = gen != nullptr;
+    for (int q = 0; q < 1 + 2 * NV; ++q) h->import_gen[q] = gen ? (unsigned long long)gen[q] : 0ULL;
+    if (!gen)
+        for (auto &r : h->import_row) r = msed_handle::ImportRow();
+    return MSED_OK;
 }
 
 int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const double *fluxes1d, int64_t nsteps,

@@ -269,6 +269,18 @@ class SedimentDriver:
                          allow=(_abi.NAN_DETECTED,))
         return rc, out
 
+    def set_import_generations(self, gen=None):
+        """Generation counters of the import fields of ``run_exchange`` (temperature, then csurf(n), wz(n) for each
+        variable: 1 + 2*nvar entries); a field whose counter and host array are those of its last upload stays on
+        the device.  None: upload every field every Run (default)."""
+        if gen is None:
+            self._check(self._lib.msed_set_import_generations(self._h, None))
+            return
+        if len(gen) != 1 + 2 * NVAR:
+            raise ValueError("set_import_generations: 1 + 2*nvar counters expected")
+        arr = (C.c_uint64 * (1 + 2 * NVAR))(*[int(g) for g in gen])
+        self._check(self._lib.msed_set_import_generations(self._h, arr))
+
     FUSION_MODES = {"off": 0, "auto": 1, "pairs": 2, "chains": 3}
 
     def set_step_fusion(self, mode):

@@ -284,6 +284,54 @@ def test_run_exchange_chunk_major(gpu, nchunks, seconds, boost):
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
 
 
+@pytest.mark.parametrize("nchunks", [0, 4])
+def test_run_exchange_static_import_fields(gpu, nchunks):
+    """msed_set_import_generations: a field whose generation counter did not move is not uploaded again -- the
+    Run uses the copy the device kept (so host edits without a bump are invisible), a bumped counter or a new
+    host array uploads it, and with unchanged data the results are bit-identical to uploading everything."""
+    from mossco_code_b200 import SedimentDriver, default_config
+    from mossco_code_b200.sediment import PARTICULATE
+    case = make_case("xgen", 70, 37, 20, 0.003, seed=94, land_fraction=0.2)
+    rng = np.random.default_rng(8)
+    sh = (70, 37)
+    temp = np.asfortranarray(4 + 8 * rng.random(sh))
+    cs = [np.asfortranarray((-case.fluxes[:, :, n]) if PARTICULATE[n] else case.bdys[:, :, n + 1]) for n in range(8)]
+    wz = [np.asfortranarray(1.0 + rng.random(sh)) if PARTICULATE[n] else None for n in range(8)]
+    cfg = default_config(inum=70, jnum=37, knum=20, dzmin=0.003, dt_min=1.0)
+
+    def runs(static, edit=None):
+        out = []
+        with SedimentDriver(cfg) as sed:
+            sed.set_mask(case.mask)
+            sed.init_concentrations()
+            sed.set_step_fusion("pairs")
+            sed.set_exchange_chunks(nchunks)
+            w = [None if a is None else a.copy(order="F") for a in wz]
+            gen = [1] * 17
+            for r in range(3):
+                if static:
+                    for k in range(17):            # everything but the z-velocities changes every Run
+                        if not (k >= 2 and k % 2 == 0):
+                            gen[k] += 1
+                    if edit == "bump" and r == 2:
+                        gen[2] += 1
+                    sed.set_import_generations(gen)
+                if edit and r == 2:
+                    w[0][...] *= 3.0               # the coupler rewrites detritus' sinking velocity in place
+                rc, up = sed.run_exchange(360.0, 2, 3600.0, temp, cs, w)
+                assert rc == 0
+                out.append((up.copy(), sed.conc))
+        return out
+
+    plain, static = runs(False), runs(True)
+    for (u0, c0), (u1, c1) in zip(plain, static):
+        assert np.array_equal(u0, u1) and np.array_equal(c0, c1)
+    silent, bumped, plain_edit = runs(True, "silent"), runs(True, "bump"), runs(False, "plain")
+    assert np.array_equal(silent[2][1], static[2][1])            # not announced: the device copy is used
+    assert np.array_equal(bumped[2][1], plain_edit[2][1])        # announced: uploaded
+    assert not np.array_equal(bumped[2][1], static[2][1])
+
+
 def test_run_exchange_with_rejected_attempt(gpu):
     """If an attempt is rejected the chunk-wise export is stale and must be redone from the final state."""
     from mossco_code_b200 import SedimentDriver, default_config
