@@ -519,6 +519,17 @@ def main():
     e2e_s = timed_runs(nruns)
     d2h = sum(exp[f"{v}_upward_flux_at_soil_surface"].nbytes for v in VARIABLE_NAMES)
     e2e_value = cells_total * nruns * steps_per_run / e2e_s
+    # where the last timed Run spent its time on each rank's device (msed_get_exchange_timing): with transfers fully
+    # hidden the span is the kernels' time; the excess is exposed PCIe traffic (profiles/r02_n8_pcie_contention.json)
+    ph = [round(x, 3) for x in sed.exchange_timing()]
+    phases = [ph]
+    if world > 1:
+        phases = [None] * world
+        dist.all_gather_object(phases, ph)
+    e2e_phases = {"wall_ms_per_run": round(1e3 * e2e_s / nruns, 3),
+                  "per_rank_ms": {"last_h2d_landed": [p_[0] for p_ in phases], "last_kernel_done": [p_[1] for p_ in phases],
+                                  "d2h_tail_after_kernels": [p_[2] for p_ in phases], "device_span": [p_[3] for p_ in phases]},
+                  "of": "the last timed Run, ms since its first import copy was issued"}
     comp.static_import_suffixes = ()
     sed.set_import_generations(None)
     if subcyc:
@@ -654,6 +665,7 @@ def main():
                     "includes_3d_export": False,
                     "static_import_fields": "the 3 *_z_velocity_at_soil_surface fields (constant sinking speeds) are "
                                             "declared static and uploaded once, outside the timed Runs"},
+            "e2e_phases": e2e_phases,
             "e2e_all_fields": {"value": e2e_all_value, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d / steps_per_run,
                                "d2h_bytes_per_step": d2h / steps_per_run,
                                "note": "every one of the 12 import fields uploaded every Run"},

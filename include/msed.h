@@ -205,6 +205,11 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
  * fabm_sediment_component.F90:1865-2030 are re-read every Run only because ESMF gives no cheaper way to know).
  * The caller bumps a field's counter whenever it changes the field's data.  gen == NULL (the default state):
  * every field is uploaded every Run. */
+/* Device-side phase marks of the last pipelined msed_run_exchange, in ms from the moment its first import copy was
+ * issued: ms4[0] last import field landed (H2D), ms4[1] last stepping kernel done, ms4[2] from there to the last
+ * flux field landed on the host (the exposed D2H tail; negative if the copies were done first), ms4[3] whole
+ * span.  A measuring aid for the overlap of transfers and kernels (bench.py e2e_phases). */
+int msed_get_exchange_timing(const msed_handle *h, double *ms4);
 #define MSED_NIMPORT_GEN (1 + 2 * MSED_NVAR)
 int msed_set_import_generations(msed_handle *h, const uint64_t *gen);
 /* Step fusion (default on): Euler / adaptive-Euler steps are issued in speculative fused launches that

@@ -155,6 +155,7 @@ SYMBOLS = {
     "msed_step": (C.c_int, [_h, C.c_double, C.c_int, C.c_int64, C.POINTER(StepInfo)]),
     "msed_run": (C.c_int, [_h, C.c_double, C.c_int, C.c_double, C.POINTER(StepInfo)]),
     "msed_set_import_generations": (C.c_int, [_h, C.POINTER(C.c_uint64)]),
+    "msed_get_exchange_timing": (C.c_int, [_h, C.POINTER(C.c_double)]),
     "msed_run_exchange": (C.c_int, [_h, C.c_double, C.c_int, C.c_double, _dp, C.POINTER(_dp), C.POINTER(_dp),
                                     _dp, C.POINTER(StepInfo)]),
     "msed_set_exchange_chunks": (C.c_int, [_h, C.c_int]),

@@ -96,8 +96,12 @@ struct msed_handle {
     double last_min_dt = (double)1.e20f;  // solver_library.F90:44 (default-real literal)
     int last_min_dt_grid_cell[4] = {-99, -99, -99, -99};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
-    cudaStream_t copy_stream = nullptr;           // PCIe traffic of msed_run_exchange
+    cudaStream_t copy_stream = nullptr;           // msed_run_exchange: H2D of the import fields
+    cudaStream_t d2h_stream = nullptr;            // ... D2H of the bed fluxes, on its own stream: the fluxes of chunk c
+                                                  // leave while the import fields of later chunks still arrive
     cudaEvent_t ev_pool[2 * 16] = {};             // per-chunk H2D-done / compute-done events
+    cudaEvent_t ev_x[3] = {};                     // msed_run_exchange phase marks: first H2D issued, last H2D landed, last D2H landed
+    double exchange_ms[4] = {0, 0, 0, 0};         // msed_get_exchange_timing of the last pipelined msed_run_exchange
     int exchange_chunks = 0;                      // 0 = choose from the tile size
     int step_fusion = 1;                          // 0 off, 1 auto (chains where they apply, else pairs),
                                                   // 2 pairs only, 3 chains wherever knum allows
@@ -499,13 +503,13 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     auto export_chunk = [&](int c) -> int {
         const int c0 = plan->c0[c], c1 = plan->c1[c];
         CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], h->stream));
-        CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_pool[16 + c], 0));
-        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->copy_stream>>>(plan->neg + c0, h->fluxes + c0, h->ld,
+        CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_pool[16 + c], 0));
+        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->d2h_stream>>>(plan->neg + c0, h->fluxes + c0, h->ld,
                                                                          c1 - c0, NV);
         launches += 1;
         CUDA_TRY(h, cudaMemcpy2DAsync(plan->host_out + c0, (size_t)h->ncol * sizeof(double), plan->neg + c0,
                                       h->ld * sizeof(double), (size_t)(c1 - c0) * sizeof(double), NV,
-                                      cudaMemcpyDeviceToHost, h->copy_stream));
+                                      cudaMemcpyDeviceToHost, h->d2h_stream));
         return MSED_OK;
     };
 
@@ -825,7 +829,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
 
     const Ctl &r = *h->ctl_host;
     if (plan && plan->last) {  // the chunked export is final only if every attempt went as planned
-        CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
         // ... i.e. the call took one round and the launch the export rode on produced the final state: the last
         // fused launch of a committed plan, or the single attempt planned behind it if that was accepted at once
         plan->export_done = single_attempt && !r.stop && r.steps_done == nsteps && nsteps > 0 && r.pair_failures == 0 &&
@@ -1058,7 +1062,9 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     for (auto &e : h->ev_pool) CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : h->ev_x) CREATE_TRY(cudaEventCreate(&e));
     CREATE_TRY(cudaEventCreate(&h->ev0));
     CREATE_TRY(cudaEventCreate(&h->ev_mid));
     CREATE_TRY(cudaEventCreate(&h->ev1));
@@ -1112,6 +1118,7 @@ int msed_destroy(msed_handle *h)
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev_mid) cudaEventDestroy(h->ev_mid);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1573,6 +1580,7 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
     }
     plan.neg = stage + (size_t)12 * h->ld;
     plan.host_out = upward_fluxes;
+    CUDA_TRY(h, cudaEventRecord(h->ev_x[0], h->copy_stream));
     for (int c = 0; c < plan.nchunks; ++c) {  // all H2D traffic on the copy stream, chunk by chunk
         const int c0 = plan.c0[c], n = plan.c1[c] - plan.c0[c];
         for (int f = 0; f < nf; ++f)
@@ -1581,6 +1589,7 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
                                             cudaMemcpyHostToDevice, h->copy_stream));
         CUDA_TRY(h, cudaEventRecord(h->ev_pool[c], h->copy_stream));
     }
+    CUDA_TRY(h, cudaEventRecord(h->ev_x[1], h->copy_stream));
     msed_step_info a, b;
     std::memset(&a, 0, sizeof(a));
     std::memset(&b, 0, sizeof(b));
@@ -1599,7 +1608,18 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
         rc = run_steps(h, rem, method, 1, true, &b, &plan);
         exported = plan.export_done;
     }
+    CUDA_TRY(h, cudaEventRecord(h->ev_x[2], h->d2h_stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));
+    {   // phase marks of this Run (msed_get_exchange_timing); ev0 / ev1 bracket the kernels of the last run_steps
+        float t01 = 0.f, t0k = 0.f, tk2 = 0.f, t02 = 0.f;
+        cudaEventElapsedTime(&t01, h->ev_x[0], h->ev_x[1]);
+        cudaEventElapsedTime(&t0k, h->ev_x[0], h->ev1);
+        cudaEventElapsedTime(&tk2, h->ev1, h->ev_x[2]);
+        cudaEventElapsedTime(&t02, h->ev_x[0], h->ev_x[2]);
+        cudaGetLastError();
+        h->exchange_ms[0] = t01; h->exchange_ms[1] = t0k; h->exchange_ms[2] = tk2; h->exchange_ms[3] = t02;
+    }
     if (rc < 0) return rc;
     if (!exported) {  // an attempt was rejected (or NaN): export again from the final state
         const int rc2 = msed_get_upward_fluxes(h, upward_fluxes);
@@ -1622,6 +1642,13 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
         }
     }
     return rc;
+}
+
+int msed_get_exchange_timing(const msed_handle *h, double *ms4)
+{
+    if (!h || !ms4) return MSED_ERR_ARG;
+    for (int q = 0; q < 4; ++q) ms4[q] = h->exchange_ms[q];
+    return MSED_OK;
 }
 
 int msed_set_import_generations(msed_handle *h, const uint64_t *gen)

@@ -269,6 +269,13 @@ class SedimentDriver:
                          allow=(_abi.NAN_DETECTED,))
         return rc, out
 
+    def exchange_timing(self):
+        """Phase marks of the last pipelined ``run_exchange`` in ms: (last H2D landed, last kernel done, exposed D2H
+        tail after it, whole device-side span)."""
+        ms = (C.c_double * 4)()
+        self._check(self._lib.msed_get_exchange_timing(self._h, ms))
+        return tuple(ms)
+
     def set_import_generations(self, gen=None):
         """Generation counters of the import fields of ``run_exchange`` (temperature, then csurf(n), wz(n) for each
         variable: 1 + 2*nvar entries); a field whose counter and host array are those of its last upload stays on
