@@ -206,6 +206,9 @@ void fill_params(const msed_handle *h, KParams &p)
     p.mask = h->mask;
     p.colmap = nullptr;
     p.feed_bulk = 0;
+    p.min_zero = 1;
+    for (int n = 0; n < NV; ++n)
+        if (h->cfg.minimum[n] != 0.0) p.min_zero = 0;
     p.ctl = h->ctl;
     p.ld = h->ld;
     p.ncol = h->ncol;

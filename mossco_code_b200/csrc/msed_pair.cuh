@@ -32,6 +32,8 @@
 #define MSED_PAIR_UNROLL 2
 #endif
 #define MSED_PAIR_UNROLL_PRAGMA MSED_UNROLL_PRAGMA(MSED_PAIR_UNROLL)
+// (the lambdas of pair_kernel carry always_inline: with six instantiations of the column walk the inliner's budget
+//  runs out and the stages would become real calls with their arrays in local memory)
 constexpr int PAIR_WIN = 4;  // c1 window slots (3 live layers: j, j+1 and the one being written)
 constexpr uint32_t PAIR_STAGE_BYTES = NV * ROW_BYTES;                    // input ring: 8 rows per layer
 constexpr uint32_t PAIR_RING_BYTES = RING_STAGES * PAIR_STAGE_BYTES;
@@ -79,6 +81,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 }
 
 // How the input state reaches shared memory:
+// what a stage does where the component checks for NaN and clips to the minimum
+enum PairClip : int { CLIP_NONE = 0, CLIP_NOW, CLIP_DETECT };
+
 enum PairFeed : int {
     FEED_CPASYNC = 0,  // every thread copies its own column, 8 bytes per row (LDGSTS through the L1)
     FEED_COLMAP,       // the same over the wet-column list of a tile with land (columns of a warp are not contiguous)
@@ -167,7 +172,7 @@ pair_kernel(const __grid_constant__ KParams p)
         }
         __syncwarp();
     }
-    {
+    auto fetch_column_rows = [&]() __attribute__((always_inline)) {
         cp_async8(cbase, p.bdys + col);                                   // temp3d(:,:,k) = bdys(:,:,1), driver :602
         if (p.por_mode == 2) cp_async8(cbase + ROW_BYTES, p.por + col);   // porosity(:,:,1), driver :411
 #pragma unroll
@@ -176,10 +181,10 @@ pair_kernel(const __grid_constant__ KParams p)
             if (bc == 1 || bc == 4) cp_async8(cbase + (2 + n) * ROW_BYTES, p.fluxes + (size_t)n * ld + col);   // :783,:792
             else if (bc == 2) cp_async8(cbase + (2 + n) * ROW_BYTES, p.bdys + (size_t)(n + 1) * ld + col);    // :786
         }
-    }
+    };
     const double *g_in = in;
     int k_fetch = 0;
-    auto fetch_next = [&]() {
+    auto fetch_next = [&]() __attribute__((always_inline)) {
         if (BULK) {
             if (k_fetch < K) {
                 const uint32_t slot = (uint32_t)(k_fetch & (RING_STAGES - 1));
@@ -205,15 +210,17 @@ pair_kernel(const __grid_constant__ KParams p)
         ++k_fetch;
         cp_async_commit();
     };
-#pragma unroll
-    for (int s = 0; s < RING_STAGES - 1; ++s) fetch_next();
-    if (BULK) cp_async_commit();  // the column's scalars
-
     double por_surf = 1.0, cpart, cdiss, fT, temp;
-    auto por_at = [&](int kk) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
+    double FA[NV], FB[NV];
+    int viol1 = 0, viol2 = 0;  // sign bit = some relative change fell below relative_change_min (violates_acc)
+    bool nan1 = false, nan2 = false;
+    int neg = 0;               // sign bit = some new value was negative where the component clips (lazy clip, below)
+    double *g_out = out;
+    double fT_diag = 1.0;
+    auto por_at = [&](int kk) __attribute__((always_inline)) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
 
     // upper boundary of one step: F[n] = Flux(1) (diff3d :782-803), c0(n) = state of layer 1
-    auto top_boundary = [&](auto c0, double por0, double (&F)[NV], bool write_fluxes) {
+    auto top_boundary = [&](auto c0, double por0, double (&F)[NV], bool write_fluxes) __attribute__((always_inline)) {
         double Dp, Dd;
         top_coeffs(cpart, cdiss, por0, p.bf[0], Dp, Dd);
         const double rdz0 = 1.0 / p.dz[0];
@@ -238,28 +245,37 @@ pair_kernel(const __grid_constant__ KParams p)
     };
 
     // layer kk has landed (kk < K)
-    auto wait_layer = [&](int kk) {
+    auto wait_layer = [&](int kk) __attribute__((always_inline)) {
         if (BULK) mbar_wait(bar0 + (uint32_t)(kk & (RING_STAGES - 1)) * 8u, (uint32_t)(kk / RING_STAGES) & 1u);
         else cp_async_wait<RING_STAGES - 2>();
     };
-    if (BULK) cp_async_wait<0>();
-    wait_layer(0);  // ... and the column's scalars
-    if (p.por_mode == 2) por_surf = lds64(cbase + ROW_BYTES);
-    temp = lds64(cbase);
-    column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
-    double FA[NV], FB[NV];
-    // Step 1 reads the particulate input fluxes BEFORE step 2 may overwrite the dissolved entries of
-    // the same array; with bcup_dissolved = 1 the dissolved input fluxes are read here as well and
-    // rewritten unchanged by step 2 (:692).
-    top_boundary([&](int n) { return lds64(sbase + n * SROW); }, por_at(0), FA, false);
-
-    int viol1 = 0, viol2 = 0;  // sign bit = some relative change fell below relative_change_min (violates_acc)
-    bool nan1 = false, nan2 = false;
-    double *g_out = out;
-    // The last pair of a call leaves the denitrification diagnostic of its second step behind: it
-    // describes the state of the last get_rhs call, which here never reaches HBM.
-    double fT_diag = fT;
-    if (MODEL != MSED_MODEL_OMEXDIA_P && DENIT) fT_diag = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
+    // (re)start the walk down the column: the input stream from layer 0, the column's scalars and constants,
+    // the upper boundary of step 1
+    auto start_column = [&]() __attribute__((always_inline)) {
+        if (!BULK) cp_async_wait<0>();   // (a restart: nothing of the first walk is still in flight)
+        fetch_column_rows();
+        g_in = in;
+        k_fetch = 0;
+        g_out = out;
+#pragma unroll
+        for (int s = 0; s < RING_STAGES - 1; ++s) fetch_next();
+        if (BULK) {
+            cp_async_commit();  // the column's scalars
+            cp_async_wait<0>();
+        }
+        wait_layer(0);  // ... and the column's scalars
+        if (p.por_mode == 2) por_surf = lds64(cbase + ROW_BYTES);
+        temp = lds64(cbase);
+        column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
+        // Step 1 reads the particulate input fluxes BEFORE step 2 may overwrite the dissolved entries of
+        // the same array; with bcup_dissolved = 1 the dissolved input fluxes are read here as well and
+        // rewritten unchanged by step 2 (:692).
+        top_boundary([&](int n) { return lds64(sbase + n * SROW); }, por_at(0), FA, false);
+        // The last pair of a call leaves the denitrification diagnostic of its second step behind: it
+        // describes the state of the last get_rhs call, which here never reaches HBM.
+        fT_diag = fT;
+        if (MODEL != MSED_MODEL_OMEXDIA_P && DENIT) fT_diag = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
+    };
 
     // one step of one layer: finishes layer kk given its state cc, the state cn of the layer below and
     // the flux F through its upper interface; the new state goes to `sink`.  HAS_NEXT and CLIP are
@@ -267,7 +283,7 @@ pair_kernel(const __grid_constant__ KParams p)
     // state-independent coefficients of layer kk and of its lower interface: both steps of the pair
     // need the same ones (step 2 one iteration later), so they are computed once
     struct LayerCoef { double porc, porn, mDp, mDd, rpd; };
-    auto make_coef = [&](auto has_next_tag, int kk) -> LayerCoef {
+    auto make_coef = [&](auto has_next_tag, int kk) __attribute__((always_inline)) -> LayerCoef {
         LayerCoef lc;
         lc.porc = por_at(kk);
         lc.porn = lc.mDp = lc.mDd = 0.0;
@@ -288,9 +304,9 @@ pair_kernel(const __grid_constant__ KParams p)
     const int depth = p.depth;
 
     auto step_layer = [&](auto has_next_tag, auto clip_tag, auto up_tag, const LayerCoef &lc, const double (&cc)[NV],
-                          auto cn, double (&F)[NV], int &viol, bool &nanf, auto sink, auto denit) {
+                          auto cn, double (&F)[NV], int &viol, bool &nanf, auto sink, auto denit) __attribute__((always_inline)) {
         constexpr bool HAS_NEXT = decltype(has_next_tag)::value;
-        constexpr bool CLIP = decltype(clip_tag)::value;
+        constexpr int CLIPM = decltype(clip_tag)::value;   // CLIP_NONE / CLIP_NOW / CLIP_DETECT
         constexpr bool UP = decltype(up_tag)::value;
         double Fn[NV];
         if (HAS_NEXT) {
@@ -327,10 +343,10 @@ pair_kernel(const __grid_constant__ KParams p)
                     if (l < depth && violates(p.fac, c0, euler_update(dt_up[l], rhs, c0))) viol_up |= 1 << l;
             }
             raw[n] = newc;
-            if (CLIP) {
+            if (CLIPM != CLIP_NONE) {
                 if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
-                const double mn = p.om.minimum[n];
-                newc = clip_min(newc, mn);
+                if (CLIPM == CLIP_NOW) newc = clip_min(newc, p.om.minimum[n]);
+                else neg |= __double2hiint(newc);   // (merged by the compiler into one LOP3 per two values)
             }
             sink(n, newc);
         }
@@ -338,7 +354,7 @@ pair_kernel(const __grid_constant__ KParams p)
 
     LayerCoef coef_prev;  // coefficients of the layer step 2 is about to process (made by step 1)
     // step 1, layer k: state from the ring, result into the c1 window; returns the layer coefficients
-    auto stage_a = [&](auto has_next_tag, auto clip_tag, auto up_tag, int k) -> LayerCoef {
+    auto stage_a = [&](auto has_next_tag, auto clip_tag, auto up_tag, int k) __attribute__((always_inline)) -> LayerCoef {
         fetch_next();
         if (!BULK || decltype(has_next_tag)::value) wait_layer(k + 1);
         const uint32_t sc = sbase + (uint32_t)(k & (RING_STAGES - 1)) * SSTAGE;
@@ -353,7 +369,7 @@ pair_kernel(const __grid_constant__ KParams p)
         return lc;
     };
     // step 2, layer j: state from the c1 window, result to HBM
-    auto stage_b = [&](auto has_next_tag, auto clip_tag, int j, const LayerCoef &lc) {
+    auto stage_b = [&](auto has_next_tag, auto clip_tag, int j, const LayerCoef &lc) __attribute__((always_inline)) {
         const uint32_t wj = wbase + (uint32_t)(j & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
         const uint32_t wn = wbase + (uint32_t)((j + 1) & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
         double cc[NV];
@@ -374,9 +390,10 @@ pair_kernel(const __grid_constant__ KParams p)
 
     // clip_a / clip_b: check_NaN + minimum clip after stage A / stage B (the stage ends an ode_solver call and
     // the component wrapper is on); up_tag: stage A also tests the planned rejections
-    auto sweep = [&](auto clip_a, auto clip_b, auto up_tag) {
+    auto sweep = [&](auto clip_a, auto clip_b, auto up_tag) __attribute__((always_inline)) {
         using Y = std::true_type;
         using N = std::false_type;
+        start_column();
         if (K == 1) {  // degenerate column: both stages see a closed bottom right away
             coef_prev = stage_a(N{}, clip_a, up_tag, 0);
             top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
@@ -401,11 +418,39 @@ pair_kernel(const __grid_constant__ KParams p)
         const int kind = ADAPTIVE ? p.pair_kind : (int)PAIR_FULL;
         // one call site per instantiation (the lambda body is inlined wherever it is called)
         const int sel = (kind == PAIR_FULL && do_clip) ? 0 : (kind == PAIR_FIRST) ? 1 : (kind == PAIR_LAST && do_clip) ? 2 : 3;
+        using C0 = std::integral_constant<int, CLIP_NONE>;
+        using C1 = std::integral_constant<int, CLIP_NOW>;
+        using CD = std::integral_constant<int, CLIP_DETECT>;
+        // Lazy clip.  The component's clip to the minimum (fabm_sediment_component.F90:1728-1730) is a safety net
+        // that almost never fires, but as four integer instructions per value it is an eighth of the loop.  With
+        // zero minima (the FABM default) "some value would be clipped" is "some value has its sign bit set": the
+        // column is walked without the clip, the sign bits are collected, and a thread that did meet a negative
+        // value (or -0.0) walks its column again with the clip in place -- the input buffer is untouched, every
+        // output is simply written again.  Same bits either way.
+        // (the reaction-free test model keeps the plain clip: two walks fewer to compile)
+        constexpr bool LAZY = MODEL == MSED_MODEL_OMEXDIA_P && !BULK;
+        const bool lazy = LAZY && p.min_zero != 0;
         switch (sel) {
-        case 0: sweep(Y{}, Y{}, N{}); break;
-        case 1: sweep(N{}, N{}, Y{}); break;
-        case 2: sweep(N{}, Y{}, N{}); break;
-        default: sweep(N{}, N{}, N{}); break;
+        case 0:
+            if constexpr (LAZY) {
+                if (lazy) {
+                    sweep(CD{}, CD{}, N{});
+                    if (neg >= 0) break;
+                }
+            }
+            sweep(C1{}, C1{}, N{});   // no lazy clip, or the thread met a value the clip changes
+            break;
+        case 1: sweep(C0{}, C0{}, Y{}); break;
+        case 2:
+            if constexpr (LAZY) {
+                if (lazy) {
+                    sweep(C0{}, CD{}, N{});
+                    if (neg >= 0) break;
+                }
+            }
+            sweep(C0{}, C1{}, N{});
+            break;
+        default: sweep(C0{}, C0{}, N{}); break;
         }
     }
     if (!BULK) cp_async_wait<0>();

@@ -108,6 +108,7 @@ struct KParams {
     double *denit_out;       // [K][ld]: FABM denit diagnostic of the second step of a call's last pair, or null
     const int *colmap;       // pair_kernel on a masked tile: indices of the wet columns, ascending; col0/col_end
                              // then count wet columns (null: identity)
+    int min_zero;            // every state variable's minimum is +0: pair_kernel may clip lazily (msed_pair.cuh)
     int feed_bulk;           // pair_kernel: the tensor maps below are valid and the tile has no masked column, so the
                              // state may be fed to shared memory by TMA box copies (msed_pair.cuh, FEED_BULK)
     // TMA descriptors of the state buffers as 3-D tensors [nvar][K][ld] of fp64, box = 32 columns x 1 layer x

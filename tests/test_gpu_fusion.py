@@ -171,6 +171,22 @@ def test_fusion_accepts_violations_below_dt_min(gpu, mode):
     assert on["launches"] < off["launches"]
 
 
+@pytest.mark.parametrize("method", [0, 2])
+def test_pair_lazy_clip_redoes_columns_that_need_the_clip(gpu, method):
+    """pair_kernel walks a column without the clip and again with it if some new value had its sign bit set (zero
+    minima): with reaction rates that overshoot, some columns do need the clip -- cells end exactly at the
+    minimum -- and the result must still be the bits of the single steps, which clip every value."""
+    case = make_case("lazy", 40, 24, 20, 0.003, seed=77, land_fraction=0.15)
+    kw = dict(rnit=2.0e3, rODUox=2.0e3, dt_min=400.0)      # dt <= dt_min: every attempt is accepted as it is
+    on = _run(case, "pairs", method, 6, **kw)
+    off = _run(case, False, method, 6, **kw)
+    _same(on, off)
+    wet = case.mask == 0
+    clipped = (on["conc"][wet] == 0.0).sum()
+    assert 0 < clipped < on["conc"][wet].size // 2          # the clip fired somewhere, not everywhere
+    assert on["launches"] < off["launches"]
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_fusion_nan_stops_at_the_same_step(gpu, mode):
     case = make_case("fusen", 6, 5, 12, 0.004, seed=4)
