@@ -111,6 +111,8 @@ struct msed_handle {
     int chunk_major = 1;                          // msed_run_exchange: whole coupling interval chunk by chunk
     int pred_depth = 0;                           // how the next call's steps are predicted to go: every step at
                                                   // dt/4^pred_depth (what the last completed step did); -1: no prediction
+    int regime_depth = 0;                         // depth of the last fused group that was committed: the prediction
+                                                  // after a step whose own attempt sequence was irregular
     long long pairs_committed = 0;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -361,7 +363,7 @@ cudaError_t enable_pair_smem()
 }
 
 // nflags: 4 (violation / NaN of up to two stages) or, for a group that plans rejections, all of Ctl::flags
-int reduce_flags(msed_handle *h, int nflags = 4)
+int reduce_flags(msed_handle *h, int nflags = 8)
 {
     if (h->hook) {
         void *flags = (void *)((char *)h->ctl + offsetof(Ctl, flags));
@@ -524,6 +526,8 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     // one wrong prediction sent the rest of the call down the single-attempt path.)
     const bool adaptive = method == MSED_ADAPTIVE_EULER;
     int pred = adaptive ? h->pred_depth : 0;
+    int regime = adaptive ? h->regime_depth : 0;
+    long long fused_before = 0;     // Ctl::fused_launches when the current round began
     long long base = 0;             // ode_solver calls completed before the current round
     long long nfl_total = 0;        // fused launches enqueued by all rounds
     int nrounds = 0;
@@ -538,13 +542,23 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     const long long max_batch = 256;
     int guard = 0;
     bool stopped = false;
+    // what the previous round asks of the next one: plan only that many steps (the good front of a chain that was
+    // not committed), or take one step through single attempts (the step behind that front)
+    long long next_limit = -1;
+    bool next_single = false;
     std::vector<FusedLaunch> fl;
     for (;; ++nrounds) {
-    const long long rem = nsteps - base;
+    const long long limit = next_limit;
+    const bool force_single = next_single;
+    next_limit = -1;
+    next_single = false;
+    const long long rem_all = nsteps - base;
+    const long long rem = limit >= 0 ? std::min(limit, rem_all) : rem_all;   // steps this round plans
     int depth = pred;
     double dt_acc = dt;
     long long nq = 1;
-    bool planned = fusable && single_attempt && !diag && rem >= 1 && plan_depth(dt, h->cfg.dt_min, depth, dt_acc, nq);
+    bool planned = fusable && single_attempt && !diag && rem >= 1 && !force_single &&
+                   plan_depth(dt, h->cfg.dt_min, depth, dt_acc, nq);
     const bool use_chain = planned && chain_fit;
     const int own_rejectable = (adaptive && dt_acc > h->cfg.dt_min) ? 1 : 0;
     fl.clear();
@@ -624,7 +638,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     nfl_total += nfl;
     // the call ends with a fused launch, which then leaves the "state of the last get_rhs call" diagnostic
     // behind (KParams::denit_out)
-    last_is_fused = nfl > 0 && fused_planned == rem;
+    last_is_fused = nfl > 0 && fused_planned == rem_all;
     if (last_is_fused && (rc = ensure_denit(h))) return rc;
     p.dt_acc = dt_acc;
     p.depth = depth;
@@ -665,7 +679,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         }
         first_pending = false;
         if (collective)
-            if ((rc = reduce_flags(h, depth > 0 ? MSED_NFLAGS : 4))) return rc;
+            if ((rc = reduce_flags(h, depth > 0 ? MSED_NFLAGS : 8))) return rc;
         // commits all pairs at once (or none)
         PlanCommit pc = base_commit(0);
         pc.steps = nsteps;
@@ -703,7 +717,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
             launches += 1;
         }
         if (collective)
-            if ((rc = reduce_flags(h, fl[q].pc.up_slots > 0 ? MSED_NFLAGS : 4))) return rc;
+            if ((rc = reduce_flags(h, fl[q].pc.up_slots > 0 ? MSED_NFLAGS : 8))) return rc;
         plan_controller_kernel<<<1, 1, 0, h->stream>>>(h->ctl, fl[q].pc);
         launches += 1;
     }
@@ -713,8 +727,8 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     // steps, then another look at the prediction, when it is the step history that stands in the way
     const bool replannable = fusable && single_attempt && !diag;
     long long target = nsteps;
-    if (!planned && replannable) target = std::min(nsteps, base + 4);
-    const long long singles_planned = (planned ? rem - fused_planned : target - base);
+    if (!planned && replannable) target = std::min(nsteps, base + (force_single ? 1 : 4));
+    const long long singles_planned = planned ? (limit >= 0 ? 0 : rem - fused_planned) : target - base;
     if (target != nsteps) {   // (the device copy still holds nsteps otherwise)
         h->ctl_host->steps_target = target;
         CUDA_TRY(h, cudaMemcpyAsync(&h->ctl->steps_target, &h->ctl_host->steps_target, sizeof(long long),
@@ -790,7 +804,25 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
             // attempts, the rest of the call is planned afresh afterwards (identical on every rank: the flags
             // the controller decides on are reduced)
             failure_seen = true;
-            target = std::min(nsteps, (long long)h->ctl_host->steps_done + 1);
+            // how far single attempts go before the rest is planned afresh: the steps the launch that was not
+            // committed stood for (a pair: its two steps; a chain: all of its steps -- it cannot be committed in
+            // part); a chunk-major interval is all-or-nothing, so it is simply planned again as ordinary pairs,
+            // which commit one by one up to the step in question
+            long long extent = 1;
+            const int fstep = h->ctl_host->fail_step;
+            if (seq_round) {
+                extent = 0;
+            } else if (use_chain && fstep >= 1) {
+                // a chain is committed whole or not at all, but it says where it went wrong: the steps in front
+                // are run again as a shorter chain (next round), the step in question singly (the round after)
+                extent = 0;
+                next_limit = fstep;
+            } else if (use_chain && fstep == 0) {
+                extent = 1;   // its first step: that one singly, then a new plan
+            } else
+                for (const FusedLaunch &f : fl)
+                    if (f.pc.gate_steps == h->ctl_host->steps_done) { extent = std::max<long long>(1, f.pc.steps); break; }
+            target = std::min(nsteps, (long long)h->ctl_host->steps_done + extent);
             if (target != h->ctl_host->steps_target) {
                 h->ctl_host->steps_target = target;
                 CUDA_TRY(h, cudaMemcpyAsync(&h->ctl->steps_target, &h->ctl_host->steps_target, sizeof(long long),
@@ -807,12 +839,17 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         if (++guard > 1000000) return fail(h, MSED_ERR_STATE, "step loop did not terminate");
     }
     last_round_clean = !failure_seen && !stopped;
+    if (h->ctl_host->fused_launches > fused_before) regime = depth;   // some group of this round was committed
+    fused_before = h->ctl_host->fused_launches;
+    if (limit >= 0 && !failure_seen) next_single = true;   // the front went through: now the step behind it
     if (nrounds == 0 && seq_mode) seq_committed = last_round_clean && h->ctl_host->steps_done == nsteps;
     if (stopped || nsteps == 0) { ++nrounds; break; }
     base = h->ctl_host->steps_done;
     if (base >= nsteps) { ++nrounds; break; }
     // next round: planned the way the last completed step went; fused launches are allowed again
-    if (adaptive) pred = h->ctl_host->last_irregular ? -1 : h->ctl_host->last_depth;
+    // a step that rejected an attempt after its first accepted sub-step says nothing about its successors: back
+    // to the regime the last committed group ran in
+    if (adaptive) pred = h->ctl_host->last_irregular ? regime : h->ctl_host->last_depth;
     h->ctl_host->pairs_disabled = 0;
     h->ctl_host->steps_target = nsteps;
     CUDA_TRY(h, cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, h->stream));
@@ -839,7 +876,10 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                             nrounds == 1 && (last_is_fused0 || r.subcycles == fused_planned0 * depth0);
     }
     // the next call is planned the way this call's last step went
-    if (r.steps_done > 0 && method == MSED_ADAPTIVE_EULER) h->pred_depth = r.last_irregular ? -1 : r.last_depth;
+    if (r.steps_done > 0 && method == MSED_ADAPTIVE_EULER) {
+        h->pred_depth = r.last_irregular ? regime : r.last_depth;
+        h->regime_depth = regime;
+    }
     h->pairs_committed += r.fused_launches;
     // (the call's last step sits in a committed fused launch of the last round)
     h->denit_valid = last_is_fused && last_round_clean && !r.stop && r.steps_done == nsteps;
@@ -1490,6 +1530,7 @@ int msed_set_step_fusion(msed_handle *h, int enable)
     if (enable < 0 || enable > 3) return fail(h, MSED_ERR_ARG, "step fusion mode must be 0..3");
     h->step_fusion = enable;
     h->pred_depth = 0;
+    h->regime_depth = 0;
     return MSED_OK;
 }
 

@@ -220,7 +220,10 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
         }
         // a rejectable violation anywhere in the column: the chain will not be committed, stop here
         if (rejectable && __any_sync(FULL, viol < 0 && active)) {
-            if (lane == 0) atomicOr(&p.ctl->flags[0], 1);
+            if (lane == 0) {
+                atomicOr(&p.ctl->flags[0], 1);
+                atomicMax(&p.ctl->flags[FLAG_FAIL], 64 - s);   // where: the earliest such step wins (run_steps re-plans)
+            }
             return;
         }
     }

@@ -79,12 +79,24 @@ __global__ void plan_controller_kernel(Ctl *c, PlanCommit pc)
     c->step_completed = 0;
     if (c->stop || c->pairs_disabled || c->steps_done != pc.gate_steps) return;
     const int own = c->flags[0] | c->flags[2], nanf = c->flags[1] | c->flags[3];
-    int up_all = 1;
-    for (int s = 0; s < pc.up_slots; ++s) up_all &= (c->flags[FLAG_UP0 + s] != 0);
+    int up_all = 1, first_missing = -1;
+    for (int s = 0; s < pc.up_slots; ++s)
+        if (c->flags[FLAG_UP0 + s] == 0) {
+            up_all = 0;
+            if (first_missing < 0) first_missing = s;
+        }
+    const int stopped_at = c->flags[FLAG_FAIL] > 0 ? 64 - c->flags[FLAG_FAIL] : -1;   // chain_kernel
     for (int s = 0; s < MSED_NFLAGS; ++s) c->flags[s] = 0;
     if ((pc.own_rejectable && own) || (c->do_clip && nanf) || !up_all) {
         c->pairs_disabled = 1;
         c->pair_failures += 1;
+        // a step of the group at or before which the plan went wrong (chains: run_steps re-runs the steps in
+        // front of it as a shorter chain): the first planned rejection that was not seen, the step a warp
+        // stopped at -- whichever comes first
+        int f = -1;
+        if (first_missing >= 0 && pc.depth > 0) f = first_missing / pc.depth;
+        if (stopped_at >= 0 && (f < 0 || stopped_at < f)) f = stopped_at;
+        c->fail_step = f;
         return;
     }
     if (pc.flip) c->cur ^= 1;

@@ -29,6 +29,7 @@ constexpr int NPART = 3;  // ldetC, sdetC, detP are particulate (main.F90:92-101
 constexpr int COL_BLOCK = MSED_COL_BLOCK;            // threads (= columns) per CTA of the column kernel
 constexpr int COL_MIN_BLOCKS = MSED_COL_MIN_BLOCKS;  // 4 CTAs/SM -> <=128 registers/thread, 16 warps/SM
 #define MSED_NFLAGS 40
+constexpr int FLAG_FAIL = 4;                         // chain_kernel: 64 - (step of the launch a rejectable violation stopped a warp at)
 constexpr int FLAG_UP0 = 8;                          // first "planned rejection seen" slot of Ctl::flags
 constexpr int MAX_UP_SLOTS = MSED_NFLAGS - FLAG_UP0; // planned rejections one fused group can hold
 constexpr int MAX_PLAN_DEPTH = 2;                    // fused launches cover steps that run at dt, dt/4 or dt/16
@@ -73,6 +74,8 @@ struct Ctl {
     int step_accepts;   // accepted sub-steps of the current call
     int last_depth;     // step_rej_first of the last completed call: it ran at dt/4^last_depth
     int last_irregular; // ... and whether it rejected anything after its first accepted sub-step
+    int fail_step;      // set when a chain launch is not committed: a step of the launch (0-based) at or before which it
+                        // went wrong -- the steps in front of it can be re-run as a shorter chain; -1 unknown
 };
 
 struct OmexDev {  // hzg_omexdia_p parameters, rates already per second
