@@ -19,7 +19,9 @@ module msed_b200
   use, intrinsic :: iso_c_binding
   implicit none
   private
-  public :: msed_soil_pelagic_connector
+  public :: msed_soil_pelagic_connector, msed_pelagic_soil_connector, msed_pelagic_soil_params_defaults, &
+            msed_spinup_batch, msed_set_import_generations, msed_export_state_begin, msed_export_state_wait, &
+            msed_set_compat, msed_diagnostics, msed_state_checksum
 
   integer, parameter, public :: rk = c_double
   integer, parameter, public :: MSED_NVAR = 8
@@ -66,6 +68,23 @@ module msed_b200
   type, bind(c), public :: msed_soil_pelagic_fluxes
     type(c_ptr) :: nitrate, ammonium, DIN, DIP, oxygen, odu, detN, detC, detP
   end type
+
+  !> mirrors `struct msed_spinup_member` / `msed_pelagic_soil_state` / `msed_pelagic_soil_params` (include/msed.h)
+  type, bind(c), public :: msed_spinup_member
+    real(c_double) :: rLabile, rSemilabile, NCrLdet, NCrSdet, PAds, PAdsODU, NH3Ads, CprodMax
+    real(c_double) :: rnit, ksO2nitri, rODUox, ksO2oduox, ksO2oxic, ksNO3denit, kinO2denit
+    real(c_double) :: kinNO3anox, kinO2anox
+    real(c_double) :: initial_value(MSED_NVAR)
+  end type
+  type, bind(c), public :: msed_pelagic_soil_state
+    type(c_ptr) :: temperature, par, oxygen, odu, detN, detN_z_velocity, detC, detP, detP_z_velocity
+    type(c_ptr) :: nitrate, ammonium, DIN, DIP, water_depth, tke
+  end type
+  type, bind(c), public :: msed_pelagic_soil_params
+    real(c_double) :: sinking_factor, sinking_factor_min, NC_ldet, NC_sdet
+    real(c_double) :: half_sedimentation_depth, half_sedimentation_tke, critical_detritus, convertN, convertP
+  end type
+  integer(c_int), parameter, public :: MSED_COMPAT_P2B_OXYGEN_LAST_CELL = 1, MSED_COMPAT_P2S_HEAD = 2
 
   interface
     integer(c_int) function msed_config_defaults(cfg) bind(c, name='msed_config_defaults')
@@ -206,6 +225,49 @@ module msed_b200
         bind(c, name='msed_soil_pelagic_connector')
       import; type(c_ptr), value :: h
       type(msed_soil_pelagic_params), intent(in) :: par; type(msed_soil_pelagic_fluxes), intent(in) :: fluxes_out
+    end function
+    !> the same pre-simulation for nmembers sed1d clones in one launch (members: c_null_ptr or an array of
+    !> msed_spinup_member; bdys1d(nmembers,nvar+1), fluxes1d(nmembers,nvar), conc1d(nmembers,1,knum,nvar))
+    integer(c_int) function msed_spinup_batch(cfg, nmembers, members, bdys1d, fluxes1d, nsteps, method, conc1d, info) &
+        bind(c, name='msed_spinup_batch')
+      import; type(msed_config), intent(in) :: cfg; integer(c_int32_t), value :: nmembers; type(c_ptr), value :: members
+      real(c_double), intent(in) :: bdys1d(*), fluxes1d(*)
+      integer(c_int64_t), value :: nsteps; integer(c_int), value :: method
+      real(c_double), intent(out) :: conc1d(*); type(c_ptr), value :: info
+    end function
+    !> import fields the coupler has not changed since their last upload stay on the device: gen(1) temperature,
+    !> gen(2n), gen(2n+1) the surface concentration and z-velocity of variable n; c_null_ptr: upload everything
+    integer(c_int) function msed_set_import_generations(h, gen) bind(c, name='msed_set_import_generations')
+      import; type(c_ptr), value :: h, gen
+    end function
+    !> <name>_in_soil write-back (fabm_sediment_component.F90:1773-1822) at an output cadence: begin snapshots the
+    !> state on the device and copies it to conc_host under the following Runs, wait completes it
+    integer(c_int) function msed_export_state_begin(h, conc_host) bind(c, name='msed_export_state_begin')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: conc_host(*)
+    end function
+    integer(c_int) function msed_export_state_wait(h) bind(c, name='msed_export_state_wait')
+      import; type(c_ptr), value :: h
+    end function
+    !> pelagic_soil_connector Run, src/mediators/pelagic_soil_connector.F90:176-2122
+    integer(c_int) function msed_pelagic_soil_params_defaults(par) bind(c, name='msed_pelagic_soil_params_defaults')
+      import; type(msed_pelagic_soil_params), intent(out) :: par
+    end function
+    integer(c_int) function msed_pelagic_soil_connector(h, state, par) bind(c, name='msed_pelagic_soil_connector')
+      import; type(c_ptr), value :: h
+      type(msed_pelagic_soil_state), intent(in) :: state; type(msed_pelagic_soil_params), intent(in) :: par
+    end function
+    integer(c_int) function msed_set_compat(h, flags) bind(c, name='msed_set_compat')
+      import; type(c_ptr), value :: h; integer(c_int), value :: flags
+    end function
+    !> bed-flux sums and inventories per variable over the wet columns (all tiles with reduce_over_ranks /= 0)
+    integer(c_int) function msed_diagnostics(h, bed_flux_sum, inventory, reduce_over_ranks) &
+        bind(c, name='msed_diagnostics')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: bed_flux_sum(*), inventory(*)
+      integer(c_int), value :: reduce_over_ranks
+    end function
+    integer(c_int) function msed_state_checksum(h, global_ncol, col_offset, out2) bind(c, name='msed_state_checksum')
+      import; type(c_ptr), value :: h; integer(c_int64_t), value :: global_ncol, col_offset
+      integer(c_int64_t), intent(out) :: out2(2)
     end function
     integer(c_int) function msed_set_stream(h, cuda_stream) bind(c, name='msed_set_stream')
       import; type(c_ptr), value :: h, cuda_stream
