@@ -45,7 +45,10 @@ constexpr size_t PAIR_SMEM_BYTES = (size_t)PAIR_RING_BYTES + PAIR_WIN_BYTES + MS
 #else
 constexpr size_t PAIR_SMEM_BYTES = (size_t)PAIR_RING_BYTES + PAIR_WIN_BYTES;
 #endif
-constexpr int PAIR_MIN_BLOCKS = 3;
+#ifndef MSED_PAIR_MIN_BLOCKS
+#define MSED_PAIR_MIN_BLOCKS (384 / MSED_COL_BLOCK)   // 12 warps per SM: 168 registers per thread
+#endif
+constexpr int PAIR_MIN_BLOCKS = MSED_PAIR_MIN_BLOCKS;
 
 __device__ __forceinline__ void sts64(uint32_t addr, double v)
 {
