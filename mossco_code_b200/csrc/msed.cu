@@ -392,6 +392,8 @@ struct ExchangePlan {
     double *host_out = nullptr;
     bool export_done = false;  // out: host_out holds the final upward fluxes
     bool stage_private = false;  // the staging rows are not in h->scratch, which may then hold a state
+    bool zero_copy = false;      // small tile, pinned host fields: the boundary kernel reads the import fields and the
+    double *host_out_dev = nullptr;  // export kernel writes the fluxes straight through PCIe (no copies, no staging)
 };
 
 // One fused launch of a call's plan: a pair (two accepted sub-steps), or a chain of m ode_solver calls
@@ -509,7 +511,13 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         const int c0 = plan->c0[c], c1 = plan->c1[c];
         CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], h->stream));
         CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_pool[16 + c], 0));
-        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->d2h_stream>>>(plan->neg + c0, h->fluxes + c0, h->ld,
+        if (plan->zero_copy) {   // -fluxes straight into the caller's pinned array (rows ncol apart)
+            negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->d2h_stream>>>(plan->host_out_dev + c0, h->fluxes + c0,
+                                                                             (size_t)h->ncol, h->ld, c1 - c0, NV);
+            launches += 1;
+            return MSED_OK;
+        }
+        negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->d2h_stream>>>(plan->neg + c0, h->fluxes + c0, h->ld, h->ld,
                                                                          c1 - c0, NV);
         launches += 1;
         CUDA_TRY(h, cudaMemcpy2DAsync(plan->host_out + c0, (size_t)h->ncol * sizeof(double), plan->neg + c0,
@@ -1417,7 +1425,7 @@ int msed_get_upward_fluxes(msed_handle *h, double *upward)
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc = ensure_scratch(h);
     if (rc) return rc;
-    negate_rows_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->scratch, h->fluxes, h->ld, h->ncol, NV);
+    negate_rows_kernel<<<nblocks(h->ncol), 256, 0, h->stream>>>(h->scratch, h->fluxes, h->ld, h->ld, h->ncol, NV);
     CUDA_TRY(h, cudaGetLastError());
     return download_rows(h, upward, h->scratch, NV);
 }
@@ -1610,16 +1618,42 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
         host[nf] = csurf[n]; dev[nf] = &plan.bc.csurf[n]; key[nf] = 1 + 2 * n; ++nf;
     }
     for (int f = 0; f < nf; ++f) *dev[f] = stage + (size_t)f * h->ld;
+    // A tile of one chunk is a Run of a few hundred microseconds, of which a dozen small copies and their staging
+    // are a third: when every field the caller handed over is pinned host memory, the boundary kernel reads the
+    // import fields, and the export kernel writes the fluxes, directly through PCIe instead.
+    {
+        static const bool off = std::getenv("MSED_EXCHANGE_ZERO_COPY") && std::atoi(std::getenv("MSED_EXCHANGE_ZERO_COPY")) == 0;
+        bool zc = plan.nchunks == 1 && !off;
+        const void *devp[12];
+        void *outp = nullptr;
+        for (int f = 0; f <= nf && zc; ++f) {
+            cudaPointerAttributes at;
+            const void *q = f < nf ? (const void *)host[f] : (const void *)upward_fluxes;
+            if (cudaPointerGetAttributes(&at, q) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                zc = false;
+            } else if (f < nf) {
+                devp[f] = at.devicePointer;
+            } else {
+                outp = at.devicePointer;
+            }
+        }
+        if (zc) {
+            for (int f = 0; f < nf; ++f) *dev[f] = (const double *)devp[f];
+            plan.zero_copy = true;
+            plan.host_out_dev = (double *)outp;
+        }
+    }
     // a field the caller has not changed since its last upload (same counter, same host array, same staging
     // row of a staging area nothing else writes) is already on the device
     bool resident[12];
     for (int f = 0; f < nf; ++f) {
         msed_handle::ImportRow &r = h->import_row[key[f]];
-        resident[f] = h->import_gen_on && plan.stage_private && r.row == f && r.stage == stage && r.host == host[f] &&
-                      r.gen == h->import_gen[key[f]];
+        resident[f] = plan.zero_copy || (h->import_gen_on && plan.stage_private && r.row == f && r.stage == stage &&
+                                         r.host == host[f] && r.gen == h->import_gen[key[f]]);
         r.host = host[f];
         r.gen = h->import_gen[key[f]];
-        r.row = (h->import_gen_on && plan.stage_private) ? f : -1;
+        r.row = (h->import_gen_on && plan.stage_private && !plan.zero_copy) ? f : -1;
         r.stage = stage;
     }
     plan.neg = stage + (size_t)12 * h->ld;

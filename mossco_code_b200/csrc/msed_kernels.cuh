@@ -362,11 +362,11 @@ __global__ void pelagic_flux_kernel(double *pel, const double *fluxes, const dou
 }
 
 // -fluxes(:,:,n) for the export state, component :1819
-__global__ void negate_rows_kernel(double *dst, const double *src, size_t ld, int ncol, int rows)
+__global__ void negate_rows_kernel(double *dst, const double *src, size_t ld_dst, size_t ld, int ncol, int rows)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= ncol) return;
-    for (int q = 0; q < rows; ++q) dst[(size_t)q * ld + col] = -src[(size_t)q * ld + col];
+    for (int q = 0; q < rows; ++q) dst[(size_t)q * ld_dst + col] = -src[(size_t)q * ld + col];
 }
 
 // derived 3-D export fields (driver :597-604,:434-435,:284-291,:627-644 and the FABM denit diagnostic)

@@ -49,6 +49,9 @@ def default_config(**kw) -> Config:
 
 
 def _f64(a, shape=None, name="array") -> np.ndarray:
+    if (type(a) is np.ndarray and a.dtype == np.float64 and a.flags.f_contiguous and
+            (shape is None or a.shape == tuple(shape))):
+        return a                     # the common case on the Run path: nothing to convert
     a = np.asarray(a, dtype=np.float64)
     if shape is not None and tuple(a.shape) != tuple(shape):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
@@ -250,22 +253,38 @@ class SedimentDriver:
         """One component Run with host buffers (component :1493-1829): boundary assembly from the import
         fields, the step loop, and the upward bed fluxes into ``out`` -- PCIe transfers overlapped with
         the first and last attempt.  Returns (rc, upward_fluxes)."""
-        keep = []
-        t = None if temperature is None else _f64(temperature, self.shape2d, "temperature")
-        cs = (C.POINTER(C.c_double) * NVAR)()
-        ws = (C.POINTER(C.c_double) * NVAR)()
-        for n in range(NVAR):
-            for arr, src in ((cs, csurf), (ws, wz)):
-                if src is not None and src[n] is not None:
-                    a = _f64(src[n], self.shape2d, "import field")
-                    keep.append(a)
-                    arr[n] = _ptr(a)
-        if out is None:
-            out = np.zeros(self.shape2d + (self.nvar,), order="F")
-        elif out.shape != self.shape2d + (self.nvar,) or not out.flags.f_contiguous or out.dtype != np.float64:
-            raise ValueError("run_exchange: out must be fp64, Fortran order, shape (inum,jnum,nvar)")
+        # a coupler hands over the same field arrays every Run: the pointer tables are built once per set of arrays
+        # (the cache holds the arrays, so their identities stay valid)
+        key = (id(temperature), tuple(map(id, csurf)) if csurf is not None else None,
+               tuple(map(id, wz)) if wz is not None else None, id(out) if out is not None else None)
+        cached = getattr(self, "_rx_cache", None)
+        if cached is not None and cached[0] == key:
+            _, tp, cs, ws, outp, out, _keep = cached
+        else:
+            keep = [temperature, csurf, wz]
+            t = None if temperature is None else _f64(temperature, self.shape2d, "temperature")
+            cs = (C.POINTER(C.c_double) * NVAR)()
+            ws = (C.POINTER(C.c_double) * NVAR)()
+            for n in range(NVAR):
+                for arr, src in ((cs, csurf), (ws, wz)):
+                    if src is not None and src[n] is not None:
+                        a = _f64(src[n], self.shape2d, "import field")
+                        keep.append(a)
+                        arr[n] = _ptr(a)
+            fresh_out = out is None
+            if fresh_out:
+                out = np.zeros(self.shape2d + (self.nvar,), order="F")
+            elif out.shape != self.shape2d + (self.nvar,) or not out.flags.f_contiguous or out.dtype != np.float64:
+                raise ValueError("run_exchange: out must be fp64, Fortran order, shape (inum,jnum,nvar)")
+            keep.append(t)
+            tp, outp = _ptr(t), _ptr(out)
+            # only cacheable when no conversion copied a field (the copy would go stale) and the caller owns `out`
+            same = (t is temperature or t is None) and all(
+                src is None or src[n] is None or any(src[n] is k for k in keep[3:])
+                for src in (csurf, wz) for n in range(NVAR))
+            self._rx_cache = (key, tp, cs, ws, outp, out, keep) if (same and not fresh_out) else None
         rc = self._check(self._lib.msed_run_exchange(self._h, float(dt), int(method), float(run_seconds),
-                                                     _ptr(t), cs, ws, _ptr(out), C.byref(self.info)),
+                                                     tp, cs, ws, outp, C.byref(self.info)),
                          allow=(_abi.NAN_DETECTED,))
         return rc, out
 

@@ -332,6 +332,53 @@ def test_run_exchange_static_import_fields(gpu, nchunks):
     assert not np.array_equal(bumped[2][1], static[2][1])
 
 
+def test_run_exchange_zero_copy_with_pinned_fields(gpu):
+    """A one-chunk tile whose import fields and flux buffer are pinned host memory takes the zero-copy path of
+    msed_run_exchange (the boundary kernel reads the fields, the export kernel writes the fluxes through PCIe):
+    same bits as the staged copies pageable arrays get, Run after Run, also when the coupler rewrites a field in
+    place between Runs."""
+    import torch
+    from mossco_code_b200 import SedimentDriver, default_config
+    from mossco_code_b200.sediment import PARTICULATE
+    case = make_case("xzc", 50, 31, 20, 0.003, seed=95, land_fraction=0.2)
+    rng = np.random.default_rng(10)
+    sh = (50, 31)
+    keep = []
+
+    def pinned(a):
+        t = torch.empty(tuple(reversed(a.shape)), dtype=torch.float64).pin_memory()
+        keep.append(t)
+        v = t.numpy().T
+        v[...] = a
+        return v
+
+    temp = np.asfortranarray(4 + 8 * rng.random(sh))
+    cs = [np.asfortranarray((-case.fluxes[:, :, n]) if PARTICULATE[n] else case.bdys[:, :, n + 1]) for n in range(8)]
+    wz = [np.asfortranarray(1.0 + rng.random(sh)) if PARTICULATE[n] else None for n in range(8)]
+    cfg = default_config(inum=50, jnum=31, knum=20, dzmin=0.003, dt_min=1.0)
+
+    def runs(pin):
+        conv = pinned if pin else (lambda a: a.copy(order="F"))
+        t, c, w = conv(temp), [conv(a) for a in cs], [None if a is None else conv(a) for a in wz]
+        out = conv(np.zeros(sh + (8,), order="F"))
+        res = []
+        with SedimentDriver(cfg) as sed:
+            sed.set_mask(case.mask)
+            sed.init_concentrations()
+            for r in range(3):
+                if r == 2:
+                    c[6][...] *= 0.5            # oxygen above the bed halves
+                rc, up = sed.run_exchange(360.0, 2, 3600.0, t, c, w, out=out)
+                assert rc == 0 and up is out
+                res.append((up.copy(), sed.conc))
+        return res
+
+    a, b = runs(False), runs(True)
+    for (u0, c0), (u1, c1) in zip(a, b):
+        assert np.array_equal(u0, u1) and np.array_equal(c0, c1)
+    assert not np.array_equal(a[1][0], a[2][0])
+
+
 def test_run_exchange_with_rejected_attempt(gpu):
     """If an attempt is rejected the chunk-wise export is stale and must be redone from the final state."""
     from mossco_code_b200 import SedimentDriver, default_config
