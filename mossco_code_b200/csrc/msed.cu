@@ -97,6 +97,8 @@ struct msed_handle {
     int last_min_dt_grid_cell[4] = {-99, -99, -99, -99};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     cudaStream_t copy_stream = nullptr;           // msed_run_exchange: H2D of the import fields
+    cudaStream_t stream2 = nullptr;               // chunk-major Run: odd chunks run here, so that the tail of one chunk's
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // launches overlaps the head of the next chunk's
     cudaStream_t d2h_stream = nullptr;            // ... D2H of the bed fluxes, on its own stream: the fluxes of chunk c
                                                   // leave while the import fields of later chunks still arrive
     cudaEvent_t ev_pool[2 * 16] = {};             // per-chunk H2D-done / compute-done events
@@ -322,7 +324,7 @@ bool state_tmap(msed_handle *h, const double *base, CUtensorMap *out)
     return true;
 }
 
-cudaError_t launch_pair(msed_handle *h, int method, const KParams &pin)
+cudaError_t launch_pair(msed_handle *h, int method, const KParams &pin, cudaStream_t stream = nullptr)
 {
     KParams p = pin;
     if (h->colmap) {  // masked tile: run over the wet columns of [col0, col_end) only
@@ -341,7 +343,7 @@ cudaError_t launch_pair(msed_handle *h, int method, const KParams &pin)
             (!p.in_ovr || state_tmap(h, p.in_ovr, &p.tmap[2])))
             p.feed_bulk = 1;
     }
-    return tu_launch_pair(h->cfg.model, method == MSED_ADAPTIVE_EULER, p, h->stream);
+    return tu_launch_pair(h->cfg.model, method == MSED_ADAPTIVE_EULER, p, stream ? stream : h->stream);
 }
 
 // one launch = m ode_solver calls, warp per column (msed_chain.cuh)
@@ -472,16 +474,17 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
 
     // get_boundary_conditions of one chunk of msed_run_exchange as soon as its fields have landed
-    auto boundary_chunk = [&](int c) -> int {
+    auto boundary_chunk = [&](int c, cudaStream_t st = nullptr) -> int {
+        if (!st) st = h->stream;
         const int c0 = plan->c0[c], c1 = plan->c1[c];
-        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_pool[c], 0));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_pool[c], 0));
         BcPtrs bc = plan->bc;
         if (bc.temperature) bc.temperature += c0;
         for (int n = 0; n < NV; ++n) {
             if (bc.csurf[n]) bc.csurf[n] += c0;
             if (bc.wz[n]) bc.wz[n] += c0;
         }
-        boundary_kernel<<<nblocks(c1 - c0), 256, 0, h->stream>>>(
+        boundary_kernel<<<nblocks(c1 - c0), 256, 0, st>>>(
             h->bdys + c0, h->fluxes + c0, h->buf[h->cur] + c0, h->por + c0, bc, h->ld, h->ld, c1 - c0, h->K,
             h->cfg.bcup_dissolved_variables, h->bioturbation_eff, h->cfg.diffusivity, h->dz[0]);
         launches += 1;
@@ -507,9 +510,10 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     //  auto mode then stays with pairs; mode 3, set on every rank, selects chains)
 
     // export of one chunk of msed_run_exchange while the next chunks are still being computed
-    auto export_chunk = [&](int c) -> int {
+    auto export_chunk = [&](int c, cudaStream_t st = nullptr) -> int {
+        if (!st) st = h->stream;
         const int c0 = plan->c0[c], c1 = plan->c1[c];
-        CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_pool[16 + c], st));
         CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_pool[16 + c], 0));
         if (plan->zero_copy) {   // -fluxes straight into the caller's pinned array (rows ncol apart)
             negate_rows_kernel<<<nblocks(c1 - c0), 256, 0, h->d2h_stream>>>(plan->host_out_dev + c0, h->fluxes + c0,
@@ -665,8 +669,17 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         seq_mode = true;
         seq_nfl = nfl;
         double *A = h->buf[cur_before], *B = h->buf[1 - cur_before], *S = h->scratch;
+        // the chunks are independent until the commit: they alternate between two streams, so that the SMs one
+        // chunk's last wave leaves idle are taken by the next chunk's first wave (a chunk launch is only a few
+        // waves long: 2.4 on C3, where the rounding-up to whole waves cost a quarter of the Run's kernel time)
+        const bool two = plan->nchunks >= 2 && h->stream2 != nullptr;
+        if (two) {
+            CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+        }
         for (int c = 0; c < plan->nchunks; ++c) {
-            if ((rc = boundary_chunk(c))) return rc;
+            cudaStream_t st = (two && (c & 1)) ? h->stream2 : h->stream;
+            if ((rc = boundary_chunk(c, st))) return rc;
             const double *in = A;
             for (long long q = 0; q < nfl; ++q) {
                 double *out = (q % 2 == 0) ? B : S;
@@ -679,11 +692,15 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                 pc.gate_steps = 0;                       // nothing is committed before the whole interval
                 pc.up_slot = fl[q].step * depth;
                 if (q == nfl - 1) pc.denit_out = h->denit;
-                CUDA_TRY(h, launch_pair(h, method, pc));
+                CUDA_TRY(h, launch_pair(h, method, pc, st));
                 launches += 1;
                 in = out;
             }
-            if ((rc = export_chunk(c))) return rc;
+            if ((rc = export_chunk(c, st))) return rc;
+        }
+        if (two) {
+            CUDA_TRY(h, cudaEventRecord(h->ev_join, h->stream2));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         }
         first_pending = false;
         if (collective)
@@ -1114,6 +1131,10 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     h->own_stream = true;
     CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    if (!(std::getenv("MSED_EXCHANGE_TWO_STREAMS") && std::atoi(std::getenv("MSED_EXCHANGE_TWO_STREAMS")) == 0))
+        CREATE_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (auto &e : h->ev_pool) CREATE_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : h->ev_x) CREATE_TRY(cudaEventCreate(&e));
     CREATE_TRY(cudaEventCreate(&h->ev0));
@@ -1170,6 +1191,9 @@ int msed_destroy(msed_handle *h)
     for (auto &e : h->ev_pool) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev_mid) cudaEventDestroy(h->ev_mid);
     if (h->ev1) cudaEventDestroy(h->ev1);
