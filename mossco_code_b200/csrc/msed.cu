@@ -1695,170 +1695,6 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
     msed_step_info a, b;
     std::memset(&a, 0, sizeof(a));
     std::memset(&b, 0, sizeof(b));
-    int rc = run_steps(h, dt, method, nfull, true, &a);
-    if (rc == MSED_OK && rem > 0.0) rc = run_steps(h, rem, method, 1, true, &b);
-    if (info) {
-        *info = a;
-        if (rem > 0.0) {
-            info->steps_done += b.steps_done;
-            info->rhs_evaluations += b.rhs_evaluations;
-            info->subcycle_warnings += b.subcycle_warnings;
-            info->last_min_dt = b.last_min_dt;
-            for (int q = 0; q < 4; ++q) info->last_min_dt_grid_cell[q] = b.last_min_dt_grid_cell[q];
-            info->nan_detected |= b.nan_detected;
-            info->kernel_ms += b.kernel_ms;
-            info->kernel_launches += b.kernel_launches;
-            info->fused_pairs += b.fused_pairs;
-            info->fused_steps += b.fused_steps;
-            info->fused_ms += b.fused_ms;
-        }
-    }
-    return rc;
-}
-
-int msed_set_step_fusion(msed_handle *h, int enable)
-{
-    if (!h) return MSED_ERR_ARG;
-    if (enable < 0 || enable > 3) return fail(h, MSED_ERR_ARG, "step fusion mode must be 0..3");
-    h->step_fusion = enable;
-    h->pred_depth = 0;
-    h->regime_depth = 0;
-    return MSED_OK;
-}
-
-int msed_set_exchange_order(msed_handle *h, int chunk_major)
-{
-    if (!h) return MSED_ERR_ARG;
-    h->chunk_major = chunk_major ? 1 : 0;
-    return MSED_OK;
-}
-
-int msed_set_exchange_chunks(msed_handle *h, int nchunks)
-{
-    if (!h || nchunks < 0 || nchunks > 16) return fail(h, MSED_ERR_ARG, "nchunks must be in [0,16]");
-    h->exchange_chunks = nchunks;
-    return MSED_OK;
-}
-
-int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds, const double *temperature2d,
-                      const double *const *csurf, const double *const *wz, double *upward_fluxes,
-                      msed_step_info *info)
-{
-    if (!h || !upward_fluxes) return fail(h, MSED_ERR_ARG, "null argument");
-    if (!(dt > 0.0) || run_seconds < 0.0) return fail(h, MSED_ERR_ARG, "dt <= 0 or run_seconds < 0");
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    long long nfull = (long long)std::floor(run_seconds / dt * (1.0 + 1e-14));
-    double rem = run_seconds - (double)nfull * dt;
-    if (rem < 1e-9 * dt) rem = 0.0;
-    int nchunks = h->exchange_chunks;
-    // chosen from the tile size: small tiles are one chunk -- nothing to overlap, but the asynchronous
-    // sequence below still saves the host synchronisations of the three separate calls, which dominate a
-    // Run of a few tens of microseconds; msed_set_exchange_chunks(1) asks for the plain sequence
-    const bool auto_chunks = nchunks == 0;
-    if (auto_chunks) nchunks = h->ncol >= (1 << 20) ? 8 : (h->ncol >= (1 << 17) ? 4 : 1);
-    const bool pipelined = (nchunks > 1 || auto_chunks) && (method == MSED_EULER || method == MSED_ADAPTIVE_EULER) &&
-                           !h->cfg.adaptive_solver_diagnostics && (nfull + (rem > 0.0 ? 1 : 0)) > 0 &&
-                           (size_t)NV * h->K >= 12 + NV;
-    int rc;
-    if (!pipelined) {  // plain sequence: boundary, loop, export
-        if ((rc = msed_get_boundary_conditions(h, temperature2d, csurf, wz))) return rc;
-        rc = msed_run(h, dt, method, run_seconds, info);
-        if (rc < 0) return rc;
-        const int rc2 = msed_get_upward_fluxes(h, upward_fluxes);
-        return rc2 ? rc2 : rc;
-    }
-    if ((rc = ensure_scratch(h))) return rc;
-    ExchangePlan plan;
-    std::memset(&plan.bc, 0, sizeof(plan.bc));
-    plan.nchunks = nchunks;
-    const int per = ((h->ncol + nchunks - 1) / nchunks + COL_BLOCK - 1) / COL_BLOCK * COL_BLOCK;
-    int used = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int c0 = c * per, c1 = std::min(h->ncol, (c + 1) * per);
-        if (c0 >= c1) break;
-        plan.c0[used] = c0;
-        plan.c1[used] = c1;
-        ++used;
-    }
-    plan.nchunks = used;
-    // staging rows: [0..11] import fields, [12..19] negated fluxes
-    double *stage = h->scratch;
-    if (h->chunk_major) {  // the staging buffer proper is a state buffer of the chunk-major sequence (run_steps)
-        if (!h->xstage) CUDA_TRY(h, cudaMalloc(&h->xstage, (size_t)(12 + NV) * h->ld * sizeof(double)));
-        stage = h->xstage;
-        plan.stage_private = true;
-    }
-    const double *host[12];
-    const double **dev[12];
-    int key[12];   // index of the field in the generation table (msed_set_import_generations)
-    int nf = 0;
-    if (temperature2d) { host[nf] = temperature2d; dev[nf] = &plan.bc.temperature; key[nf] = 0; ++nf; }
-    for (int n = 0; n < NV; ++n) {
-        if (!csurf || !csurf[n]) continue;
-        if (n < NPART) {
-            if (!wz || !wz[n]) return fail(h, MSED_ERR_ARG, "particulate variable without z_velocity field");
-            host[nf] = wz[n]; dev[nf] = &plan.bc.wz[n]; key[nf] = 2 + 2 * n; ++nf;
-        }
-        host[nf] = csurf[n]; dev[nf] = &plan.bc.csurf[n]; key[nf] = 1 + 2 * n; ++nf;
-    }
-    for (int f = 0; f < nf; ++f) *dev[f] = stage + (size_t)f * h->ld;
-    // A tile of one chunk is a Run of a few hundred microseconds, of which a dozen small copies and their staging
-    // are a third: when every field the caller handed over is pinned host memory, the boundary kernel reads the
-    // import fields, and the export kernel writes the fluxes, directly through PCIe instead.
-    {
-        static const bool off = std::getenv("MSED_EXCHANGE_ZERO_COPY") && std::atoi(std::getenv("MSED_EXCHANGE_ZERO_COPY")) == 0;
-        bool zc = plan.nchunks == 1 && !off;
-        const void *devp[12];
-        void *outp = nullptr;
-        for (int f = 0; f <= nf && zc; ++f) {
-            cudaPointerAttributes at;
-            const void *q = f < nf ? (const void *)host[f] : (const void *)upward_fluxes;
-            if (cudaPointerGetAttributes(&at, q) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
-                cudaGetLastError();
-                zc = false;
-            } else if (f < nf) {
-                devp[f] = at.devicePointer;
-            } else {
-                outp = at.devicePointer;
-            }
-        }
-        if (zc) {
-            for (int f = 0; f < nf; ++f) *dev[f] = (const double *)devp[f];
-            plan.zero_copy = true;
-            plan.host_out_dev = (double *)outp;
-        }
-    }
-    // a field the caller has not changed since its last upload (same counter, same host array, same staging
-    // row of a staging area nothing else writes) is already on the device
-    bool resident[12];
-    for (int f = 0; f < nf; ++f) {
-        msed_handle::ImportRow &r = h->import_row[key[f]];
-        resident[f] = plan.zero_copy || (h->import_gen_on && plan.stage_private && r.row == f && r.stage == stage &&
-                                         r.host == host[f] && r.gen == h->import_gen[key[f]]);
-        r.host = host[f];
-        r.gen = h->import_gen[key[f]];
-        r.row = (h->import_gen_on && plan.stage_private && !plan.zero_copy) ? f : -1;
-        r.stage = stage;
-    }
-    plan.neg = stage + (size_t)12 * h->ld;
-    plan.host_out = upward_fluxes;
-    CUDA_TRY(h, cudaEventRecord(h->ev_x[0], h->copy_stream));
-    for (int c = 0; c < plan.nchunks; ++c) {  // all H2D traffic on the copy stream, chunk by chunk
-        const int c0 = plan.c0[c], n = plan.c1[c] - plan.c0[c];
-        for (int f = 0; f < nf; ++f)
-            if (!resident[f])
-                CUDA_TRY(h, cudaMemcpyAsync(stage + (size_t)f * h->ld + c0, host[f] + c0, (size_t)n * sizeof(double),
-                                            cudaMemcpyHostToDevice, h->copy_stream));
-        CUDA_TRY(h, cudaEventRecord(h->ev_pool[c], h->copy_stream));
-    }
-    CUDA_TRY(h, cudaEventRecord(h->ev_x[1], h->copy_stream));
-    {   // experiment switch: hold the flux copies back until every import field has landed (simplex instead of duplex)
-        static const bool gate = std::getenv("MSED_EXCHANGE_D2H_AFTER_H2D") && std::atoi(std::getenv("MSED_EXCHANGE_D2H_AFTER_H2D")) != 0;
-        if (gate) CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_x[1], 0));
-    }
-    msed_step_info a, b;
-    std::memset(&a, 0, sizeof(a));
-    std::memset(&b, 0, sizeof(b));
     bool exported = false;
     rc = MSED_OK;
     if (nfull > 0) {
