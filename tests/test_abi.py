@@ -55,6 +55,11 @@ def test_bad_arguments_are_rejected(msed_lib):
         cfg = default_config(**kw)
         assert msed_lib.msed_create(C.byref(cfg), C.byref(h)) == _abi.ERR_ARG
         assert not h.value
+    # the minimum clip compares bit patterns (clip_min): a negative floor or a NaN is refused up front
+    for bad in (-1.0e-3, float("nan")):
+        cfg = default_config(minimum=[0.0, 0.0, bad, 0.0, 0.0, 0.0, 0.0, 0.0])
+        assert msed_lib.msed_create(C.byref(cfg), C.byref(h)) == _abi.ERR_ARG
+        assert b"minimum" in msed_lib.msed_last_error(None)
     assert msed_lib.msed_destroy(None) == 0
 
 
