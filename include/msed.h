@@ -214,7 +214,8 @@ int msed_get_exchange_timing(const msed_handle *h, double *ms4);
 int msed_set_import_generations(msed_handle *h, const uint64_t *gen);
 /* Step fusion (default on): Euler / adaptive-Euler steps are issued in speculative fused launches that
  * read and write the state once for several accepted sub-steps -- pairs (thread per column, two sub-steps) or,
- * for knum <= 32, chains (warp per column with the state in registers, up to 16 sub-steps).  Each call is
+ * for knum <= 64, chains (warp per column with the state in registers, up to 16 sub-steps; one layer per lane up to
+ * 32 layers, two above).  Each call is
  * planned as a definite piece of the reference's attempt sequence (solver_library.F90:104-140), the way the
  * last completed step went: every step accepted at dt on its first attempt, or -- in a sub-cycling episode --
  * every step as the rejected attempts at dt (, dt/4) followed by 4 (16) accepted sub-steps of dt/4 (dt/16); a
@@ -224,7 +225,7 @@ int msed_set_import_generations(msed_handle *h, const uint64_t *gen);
  * stopped by check_NaN); otherwise the same attempts are redone singly from the untouched state.  Results are
  * bit-identical in every mode.  mode: 0 off, 1 auto (default: chains where they apply, else pairs),
  * 2 pairs only, 3 chains wherever knum allows.  Mode 1 picks chains for tiles of up to 65536 wet columns
- * (environment MSED_CHAIN_MAX_COLS), where a thread per column cannot fill the GPU. */
+ * (environment MSED_CHAIN_MAX_COLS; a fifth of that above 32 layers), where a thread per column cannot fill the GPU. */
 int msed_set_step_fusion(msed_handle *h, int mode);
 /* number of column chunks msed_run_exchange uses (0 = choose from the tile size: 1 to 8, always the
  * asynchronous sequence; 1 = the plain sequence of the three separate calls, no overlap) */

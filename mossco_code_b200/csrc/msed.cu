@@ -503,9 +503,12 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     h->denit_valid = false;
     // both fused kernels only work on wet columns, so the tile size that decides between them counts those
     const long long work_cols = h->colmap ? (long long)h->wet_idx.size() : (long long)h->ncol;
+    // (two layers per lane above 32 layers: one CTA per SM, so the thread-per-column pairs catch up earlier)
+    // (measured at K = 40: 15 vs 19 us per step at 10,000 columns, even at 16,384, 42 vs 29 at 32,761)
+    const long long chain_cols = h->K <= 32 ? h->chain_max_cols : h->chain_max_cols / 5;
     const bool chain_fit = h->K <= TU_CHAIN_MAX_LAYERS &&
                            (h->step_fusion == 3 ||
-                            (h->step_fusion == 1 && !collective && work_cols <= h->chain_max_cols));
+                            (h->step_fusion == 1 && !collective && work_cols <= chain_cols));
     // (with a collective every rank has to take the same decision, and the tile size is a per-rank fact:
     //  auto mode then stays with pairs; mode 3, set on every rank, selects chains)
 
@@ -1814,7 +1817,7 @@ int msed_spinup_batch(const msed_config *cfg, int32_t nmembers, const msed_spinu
     const int K = cfg->knum;
     const size_t P = (size_t)nmembers;
     // configurations outside the batch kernel's scope: member by member through msed_spinup_column
-    if (K > TU_CHAIN_MAX_LAYERS || cfg->distributed_pom_flux || cfg->model == MSED_MODEL_TEST_SOLVER) {
+    if (K > TU_SPINUP_MAX_LAYERS || cfg->distributed_pom_flux || cfg->model == MSED_MODEL_TEST_SOLVER) {
         std::vector<double> bd(NV + 1), fl(NV), col((size_t)NV * K);
         for (size_t m = 0; m < P; ++m) {
             msed_config cm = *cfg;

@@ -1,10 +1,12 @@
 // msed_chain.cuh -- included inside namespace msed after msed_pair.cuh.
 //
 // A chain of consecutive Euler / adaptive-Euler steps with the column state held in REGISTERS: one
-// warp owns one sediment column, lane k owns layer k (knum <= 32).  The vertical stencil of diff3d is
-// one layer wide, so a step needs the state of the layer below (one __shfl_down per variable) and the
-// flux through the upper interface, which the lane above has just computed (one __shfl_up per
-// variable).  The state is read from HBM once, advanced nsub steps, and written once: per step the
+// warp owns one sediment column, lane k owns layer k (knum <= 32) -- or, LPL = 2, layers 2k and 2k+1
+// (32 < knum <= 64: BASELINE config 4's 40 layers on a tile too small for a thread per column).  The
+// vertical stencil of diff3d is one layer wide, so a step needs the state of the layer below the lane's
+// deepest layer (one __shfl_down per variable) and the flux through the upper interface of its first
+// layer, which the lane above has just computed (one __shfl_up per variable); the interface between a
+// lane's own two layers is local.  The state is read from HBM once, advanced nsub steps, and written once: per step the
 // chain moves 128/nsub bytes per cell instead of the 128 of the single-step kernel.
 //
 // Why a second fused kernel next to pair_kernel (thread per column, two steps per launch):
@@ -33,7 +35,7 @@
 
 constexpr int CHAIN_WARPS = 8;                  // columns per CTA: 8 adjacent columns = 64 contiguous bytes per row
 constexpr int CHAIN_BLOCK = CHAIN_WARPS * 32;
-constexpr int CHAIN_MAX_LAYERS = 32;
+constexpr int CHAIN_MAX_LAYERS = 64;            // 32 layers per LPL
 #ifndef MSED_CHAIN_MIN_BLOCKS
 #define MSED_CHAIN_MIN_BLOCKS 2
 #endif
@@ -45,8 +47,9 @@ constexpr int CHAIN_MAX_LAYERS = 32;
 // (msed_step / msed_run set it, msed_ode_solver does not), mirrored in Ctl::do_clip
 // SUB: the plan holds sub-cycled steps (KParams::depth > 0); a separate instantiation so that the common
 // chain (every step accepted at dt) keeps its straight step loop
-template <int MODEL, bool ADAPTIVE, bool CLIP, bool SUB>
-__global__ void __launch_bounds__(CHAIN_BLOCK, MSED_CHAIN_MIN_BLOCKS)
+// LPL: layers per lane (1: knum <= 32, 128 registers, two CTAs per SM; 2: knum <= 64, one CTA per SM)
+template <int MODEL, bool ADAPTIVE, bool CLIP, bool SUB, int LPL = 1>
+__global__ void __launch_bounds__(CHAIN_BLOCK, LPL == 1 ? MSED_CHAIN_MIN_BLOCKS : 1)
 chain_kernel(const __grid_constant__ KParams p, const int nsub)
 {
     const Ctl *ctl = p.ctl;
@@ -71,20 +74,28 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     if (p.mask[col] != 0) return;  // conc stays missing_value in both buffers
 
     const int K = p.K;
-    const bool active = lane < K;
-    const int k = active ? lane : K - 1;   // spare lanes shadow the deepest layer; they never store or flag
-    const bool has_next = lane + 1 < K;
     const size_t ld = p.ld;
     const size_t plane = (size_t)K * ld;
-
-    double cc[NV];
-    {
-        const double *in = p.buf[cur] + (size_t)k * ld + col;
+    // the lane's layers, top to bottom; spare slots shadow the deepest layer, they never store or flag
+    bool active[LPL], has_next[LPL];
+    int k[LPL];
 #pragma unroll
-        for (int n = 0; n < NV; ++n) cc[n] = in[(size_t)n * plane];
+    for (int j = 0; j < LPL; ++j) {
+        const int kj = LPL * lane + j;
+        active[j] = kj < K;
+        k[j] = active[j] ? kj : K - 1;
+        has_next[j] = kj + 1 < K;
     }
 
-    // ---- step-invariant coefficients of this lane's layer and of its lower interface ------------
+    double cc[LPL][NV];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        const double *in = p.buf[cur] + (size_t)k[j] * ld + col;
+#pragma unroll
+        for (int n = 0; n < NV; ++n) cc[j][n] = in[(size_t)n * plane];
+    }
+
+    // ---- step-invariant coefficients of the lane's layers and of their lower interfaces ------------
     const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
     const double temp = ld_ro(p.bdys + col);
     double cpart, cdiss, fT;
@@ -93,13 +104,17 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     if (MODEL != MSED_MODEL_OMEXDIA_P && p.denit_out)
         fT_diag = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
 
-    const double porc = __dmul_rn(por_surf, p.portab[k]);
-    double porn = 0.0, mDp = 0.0, mDd = 0.0;
-    if (has_next) {
-        porn = __dmul_rn(por_surf, p.portab[k + 1]);
-        interface_coeffs(cpart, cdiss, porc, porn, p.bf[k + 1], p.rdzc[k], mDp, mDd);
+    double porc[LPL], porn[LPL], mDp[LPL], mDd[LPL], rpd[LPL];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        porc[j] = __dmul_rn(por_surf, p.portab[k[j]]);
+        porn[j] = mDp[j] = mDd[j] = 0.0;
+        if (has_next[j]) {
+            porn[j] = __dmul_rn(por_surf, p.portab[k[j] + 1]);
+            interface_coeffs(cpart, cdiss, porc[j], porn[j], p.bf[k[j] + 1], p.rdzc[k[j]], mDp[j], mDd[j]);
+        }
+        rpd[j] = fast_rcp(MSED_MUL(porc[j], p.dz[k[j]]));
     }
-    const double rpd = fast_rcp(MSED_MUL(porc, p.dz[k]));
     // upper boundary (used by lane 0 only): diff3d :782-803
     const int bc_diss = p.bcup_diss;
     const double por0 = __dmul_rn(por_surf, p.portab[0]);
@@ -107,9 +122,11 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     top_coeffs(cpart, cdiss, por0, p.bf[0], Dp0, Dd0);
     const double rdz0 = 1.0 / p.dz[0];
 
-    int viol = 0;  // sign bit = some relative change fell below relative_change_min (violates_acc)
-    bool nanf = false;
-    double dn_last = 0.0;
+    int viol[LPL];  // sign bit = some relative change fell below relative_change_min (violates_acc)
+    bool nanf[LPL];
+    double dn_last[LPL];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) { viol[j] = 0; nanf[j] = false; dn_last[j] = 0.0; }
 
     // where lane 0 finds the upper-boundary input of a dissolved variable: the concentration above the
     // bed for BcUp = 2 (bdys row n+1), the imposed flux for BcUp = 1 (fluxes row n); any other BcUp
@@ -133,37 +150,46 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
 #pragma unroll
         for (int n = 0; n < NV; ++n) tin[n] = ld_ro((n < NPART ? top_part : top_diss) + (size_t)n * ld);
 
-        // the state of the layer below is requested first: the shuffles complete while the reaction term,
-        // which does not need it, is evaluated
+        // the state of the layer below the lane's deepest layer (the next lane's first) is requested first: the
+        // shuffles complete while the reaction term, which does not need it, is evaluated
         double cn[NV];
 #pragma unroll
-        for (int n = 0; n < NV; ++n) cn[n] = __shfl_down_sync(FULL, cc[n], 1);
+        for (int n = 0; n < NV; ++n) cn[n] = __shfl_down_sync(FULL, cc[0][n], 1);
 
         // local reaction rates (fabm_do, driver :700): independent of the neighbours
-        double r[NV], dn = 0.0;
-        if (MODEL == MSED_MODEL_OMEXDIA_P) {
-            omexdia_rates(p.om, cc, fT, r, &dn);
-        } else {
-            if (last && p.denit_out) omexdia_rates(p.om, cc, fT_diag, r, &dn);
+        double r[LPL][NV];
 #pragma unroll
-            for (int n = 0; n < NV; ++n) r[n] = 0.0;
+        for (int j = 0; j < LPL; ++j) {
+            double dn = 0.0;
+            if (MODEL == MSED_MODEL_OMEXDIA_P) {
+                omexdia_rates(p.om, cc[j], fT, r[j], &dn);
+            } else {
+                if (last && p.denit_out) omexdia_rates(p.om, cc[j], fT_diag, r[j], &dn);
+#pragma unroll
+                for (int n = 0; n < NV; ++n) r[j][n] = 0.0;
+            }
+            if (last) dn_last[j] = dn;  // the FABM diagnostic describes the state of the last get_rhs call
         }
-        if (last) dn_last = dn;  // the FABM diagnostic describes the state of the last get_rhs call
 
-        // flux through the lower interface (diff3d :776-778; BcDown = 3 below the deepest layer)
-        double Fn[NV];
+        // flux through the lower interface of every layer of the lane (diff3d :776-778; BcDown = 3 below the
+        // deepest layer): towards the lane's own next layer, or towards the next lane's first
+        double Fn[LPL][NV];
 #pragma unroll
-        for (int n = 0; n < NV; ++n) {
-            const double f = (n < NPART) ? flux_particulate(mDp, cn[n], porn, cc[n], porc)
-                                         : flux_dissolved(mDd, cn[n], cc[n]);
-            Fn[n] = has_next ? f : 0.0;
+        for (int j = 0; j < LPL; ++j) {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double below = (j + 1 < LPL) ? cc[j + 1 < LPL ? j + 1 : j][n] : cn[n];
+                const double f = (n < NPART) ? flux_particulate(mDp[j], below, porn[j], cc[j][n], porc[j])
+                                             : flux_dissolved(mDd[j], below, cc[j][n]);
+                Fn[j][n] = has_next[j] ? f : 0.0;
+            }
         }
-        // flux through the upper interface = the lower-interface flux of the layer above.  (Shuffling the
-        // state up instead and recomputing that flux here, to drop this second exchange from the critical
-        // path, was measured 7-8 % slower: 19 more fp64 instructions per step.)
+        // flux through the upper interface of the lane's first layer = the lower-interface flux of the lane
+        // above's last layer.  (Shuffling the state up instead and recomputing that flux here, to drop this
+        // second exchange from the critical path, was measured 7-8 % slower: 19 more fp64 instructions per step.)
         double F[NV];
 #pragma unroll
-        for (int n = 0; n < NV; ++n) F[n] = __shfl_up_sync(FULL, Fn[n], 1);
+        for (int n = 0; n < NV; ++n) F[n] = __shfl_up_sync(FULL, Fn[LPL - 1][n], 1);
         // upper boundary, diff3d :782-803: only lane 0 keeps the result.  Every lane evaluates it (a warp
         // pays for a one-lane branch body anyway; selects keep the instruction stream straight).
         // Particulates: BcUp = 1 (the host only fuses configurations without the distributed POM flux
@@ -174,7 +200,7 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
         if (bc_diss == 2) {                                     // Dirichlet, :786
 #pragma unroll
             for (int n = NPART; n < NV; ++n) {
-                const double f = top_flux_dirichlet(Dd0, cc[n], tin[n], rdz0);
+                const double f = top_flux_dirichlet(Dd0, cc[0][n], tin[n], rdz0);
                 F[n] = top ? f : F[n];
             }
         } else if (bc_diss == 1 || bc_diss == 4) {              // imposed flux (rewritten unchanged below)
@@ -192,34 +218,41 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
             for (int n = NPART; n < NV; ++n) p.fluxes[(size_t)n * ld + col] = F[n];  // :692
         }
 
-        double raw[NV];  // new state before the clip (check_NaN looks at it first, component :1718)
         int vup = 0;
 #pragma unroll
-        for (int n = 0; n < NV; ++n) {
-            const double rhs = layer_rhs(F[n], Fn[n], rpd, r[n]);
-            const double c0 = cc[n];
-            double newc = euler_update(dt, rhs, c0);
-            if (ADAPTIVE) violates_acc(viol, p.fac, c0, newc);
-            if (ADAPTIVE && SUB && q == 0) {   // the planned rejections: tested exactly as a single attempt does
+        for (int j = 0; j < LPL; ++j) {
+            double raw[NV];  // new state before the clip (check_NaN looks at it first, component :1718)
 #pragma unroll
-                for (int l = 0; l < MAX_PLAN_DEPTH; ++l)
-                    if (l < depth && violates(p.fac, c0, euler_update(dt_up[l], rhs, c0))) vup |= 1 << l;
+            for (int n = 0; n < NV; ++n) {
+                const double fup = (j == 0) ? F[n] : Fn[j > 0 ? j - 1 : 0][n];
+                const double rhs = layer_rhs(fup, Fn[j][n], rpd[j], r[j][n]);
+                const double c0 = cc[j][n];
+                double newc = euler_update(dt, rhs, c0);
+                if (ADAPTIVE) violates_acc(viol[j], p.fac, c0, newc);
+                if (ADAPTIVE && SUB && q == 0) {   // the planned rejections: tested exactly as a single attempt does
+#pragma unroll
+                    for (int l = 0; l < MAX_PLAN_DEPTH; ++l)
+                        if (l < depth && active[j] && violates(p.fac, c0, euler_update(dt_up[l], rhs, c0))) vup |= 1 << l;
+                }
+                raw[n] = newc;
+                if (CLIP && final_sub) {
+                    if (n & 1) nanf[j] |= either_nan(raw[n - 1], raw[n]);
+                    const double mn = p.om.minimum[n];
+                    newc = clip_min(newc, mn);
+                }
+                cc[j][n] = newc;
             }
-            raw[n] = newc;
-            if (CLIP && final_sub) {
-                if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
-                const double mn = p.om.minimum[n];
-                newc = clip_min(newc, mn);
-            }
-            cc[n] = newc;
         }
         if (ADAPTIVE && SUB && q == 0) {
 #pragma unroll
             for (int l = 0; l < MAX_PLAN_DEPTH; ++l)
-                if (l < depth && __any_sync(FULL, (vup & (1 << l)) && active)) upmask |= 1u << (s * depth + l);
+                if (l < depth && __any_sync(FULL, (vup & (1 << l)) != 0)) upmask |= 1u << (s * depth + l);
         }
         // a rejectable violation anywhere in the column: the chain will not be committed, stop here
-        if (rejectable && __any_sync(FULL, viol < 0 && active)) {
+        bool v_any = false;
+#pragma unroll
+        for (int j = 0; j < LPL; ++j) v_any |= (viol[j] < 0 && active[j]);
+        if (rejectable && __any_sync(FULL, v_any)) {
             if (lane == 0) {
                 atomicOr(&p.ctl->flags[0], 1);
                 atomicMax(&p.ctl->flags[FLAG_FAIL], 64 - s);   // where: the earliest such step wins (run_steps re-plans)
@@ -228,14 +261,20 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
         }
     }
 
-    if (active) {
-        double *out = p.buf[1 - cur] + (size_t)k * ld + col;
+    bool v_any = false, n_any = false;
 #pragma unroll
-        for (int n = 0; n < NV; ++n) out[(size_t)n * plane] = cc[n];
-        if (p.denit_out) p.denit_out[(size_t)k * ld + col] = dn_last;
+    for (int j = 0; j < LPL; ++j) {
+        if (active[j]) {
+            double *out = p.buf[1 - cur] + (size_t)k[j] * ld + col;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) out[(size_t)n * plane] = cc[j][n];
+            if (p.denit_out) p.denit_out[(size_t)k[j] * ld + col] = dn_last[j];
+        }
+        v_any |= (viol[j] < 0 && active[j]);
+        n_any |= (nanf[j] && active[j]);
     }
-    const bool any_viol = __any_sync(FULL, viol < 0 && active);
-    const bool any_nan = __any_sync(FULL, nanf && active);
+    const bool any_viol = __any_sync(FULL, v_any);
+    const bool any_nan = __any_sync(FULL, n_any);
     if (lane == 0) {
         if (ADAPTIVE && any_viol) atomicOr(&p.ctl->flags[0], 1);
         if (any_nan) atomicOr(&p.ctl->flags[1], 1);

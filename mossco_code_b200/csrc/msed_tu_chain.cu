@@ -13,7 +13,12 @@ cudaError_t tu_launch_chain(int model, bool adaptive, bool clip, const KParams &
     if (p.col_end <= p.col0) return cudaSuccess;
     const dim3 grid((p.col_end - p.col0 + CHAIN_WARPS - 1) / CHAIN_WARPS), block(CHAIN_BLOCK);
     const bool sub = adaptive && p.depth > 0;
-#define MSED_CHAIN(MODEL, AD, CL, SB) chain_kernel<MODEL, AD, CL, SB><<<grid, block, 0, s>>>(p, m)
+    const bool two = p.K > 32;   // two layers per lane
+#define MSED_CHAIN(MODEL, AD, CL, SB)                                                    \
+    do {                                                                                 \
+        if (two) chain_kernel<MODEL, AD, CL, SB, 2><<<grid, block, 0, s>>>(p, m);        \
+        else chain_kernel<MODEL, AD, CL, SB, 1><<<grid, block, 0, s>>>(p, m);            \
+    } while (0)
 #define MSED_CHAIN_CL(MODEL, AD, CL) do { if (sub) MSED_CHAIN(MODEL, AD, CL, true); else MSED_CHAIN(MODEL, AD, CL, false); } while (0)
 #define MSED_CHAIN_MODEL(MODEL)                                                                              \
     do {                                                                                                     \
