@@ -88,6 +88,13 @@ struct msed_handle {
     cudaEvent_t ev_snap = nullptr, ev_export = nullptr;
     cudaStream_t export_stream = nullptr;   // its own stream: the per-Run flux copies on copy_stream must not queue behind it
     bool export_pending = false, export_direct = false;
+    // the export is handed to the copy engine a few column slices at a time (export_pump): a device-to-host engine
+    // works its queue off in submission order, and a state's worth of slices submitted at once would hold up the
+    // bed-flux copies of every Run until the whole export is through
+    const double *export_src = nullptr;
+    double *export_dst = nullptr;
+    size_t export_next = 0, export_slice = 0;    // next element of the dense host array to submit; elements per slice
+    bool export_submitted = false;               // every slice is in the queue and ev_export is recorded
     int compat = 0;             // MSED_COMPAT_* (msed_set_compat)
     int cur = 0;
     int por_mode = 1;           // how the column kernel obtains porosity (see KParams::por_mode)
@@ -378,6 +385,31 @@ int reduce_flags(msed_handle *h, int nflags = 8)
         if (rc != 0)
             return fail(h, MSED_ERR_NCCL, std::string("ncclAllReduce: ") +
                                               (api.GetErrorString ? api.GetErrorString(rc) : "error"));
+    }
+    return MSED_OK;
+}
+
+// hand the next slices of a pending state export to the copy engine: about `budget_bytes` worth (everything if < 0).
+// Slices are plain contiguous copies -- runs of whole rows when the device rows are unpadded, pieces of one row
+// otherwise -- of at most export_slice elements; export_next counts elements of the dense host array.
+int export_pump(msed_handle *h, double budget_bytes)
+{
+    if (!h->export_pending || h->export_submitted) return MSED_OK;
+    const size_t ncol = (size_t)h->ncol, total = (size_t)NV * h->K * ncol;
+    const bool dense = h->ld == ncol;
+    double sent = 0.0;
+    while (h->export_next < total && (budget_bytes < 0 || sent < budget_bytes)) {
+        const size_t e = h->export_next, r = e / ncol, c = e % ncol;
+        size_t n = std::min(h->export_slice, total - e);
+        if (!dense) n = std::min(n, ncol - c);           // stay inside the row
+        CUDA_TRY(h, cudaMemcpyAsync(h->export_dst + e, h->export_src + r * h->ld + c, n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->export_stream));
+        h->export_next += n;
+        sent += (double)(n * sizeof(double));
+    }
+    if (h->export_next >= total) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_export, h->export_stream));
+        h->export_submitted = true;
     }
     return MSED_OK;
 }
@@ -982,6 +1014,15 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
         info->fused_pairs = r.fused_launches;
         info->fused_steps = r.fused_steps;
         info->fused_ms = nfl > 0 ? ms_pairs : 0.0;
+    }
+    if (h->export_pending && !h->export_submitted && !plan) {
+        // the next helping of a pending state export: what the copy engine moves in half of the time this call's
+        // kernels took (device time, not wall time: a call that waited for copies must not order more of them), so
+        // that the next call's own device-to-host copies find the queue empty when they matter.  (A Run with host
+        // buffers does this itself, after it has waited for its flux copies: the completion of a stream whose last
+        // operation was a copy is signalled through the copy engine's queue, behind whatever was queued before.)
+        const int prc = export_pump(h, std::max(16.0e6, 0.5 * (double)ms * 1.0e-3 * 50.0e9));
+        if (prc) return prc;
     }
     return r.nan_detected ? MSED_NAN_DETECTED : MSED_OK;
 }
@@ -1730,6 +1771,10 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
         const int rc2 = msed_get_upward_fluxes(h, upward_fluxes);
         if (rc2) return rc2;
     }
+    if (h->export_pending && !h->export_submitted) {   // see run_steps
+        const int prc = export_pump(h, std::max(16.0e6, 0.5 * (a.kernel_ms + b.kernel_ms) * 1.0e-3 * 50.0e9));
+        if (prc) return prc;
+    }
     if (info) {
         *info = a;
         if (rem > 0.0) {
@@ -2120,11 +2165,20 @@ int msed_export_state_begin(msed_handle *h, double *conc_host)
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_snap, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(h->export_stream, h->ev_snap, 0));
-    CUDA_TRY(h, cudaMemcpy2DAsync(conc_host, (size_t)h->ncol * sizeof(double), src, h->ld * sizeof(double),
-                                  (size_t)h->ncol * sizeof(double), (size_t)NV * h->K, cudaMemcpyDeviceToHost,
-                                  h->export_stream));
-    CUDA_TRY(h, cudaEventRecord(h->ev_export, h->export_stream));
-    if (!h->snap) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_export, 0));   // the state must stay put
+    // in column slices of about 32 MB, a few at a time (export_pump)
+    {
+        h->export_slice = ((size_t)32 << 20) / sizeof(double);   // elements per copy
+        h->export_src = src;
+        h->export_dst = conc_host;
+        h->export_next = 0;
+        h->export_submitted = false;
+        h->export_pending = true;
+        // without a snapshot the state must stay put until the copy is through: everything at once, and the
+        // compute stream waits; with one, a first helping now and the rest under the calls that follow
+        const int rc = export_pump(h, h->snap ? 128.0e6 : -1.0);
+        if (rc) return rc;
+        if (!h->snap) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_export, 0));
+    }
     h->export_pending = true;
     return MSED_OK;
 }
@@ -2134,6 +2188,8 @@ int msed_export_state_wait(msed_handle *h)
     if (!h) return MSED_ERR_ARG;
     if (!h->export_pending) return MSED_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    const int rc = export_pump(h, -1.0);
+    if (rc) return rc;
     CUDA_TRY(h, cudaEventSynchronize(h->ev_export));
     h->export_pending = false;
     return MSED_OK;
