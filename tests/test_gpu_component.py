@@ -278,3 +278,78 @@ def test_component_masked_tile_pairs_chunk_major(gpu, seconds):
         assert set(a) == set(b)
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("shape,pin", [((37, 11), False), ((64, 8), True), ((64, 8), False), ((9, 1), True)])
+def test_asynchronous_state_export_is_a_snapshot(gpu, shape, pin):
+    """msed_export_state_begin / _wait (the <name>_in_soil write-back of fabm_sediment_component.F90:1773-1822 at an
+    output cadence): the copy is handed to the engine in slices under the stepping calls that follow, and what
+    arrives is the state at the moment of begin -- padded device rows (37x11) and unpadded ones (64x8), pinned and
+    pageable destinations, Runs with host buffers and plain steps in between, two exports in a row."""
+    import torch
+    from mossco_code_b200 import SedimentDriver, default_config
+    from mossco_code_b200.sediment import PARTICULATE
+    inum, jnum = shape
+    case = make_case("xexp", inum, jnum, 20, 0.003, seed=31, land_fraction=0.2 if inum > 9 else 0.0)
+    cfg = default_config(inum=inum, jnum=jnum, knum=20, dzmin=0.003, dt_min=1.0)
+    keep = []
+
+    def buf():
+        if not pin:
+            return np.full((inum, jnum, 20, 8), -7.0, order="F")
+        t = torch.full((8, 20, jnum, inum), -7.0, dtype=torch.float64).pin_memory()
+        keep.append(t)
+        return t.numpy().T
+
+    temp = np.asfortranarray(case.bdys[:, :, 0])
+    cs = [np.asfortranarray((-case.fluxes[:, :, n]) if PARTICULATE[n] else case.bdys[:, :, n + 1]) for n in range(8)]
+    wz = [np.ones(shape, order="F") if PARTICULATE[n] else None for n in range(8)]
+    with SedimentDriver(cfg) as sed:
+        sed.set_mask(case.mask)
+        sed.init_concentrations()
+        sed.set_boundary(case.bdys, case.fluxes)
+        assert sed.step(360.0, 2, 3) == 0
+        want1 = sed.conc
+        out1 = buf()
+        sed.export_state_begin(out1)
+        for _ in range(2):                                   # Runs with host buffers while the export is pending
+            rc, _ = sed.run_exchange(360.0, 2, 3600.0, temp, cs, wz)
+            assert rc == 0
+        assert sed.step(360.0, 2, 5) == 0                    # ... and plain steps
+        want2 = sed.conc
+        out2 = buf()
+        sed.export_state_begin(out2)                          # completes the first export, starts the second
+        assert np.array_equal(out1, want1)
+        assert sed.step(360.0, 0, 2) == 0
+        sed.export_state_wait()
+        assert np.array_equal(out2, want2)
+        assert not np.array_equal(want1, want2) and not np.array_equal(sed.conc, want2)
+        sed.export_state_wait()                               # nothing pending: a no-op
+
+
+def test_component_export_cadence(gpu):
+    """export_cadence: every n-th Run starts the asynchronous export; export_ready() completes it and points the
+    <var>_in_soil fields at the buffer, which holds the state of that Run while later Runs have moved on."""
+    from mossco_code_b200.component import FabmSedimentComponent
+    case = make_case("xcad", 12, 7, 15, 0.004, seed=8)
+    comp = FabmSedimentComponent()
+    imp, exp = {}, {}
+    comp.initialize_p0(imp, exp)
+    comp.initialize_p1(imp, exp, grid_shape=(12, 7), grid_mask=1 - case.mask,
+                       run_nml=dict(numlayers=15, dzmin=0.004, dt=360.0, dt_min=1.0, ode_method=2))
+    comp.initialize_p2(imp, exp)
+    imp.update(_import_state(case, np.random.default_rng(0)))
+    comp.export_3d_every_run = False
+    comp.export_cadence = 2
+    states = []
+    for r in range(4):
+        assert comp.run(imp, exp, run_seconds=1800.0) == 0
+        states.append(comp.sed.conc)
+        if r == 2:
+            assert comp.export_ready(exp)                     # the export started after Run 2 (index 1)
+            assert np.array_equal(comp.export_buffer, states[1])
+            assert np.array_equal(exp["dissolved_oxygen_in_soil"], states[1][:, :, :, 6])
+    assert comp.export_ready(exp)                             # the one started after Run 4
+    assert np.array_equal(comp.export_buffer, states[3])
+    assert not comp.export_ready(exp)
+    comp.finalize()
