@@ -1815,6 +1815,17 @@ int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const doubl
                        int method, double *conc1d, msed_step_info *info)
 {
     if (!cfg || !bdys1d || !fluxes1d || !conc1d) return fail(nullptr, MSED_ERR_ARG, "null argument");
+    // One column is a batch of one: the whole pre-simulation in a single launch with the column in registers
+    // (2 years: about 1 s) instead of a launch per attempt on a 1x1 tile (40 s; bit-identical,
+    // tests/test_gpu_spinup.py).  MSED_SPINUP_PATH=steps keeps the launch-per-attempt path, which also serves the
+    // configurations outside the batch kernel's scope.
+    {
+        const char *e = std::getenv("MSED_SPINUP_PATH");
+        const bool steps = e && !std::strcmp(e, "steps");
+        if (!steps && cfg->knum <= TU_SPINUP_MAX_LAYERS && !cfg->distributed_pom_flux &&
+            cfg->model != MSED_MODEL_TEST_SOLVER)
+            return msed_spinup_batch(cfg, 1, nullptr, bdys1d, fluxes1d, nsteps, method, conc1d, info);
+    }
     // sed1d: a 1x1xknum clone with Dirichlet boundaries, constant bioturbation and solver
     // diagnostics switched on (component :557-611); dt_spinup = 3600 s (:574)
     msed_config c1 = *cfg;

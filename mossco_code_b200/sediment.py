@@ -11,6 +11,7 @@ Everything here calls libmsed_b200.so; there is no CPU implementation.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -481,8 +482,24 @@ def ode_solver(rhs_driver: SedimentDriver, dt: float, method: int) -> StepInfo:
     return rhs_driver.ode_solver(dt, method)
 
 
-def spinup_column(cfg: Config, bdys1d, fluxes1d, nsteps: int, method: int = ADAPTIVE_EULER):
-    """1-D pre-simulation (component :557-632): returns conc(1,1,knum,nvar) and the StepInfo."""
+def spinup_column(cfg: Config, bdys1d, fluxes1d, nsteps: int, method: int = ADAPTIVE_EULER, launch_per_attempt=False):
+    """1-D pre-simulation (component :557-632): returns conc(1,1,knum,nvar) and the StepInfo.  The library runs it
+    as a batch of one (a single launch); ``launch_per_attempt`` asks for the step-by-step path on a 1x1 tile
+    (environment MSED_SPINUP_PATH=steps), which the batch kernel is checked against."""
+    old = os.environ.get("MSED_SPINUP_PATH")
+    if launch_per_attempt:
+        os.environ["MSED_SPINUP_PATH"] = "steps"
+    try:
+        return _spinup_column(cfg, bdys1d, fluxes1d, nsteps, method)
+    finally:
+        if launch_per_attempt:
+            if old is None:
+                os.environ.pop("MSED_SPINUP_PATH", None)
+            else:
+                os.environ["MSED_SPINUP_PATH"] = old
+
+
+def _spinup_column(cfg: Config, bdys1d, fluxes1d, nsteps: int, method: int):
     b = _f64(np.asarray(bdys1d).reshape(-1), (NVAR + 1,), "bdys1d")
     f = _f64(np.asarray(fluxes1d).reshape(-1), (NVAR,), "fluxes1d")
     out = np.zeros((1, 1, cfg.knum, NVAR), order="F")

@@ -39,7 +39,7 @@ def test_spinup_batch_equals_single_columns(gpu, method, knum, dzmin):
     subs = []
     for m in range(P):
         cm = default_config(knum=knum, dzmin=dzmin, dt_min=1.0, bioturbation_profile=1, **mem[m])
-        want, wi = spinup_column(cm, bd[m], fl[m], nsteps, method)
+        want, wi = spinup_column(cm, bd[m], fl[m], nsteps, method, launch_per_attempt=True)
         assert np.array_equal(got[m], want[0], equal_nan=True), m
         assert infos[m].steps_done == nsteps
         assert infos[m].rhs_evaluations == wi.rhs_evaluations, m
