@@ -241,7 +241,7 @@ int msed_spinup_column(const msed_config *cfg, const double *bdys1d, const doubl
                        int64_t nsteps, int method, double *conc1d, msed_step_info *info);
 
 /* The same pre-simulation for a BATCH of nmembers independent 1-D columns in one launch (warp per member,
- * the column in registers for all nsteps calls; knum <= 32, no distributed POM flux -- other configurations
+ * the column in registers for all nsteps calls, one layer per lane up to 32 layers and two above; no distributed POM flux -- other configurations
  * loop over msed_spinup_column).  Members share cfg's grid and sed_nml and differ in bdys1d(nmembers,nvar+1),
  * fluxes1d(nmembers,nvar) (Fortran order: member fastest) and, if members != NULL, in their reaction
  * parameters and initial values.  Every member is its own domain, as sed1d is in the reference: the accept

@@ -1116,7 +1116,7 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     if (!h) return fail(nullptr, MSED_ERR_ALLOC, "host allocation failed");
     h->cfg = *cfg;
     for (int n = 0; n < NV; ++n) h->cfg.minimum[n] += 0.0;   // -0.0 -> +0.0
-    // auto fusion mode: tiles up to this many columns take the warp-per-column chain kernel when knum <= 32
+    // auto fusion mode: tiles up to this many columns take the warp-per-column chain kernel (a fifth of it above 32 layers)
     // measured on B200 (profiles/r01_chain_kernel.md): chains win below ~60k columns, where the thread-per-
     // column pair kernel cannot fill the machine (one wave = 148 SMs x 3 CTAs x 128 columns), and lose 5-10 % above
     h->chain_max_cols = 65536;

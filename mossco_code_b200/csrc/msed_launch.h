@@ -18,14 +18,14 @@ cudaError_t tu_enable_pair_smem();
 // chain_kernel (msed_chain.cuh): nsteps ode_solver calls per launch, warp per column, knum <= 64
 cudaError_t tu_launch_chain(int model, bool adaptive, bool clip, const KParams &p, int nsteps, cudaStream_t s);
 constexpr int TU_CHAIN_MAX_LAYERS = 64;   // one layer per lane up to 32, two above
-constexpr int TU_SPINUP_MAX_LAYERS = 32;  // spinup_kernel: one layer per lane
+constexpr int TU_SPINUP_MAX_LAYERS = 64;  // spinup_kernel: one layer per lane up to 32, two above
 constexpr int TU_CHAIN_MAX_STEPS = 16;   // steps per launch: bounds the work a failed speculation throws away
 
 // rk_pair_kernel (msed_rkpair.cuh): which = 0 for stages 1+2, 1 for stages 3+4
 cudaError_t tu_launch_rk_pair(int model, int method, int which, const KParams &p, cudaStream_t s);
 cudaError_t tu_enable_rk_smem();
 
-// spinup_kernel (msed_spinup.cuh): the 1-D pre-simulation of a batch of members, warp per member, knum <= 32
+// spinup_kernel (msed_spinup.cuh): the 1-D pre-simulation of a batch of members, warp per member, knum <= 64
 cudaError_t tu_launch_spinup(int model, const KParams &p, const SpinupArgs &a, cudaStream_t s);
 
 }  // namespace msed

@@ -312,7 +312,7 @@ class SedimentDriver:
 
     def set_step_fusion(self, mode):
         """Speculative fused launches (results are bit-identical in every mode): False/"off", True/"auto"
-        (chains -- warp per column, up to 16 steps per launch -- where knum <= 32, else pairs), "pairs"
+        (chains -- warp per column, up to 16 steps per launch -- on small tiles, else pairs), "pairs"
         (thread per column, two steps per launch) or "chains"."""
         if isinstance(mode, str):
             mode = self.FUSION_MODES[mode]
