@@ -556,6 +556,7 @@ def main():
     e2e_export = None
     if not coupled and (state_bytes <= 12e9 or os.environ.get("MSED_BENCH_EXPORT") == "1"):
         tb_, comp.export_buffer = pinned_fortran((inum, rows, knum, NVAR)); keep.append(tb_)
+        sed.export_state_begin(comp.export_buffer); sed.export_state_wait()   # untimed: allocates the snapshot buffer, creates the stream
         if not subcyc:
             sed.init_concentrations()
         comp.export_cadence, comp._runs = EXPORT_CADENCE, EXPORT_CADENCE - 1    # the first timed Run is a cadence Run
