@@ -359,6 +359,12 @@ cudaError_t launch_chain(const msed_handle *h, int method, const KParams &p, int
     return tu_launch_chain(h->cfg.model, method == MSED_ADAPTIVE_EULER, clip, p, m, h->stream);
 }
 
+// one launch = m Runge-Kutta ode_solver calls, warp per column (msed_chain.cuh)
+cudaError_t launch_rk_chain(const msed_handle *h, int method, const KParams &p, int m, bool clip)
+{
+    return tu_launch_rk_chain(h->cfg.model, method, clip, p, m, h->stream);
+}
+
 // one launch = two chained Runge-Kutta stages (msed_rkpair.cuh); which = 0 for stages 1+2, 1 for 3+4
 cudaError_t launch_rk_pair(const msed_handle *h, int method, int which, const KParams &p)
 {
@@ -613,8 +619,11 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     int depth = pred;
     double dt_acc = dt;
     long long nq = 1;
-    bool planned = fusable && single_attempt && !diag && rem >= 1 && !force_single &&
-                   plan_depth(dt, h->cfg.dt_min, depth, dt_acc, nq);
+    // (Runge-Kutta calls have no accept decision to plan: on a tile small enough for a warp per column they run as
+    //  chains of TU_RK_CHAIN_MAX_STEPS calls with the four stages on the column in registers, rk_chain_kernel)
+    const bool rk_chain = fusable && !single_attempt && chain_fit && !diag && rem >= 1;
+    bool planned = rk_chain || (fusable && single_attempt && !diag && rem >= 1 && !force_single &&
+                                plan_depth(dt, h->cfg.dt_min, depth, dt_acc, nq));
     const bool use_chain = planned && chain_fit;
     const int own_rejectable = (adaptive && dt_acc > h->cfg.dt_min) ? 1 : 0;
     fl.clear();
@@ -634,7 +643,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
     if (use_chain) {
         // chains cover every step of the round, whatever its parity; a launch holds at most
         // TU_CHAIN_MAX_STEPS accepted sub-steps
-        const long long per = std::max<long long>(1, TU_CHAIN_MAX_STEPS / nq);
+        const long long per = rk_chain ? TU_RK_CHAIN_MAX_STEPS : std::max<long long>(1, TU_CHAIN_MAX_STEPS / nq);
         const long long nl = (rem + per - 1) / per;
         const long long each = rem / nl, extra = rem % nl;   // the first `extra` chains hold one step more
         long long gate = 0;
@@ -644,7 +653,7 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
             f.step = (int)gate;
             f.pc = base_commit(gate);
             f.pc.steps = f.m;
-            f.pc.rhs_evals = f.m * (nq + depth);
+            f.pc.rhs_evals = rk_chain ? 4LL * f.m : f.m * (nq + depth);
             f.pc.subcycles = (long long)f.m * depth;
             f.pc.up_slots = f.m * depth;
             fl.push_back(f);
@@ -775,14 +784,16 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
                 KParams pc = pq;
                 pc.col0 = plan->c0[c];
                 pc.col_end = plan->c1[c];
-                CUDA_TRY(h, use_chain ? launch_chain(h, method, pc, m, wrapper_clip) : launch_pair(h, method, pc));
+                CUDA_TRY(h, rk_chain ? launch_rk_chain(h, method, pc, m, wrapper_clip)
+                                     : use_chain ? launch_chain(h, method, pc, m, wrapper_clip) : launch_pair(h, method, pc));
                 launches += 1;
                 if (chunk_last)
                     if ((rc = export_chunk(c))) return rc;
             }
             first_pending = false;
         } else {
-            CUDA_TRY(h, use_chain ? launch_chain(h, method, pq, m, wrapper_clip) : launch_pair(h, method, pq));
+            CUDA_TRY(h, rk_chain ? launch_rk_chain(h, method, pq, m, wrapper_clip)
+                                 : use_chain ? launch_chain(h, method, pq, m, wrapper_clip) : launch_pair(h, method, pq));
             launches += 1;
         }
         if (collective)

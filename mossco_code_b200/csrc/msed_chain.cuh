@@ -283,3 +283,188 @@ chain_kernel(const __grid_constant__ KParams p, const int nsub)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same for the Runge-Kutta integrators (solver_library.F90:142-185): nsub ode_solver calls per launch, the four
+// stages of every call evaluated on the column in registers -- the stage state, the base state and the accumulators
+// never leave the warp, where the thread-per-column path (rk_pair_kernel) moves them through HBM between its two
+// launches per call and, on a tile too small to fill the machine, walks every column serially.  Stage formulas and
+// their rounding are those of column_kernel's OP_RK4_* / OP_RK38_* stages, so a committed chain is bit-identical to
+// the staged path.  There is no accept decision: the launch is committed unless check_NaN (component :1718) fires.
+template <int MODEL, int METHOD, bool CLIP, int LPL = 1>
+__global__ void __launch_bounds__(CHAIN_BLOCK, 1)
+rk_chain_kernel(const __grid_constant__ KParams p, const int nsub)
+{
+    const Ctl *ctl = p.ctl;
+    if (ctl->stop || ctl->pairs_disabled || ctl->steps_done != p.gate_steps) return;
+    const int cur = ctl->cur;
+    const double dt = p.dt_acc;
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int col = p.col0 + blockIdx.x * CHAIN_WARPS + (threadIdx.x >> 5);
+    if (col >= p.col_end) return;  // warp-uniform from here on
+    if (p.mask[col] != 0) return;
+
+    const int K = p.K;
+    const bool top = lane == 0;
+    const size_t ld = p.ld;
+    const size_t plane = (size_t)K * ld;
+    bool active[LPL], has_next[LPL];
+    int k[LPL];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        const int kj = LPL * lane + j;
+        active[j] = kj < K;
+        k[j] = active[j] ? kj : K - 1;
+        has_next[j] = kj + 1 < K;
+    }
+    double cc[LPL][NV];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        const double *in = p.buf[cur] + (size_t)k[j] * ld + col;
+#pragma unroll
+        for (int n = 0; n < NV; ++n) cc[j][n] = in[(size_t)n * plane];
+    }
+    const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
+    const double temp = ld_ro(p.bdys + col);
+    double cpart, cdiss, fT;
+    column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
+    double fT_diag = fT;
+    if (MODEL != MSED_MODEL_OMEXDIA_P && p.denit_out)
+        fT_diag = exp(-p.om.E_a * (1.0 / (temp + 273.15) - 1.0 / 288.15));
+    double porc[LPL], porn[LPL], mDp[LPL], mDd[LPL], rpd[LPL];
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+        porc[j] = __dmul_rn(por_surf, p.portab[k[j]]);
+        porn[j] = mDp[j] = mDd[j] = 0.0;
+        if (has_next[j]) {
+            porn[j] = __dmul_rn(por_surf, p.portab[k[j] + 1]);
+            interface_coeffs(cpart, cdiss, porc[j], porn[j], p.bf[k[j] + 1], p.rdzc[k[j]], mDp[j], mDd[j]);
+        }
+        rpd[j] = fast_rcp(MSED_MUL(porc[j], p.dz[k[j]]));
+    }
+    const int bc_diss = p.bcup_diss;
+    const double por0 = __dmul_rn(por_surf, p.portab[0]);
+    double Dp0, Dd0;
+    top_coeffs(cpart, cdiss, por0, p.bf[0], Dp0, Dd0);
+    const double rdz0 = 1.0 / p.dz[0];
+    const double *top_part = p.fluxes + col;
+    const double *top_diss = (bc_diss == 2) ? p.bdys + ld + col : p.fluxes + col;
+    double tin[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) tin[n] = ld_ro((n < NPART ? top_part : top_diss) + (size_t)n * ld);
+
+    double Ftop[NV];       // Flux(1) of the last RHS evaluation (lane 0): sed%fluxes(dissolved), driver :692
+    double dn_last[LPL];   // FABM denit diagnostic of the last RHS evaluation
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) dn_last[j] = 0.0;
+    // get_rhs for the state x of this lane's layers
+    auto rhs_of = [&](const double (&x)[LPL][NV], double (&rhs)[LPL][NV], bool want_dn) __attribute__((always_inline)) {
+        double cn[NV];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) cn[n] = __shfl_down_sync(FULL, x[0][n], 1);
+        double r[LPL][NV], Fn[LPL][NV], F[NV];
+#pragma unroll
+        for (int j = 0; j < LPL; ++j) {
+            double dn = 0.0;
+            if (MODEL == MSED_MODEL_OMEXDIA_P) {
+                omexdia_rates(p.om, x[j], fT, r[j], &dn);
+            } else {
+                if (want_dn && p.denit_out) omexdia_rates(p.om, x[j], fT_diag, r[j], &dn);
+#pragma unroll
+                for (int n = 0; n < NV; ++n) r[j][n] = 0.0;
+            }
+            if (want_dn) dn_last[j] = dn;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double below = (j + 1 < LPL) ? x[j + 1 < LPL ? j + 1 : j][n] : cn[n];
+                const double f = (n < NPART) ? flux_particulate(mDp[j], below, porn[j], x[j][n], porc[j])
+                                             : flux_dissolved(mDd[j], below, x[j][n]);
+                Fn[j][n] = has_next[j] ? f : 0.0;
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NV; ++n) F[n] = __shfl_up_sync(FULL, Fn[LPL - 1][n], 1);
+#pragma unroll
+        for (int n = 0; n < NPART; ++n) F[n] = top ? tin[n] : F[n];
+        if (bc_diss == 2) {
+#pragma unroll
+            for (int n = NPART; n < NV; ++n) {
+                const double f = top_flux_dirichlet(Dd0, x[0][n], tin[n], rdz0);
+                F[n] = top ? f : F[n];
+            }
+        } else if (bc_diss == 1 || bc_diss == 4) {
+#pragma unroll
+            for (int n = NPART; n < NV; ++n) F[n] = top ? tin[n] : F[n];
+        } else {
+            const double f = (bc_diss == 3) ? 0.0 : tin[NPART - 1];
+#pragma unroll
+            for (int n = NPART; n < NV; ++n) F[n] = top ? f : F[n];
+        }
+#pragma unroll
+        for (int n = 0; n < NV; ++n) Ftop[n] = F[n];
+#pragma unroll
+        for (int j = 0; j < LPL; ++j) {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double fup = (j == 0) ? F[n] : Fn[j > 0 ? j - 1 : 0][n];
+                rhs[j][n] = layer_rhs(fup, Fn[j][n], rpd[j], r[j][n]);
+            }
+        }
+    };
+
+    bool nanf = false;
+    const double third = 1.0 / 3.0;
+#define MSED_RKC_ALL(stmt) _Pragma("unroll") for (int j = 0; j < LPL; ++j) _Pragma("unroll") for (int n = 0; n < NV; ++n) { stmt; }
+    for (int s = 0; s < nsub; ++s) {
+        const bool last = (s == nsub - 1);
+        double rhs[LPL][NV], base[LPL][NV], c1[LPL][NV], a1[LPL][NV];
+        MSED_RKC_ALL(base[j][n] = cc[j][n])
+        if (METHOD == MSED_RUNGE_KUTTA_4) {                              // column_kernel OP_RK4_S1..S4
+            rhs_of(cc, rhs, false);
+            MSED_RKC_ALL(c1[j][n] = fma(0.5 * dt, rhs[j][n], base[j][n]); a1[j][n] = 0.5 * rhs[j][n])
+            rhs_of(c1, rhs, false);
+            MSED_RKC_ALL(c1[j][n] = fma(0.5 * dt, rhs[j][n], base[j][n]); a1[j][n] = a1[j][n] + rhs[j][n])
+            rhs_of(c1, rhs, false);
+            MSED_RKC_ALL(c1[j][n] = fma(dt, rhs[j][n], base[j][n]); a1[j][n] = a1[j][n] + rhs[j][n])
+            rhs_of(c1, rhs, last);
+            MSED_RKC_ALL(cc[j][n] = fma(dt * third, fma(0.5, rhs[j][n], a1[j][n]), base[j][n]))
+        } else {                                                         // OP_RK38_S1..S4
+            double a2[LPL][NV];
+            rhs_of(cc, rhs, false);
+            MSED_RKC_ALL(c1[j][n] = fma(third * dt, rhs[j][n], base[j][n]); a1[j][n] = rhs[j][n])
+            rhs_of(c1, rhs, false);
+            MSED_RKC_ALL(const double r0 = a1[j][n]; c1[j][n] = fma(dt, fma(-third, r0, rhs[j][n]), base[j][n]);
+                         a1[j][n] = r0 - rhs[j][n]; a2[j][n] = fma(3.0, rhs[j][n], r0))
+            rhs_of(c1, rhs, false);
+            MSED_RKC_ALL(c1[j][n] = fma(dt, a1[j][n] + rhs[j][n], base[j][n]); a2[j][n] = fma(3.0, rhs[j][n], a2[j][n]))
+            rhs_of(c1, rhs, last);
+            MSED_RKC_ALL(cc[j][n] = fma(dt * 1.0 / 8.0, a2[j][n] + rhs[j][n], base[j][n]))
+        }
+        if (CLIP) {   // check_NaN on the new state, then the minimum clip (component :1718-1732)
+#pragma unroll
+            for (int j = 0; j < LPL; ++j)
+#pragma unroll
+                for (int n = 0; n < NV; ++n) {
+                    if (n & 1) nanf |= active[j] && either_nan(cc[j][n - 1], cc[j][n]);
+                }
+            MSED_RKC_ALL(cc[j][n] = clip_min(cc[j][n], p.om.minimum[n]))
+        }
+    }
+#undef MSED_RKC_ALL
+
+#pragma unroll
+    for (int j = 0; j < LPL; ++j)
+        if (active[j]) {
+            double *out = p.buf[1 - cur] + (size_t)k[j] * ld + col;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) out[(size_t)n * plane] = cc[j][n];
+            if (p.denit_out) p.denit_out[(size_t)k[j] * ld + col] = dn_last[j];
+        }
+    if (top && nsub > 0) {
+#pragma unroll
+        for (int n = NPART; n < NV; ++n) p.fluxes[(size_t)n * ld + col] = Ftop[n];   // :692
+    }
+    const bool any_nan = __any_sync(FULL, nanf);
+    if (top && any_nan) atomicOr(&p.ctl->flags[1], 1);
+}

@@ -17,6 +17,9 @@ cudaError_t tu_enable_pair_smem();
 
 // chain_kernel (msed_chain.cuh): nsteps ode_solver calls per launch, warp per column, knum <= 64
 cudaError_t tu_launch_chain(int model, bool adaptive, bool clip, const KParams &p, int nsteps, cudaStream_t s);
+// rk_chain_kernel (msed_chain.cuh): the same for RK4 / RK4-3/8, four stages per call on the column in registers
+cudaError_t tu_launch_rk_chain(int model, int method, bool clip, const KParams &p, int m, cudaStream_t s);
+constexpr int TU_RK_CHAIN_MAX_STEPS = 4;  // ode_solver calls per launch (16 RHS evaluations, as an Euler chain)
 constexpr int TU_CHAIN_MAX_LAYERS = 64;   // one layer per lane up to 32, two above
 constexpr int TU_SPINUP_MAX_LAYERS = 64;  // spinup_kernel: one layer per lane up to 32, two above
 constexpr int TU_CHAIN_MAX_STEPS = 16;   // steps per launch: bounds the work a failed speculation throws away

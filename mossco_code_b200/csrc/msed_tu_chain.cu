@@ -33,4 +33,26 @@ cudaError_t tu_launch_chain(int model, bool adaptive, bool clip, const KParams &
     return cudaGetLastError();
 }
 
+cudaError_t tu_launch_rk_chain(int model, int method, bool clip, const KParams &p, int m, cudaStream_t s)
+{
+    if (p.col_end <= p.col0) return cudaSuccess;
+    const dim3 grid((p.col_end - p.col0 + CHAIN_WARPS - 1) / CHAIN_WARPS), block(CHAIN_BLOCK);
+    const bool two = p.K > 32;
+#define MSED_RKC(MODEL, METH, CL)                                                          \
+    do {                                                                                   \
+        if (two) rk_chain_kernel<MODEL, METH, CL, 2><<<grid, block, 0, s>>>(p, m);         \
+        else rk_chain_kernel<MODEL, METH, CL, 1><<<grid, block, 0, s>>>(p, m);             \
+    } while (0)
+#define MSED_RKC_M(MODEL)                                                                  \
+    do {                                                                                   \
+        if (method == MSED_RUNGE_KUTTA_4) { if (clip) MSED_RKC(MODEL, MSED_RUNGE_KUTTA_4, true); else MSED_RKC(MODEL, MSED_RUNGE_KUTTA_4, false); } \
+        else { if (clip) MSED_RKC(MODEL, MSED_RUNGE_KUTTA_4_38, true); else MSED_RKC(MODEL, MSED_RUNGE_KUTTA_4_38, false); } \
+    } while (0)
+    if (model == MSED_MODEL_OMEXDIA_P) MSED_RKC_M(MSED_MODEL_OMEXDIA_P);
+    else MSED_RKC_M(MSED_MODEL_NONE);
+#undef MSED_RKC_M
+#undef MSED_RKC
+    return cudaGetLastError();
+}
+
 }  // namespace msed

@@ -225,13 +225,18 @@ def test_fusion_stream_porosity_uses_single_steps(gpu):
 
 # ---- Runge-Kutta stage pairs (msed_rkpair.cuh) --------------------------------------------------------
 @pytest.mark.parametrize("method", [1, 3])
-@pytest.mark.parametrize("knum", [2, 3, 4, 20])
-def test_rk_stage_fusion_is_bit_identical(gpu, oracle, method, knum):
+@pytest.mark.parametrize("knum", [2, 3, 4, 20, 40])
+@pytest.mark.parametrize("mode", MODES)
+def test_rk_stage_fusion_is_bit_identical(gpu, oracle, method, knum, mode):
+    """Runge-Kutta calls fused two stages per launch (mode pairs: rk_pair_kernel, thread per column) or four stages
+    and several calls per launch with the column in registers (mode chains: rk_chain_kernel, warp per column)."""
     case = make_case("rkf", 37, 21, knum, 0.003, seed=55 + knum, land_fraction=0.2, smooth_temperature=True)
-    on = _run(case, True, method, 5, calls=2)
+    on = _run(case, mode, method, 5, calls=2)
     off = _run(case, False, method, 5, calls=2)
     _same(on, off)
-    assert on["launches"] < off["launches"]                 # two launches per step instead of four
+    assert on["launches"] < off["launches"]                 # two launches per step, or one per four steps, instead of four
+    if mode == "chains":
+        assert on["launches"] < _run(case, "pairs", method, 5, calls=2)["launches"]
     ref = oracle.OracleSediment(37, 21, knum, 0.003, mask2d=case.mask, dt_min=1.0)
     ref.init_concentrations(); ref.set_boundary(case.bdys, case.fluxes)
     assert ref.step(DT, method, 10) == 0
@@ -243,7 +248,8 @@ def test_rk_stage_fusion_is_bit_identical(gpu, oracle, method, knum):
 @pytest.mark.parametrize("kw", [dict(bcup_dissolved_variables=1), dict(bioturbation_profile=2),
                                 dict(bcup_dissolved_variables=0),
                                 dict(minimum=[1., 2., 3., 0.5, 30., 1., 2., 150.]), dict(model=1)])
-def test_rk_stage_fusion_variants(gpu, method, kw):
+@pytest.mark.parametrize("mode", MODES)
+def test_rk_stage_fusion_variants(gpu, method, kw, mode):
     case = make_case("rkfv", 19, 9, 15, 0.004, seed=9)
 
     def mutate(sed):
@@ -252,14 +258,15 @@ def test_rk_stage_fusion_variants(gpu, method, kw):
             sed.set_boundary(None, fl)
         sed.update_porosity(0.5 + 0.3 * np.random.default_rng(2).random((19, 9)))   # porosity mode 2
 
-    _same(_run(case, True, method, 6, mutate=mutate, **kw), _run(case, False, method, 6, mutate=mutate, **kw))
+    _same(_run(case, mode, method, 6, mutate=mutate, **kw), _run(case, False, method, 6, mutate=mutate, **kw))
 
 
 @pytest.mark.parametrize("method", [1, 3])
-def test_rk_stage_fusion_nan_stops_at_the_same_step(gpu, method):
+@pytest.mark.parametrize("mode", MODES)
+def test_rk_stage_fusion_nan_stops_at_the_same_step(gpu, method, mode):
     case = make_case("rkfn", 12, 8, 15, 0.004, seed=3)
     kw = dict(rnit=5.0e5, rODUox=5.0e5)                     # explicit RK blows up within a few steps
-    on = _run(case, True, method, 40, **kw)
+    on = _run(case, mode, method, 40, **kw)
     off = _run(case, False, method, 40, **kw)
     assert on["rc"] == off["rc"] and on["done"] == off["done"]
     assert np.array_equal(on["conc"], off["conc"], equal_nan=True)
