@@ -227,6 +227,11 @@ int msed_set_import_generations(msed_handle *h, const uint64_t *gen);
  * 2 pairs only, 3 chains wherever knum allows.  Mode 1 picks chains for tiles of up to 65536 wet columns
  * (environment MSED_CHAIN_MAX_COLS; a fifth of that above 32 layers), where a thread per column cannot fill the GPU. */
 int msed_set_step_fusion(msed_handle *h, int mode);
+/* Runge-Kutta calls (solver_library.F90:142-185) on tiles too large for chains: stages per launch with a thread per
+ * column -- 4 (default: the whole call in one pass over the state, rk_quad_kernel; needs knum >= 5, otherwise 2 is
+ * used) or 2 (stages 1+2 and 3+4, seven state passes per call, rk_pair_kernel).  Environment MSED_RK_STAGES.
+ * Bit-identical results either way, and to the staged path (step fusion off). */
+int msed_set_rk_stages_per_launch(msed_handle *h, int stages);
 /* number of column chunks msed_run_exchange uses (0 = choose from the tile size: 1 to 8, always the
  * asynchronous sequence; 1 = the plain sequence of the three separate calls, no overlap) */
 int msed_set_exchange_chunks(msed_handle *h, int nchunks);

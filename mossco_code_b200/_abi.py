@@ -160,6 +160,7 @@ SYMBOLS = {
                                     _dp, C.POINTER(StepInfo)]),
     "msed_set_exchange_chunks": (C.c_int, [_h, C.c_int]),
     "msed_set_exchange_order": (C.c_int, [_h, C.c_int]),
+    "msed_set_rk_stages_per_launch": (C.c_int, [_h, C.c_int]),
     "msed_set_step_fusion": (C.c_int, [_h, C.c_int]),
     "msed_spinup_column": (C.c_int, [C.POINTER(Config), _dp, _dp, C.c_int64, C.c_int, _dp,
                                      C.POINTER(StepInfo)]),

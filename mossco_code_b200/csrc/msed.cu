@@ -115,6 +115,7 @@ struct msed_handle {
     int step_fusion = 1;                          // 0 off, 1 auto (chains where they apply, else pairs),
                                                   // 2 pairs only, 3 chains wherever knum allows
     long long chain_max_cols = 0;                 // auto mode: tiles up to this many columns take chain_kernel
+    int rk_stages = 4;                            // Runge-Kutta, thread per column: stages per launch (4: rk_quad_kernel, 2: rk_pair_kernel)
     double *xstage = nullptr;                     // [20][ld] staging rows of msed_run_exchange when the staging buffer
                                                   // itself serves as third state buffer (chunk-major Run)
     int chunk_major = 1;                          // msed_run_exchange: whole coupling interval chunk by chunk
@@ -366,6 +367,11 @@ cudaError_t launch_rk_chain(const msed_handle *h, int method, const KParams &p, 
 }
 
 // one launch = two chained Runge-Kutta stages (msed_rkpair.cuh); which = 0 for stages 1+2, 1 for 3+4
+cudaError_t launch_rk_quad(const msed_handle *h, int method, const KParams &p)
+{
+    return tu_launch_rk_quad(h->cfg.model, method, p, h->stream);
+}
+
 cudaError_t launch_rk_pair(const msed_handle *h, int method, int which, const KParams &p)
 {
     return tu_launch_rk_pair(h->cfg.model, method, which, p, h->stream);
@@ -374,7 +380,8 @@ cudaError_t launch_rk_pair(const msed_handle *h, int method, int which, const KP
 cudaError_t enable_pair_smem()
 {
     cudaError_t e = tu_enable_pair_smem();
-    return e != cudaSuccess ? e : tu_enable_rk_smem();
+    if (e == cudaSuccess) e = tu_enable_rk_smem();
+    return e != cudaSuccess ? e : tu_enable_rk_quad_smem();
 }
 
 // nflags: 4 (violation / NaN of up to two stages) or, for a group that plans rejections, all of Ctl::flags
@@ -850,6 +857,9 @@ int run_steps(msed_handle *h, double dt, int method, long long nsteps, bool wrap
             } else if (method == MSED_ADAPTIVE_EULER) {
                 CUDA_TRY(h, launch_column(h, OP_ADAPTIVE, p));
                 launches += 1;
+            } else if (rk_fused && h->rk_stages == 4 && h->K >= TU_RK_QUAD_MIN_LAYERS) {
+                CUDA_TRY(h, launch_rk_quad(h, method, p));   // the whole call in one pass (msed_rkquad.cuh)
+                launches += 1;
             } else if (rk_fused) {
                 CUDA_TRY(h, launch_rk_pair(h, method, 0, p));
                 CUDA_TRY(h, launch_rk_pair(h, method, 1, p));
@@ -1142,6 +1152,7 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     h->chain_max_cols = 65536;
     if (const char *e = std::getenv("MSED_CHAIN_MAX_COLS")) h->chain_max_cols = std::atoll(e);
     if (const char *e = std::getenv("MSED_EXCHANGE_CHUNK_MAJOR")) h->chunk_major = std::atoi(e) != 0;
+    if (const char *e = std::getenv("MSED_RK_STAGES")) h->rk_stages = std::atoi(e) == 2 ? 2 : 4;
     if (const char *e = std::getenv("MSED_STEP_FUSION")) {  // initial msed_set_step_fusion mode (0..3)
         const int mode = std::atoi(e);
         if (mode >= 0 && mode <= 3) h->step_fusion = mode;
@@ -1627,6 +1638,14 @@ int msed_set_step_fusion(msed_handle *h, int enable)
     h->step_fusion = enable;
     h->pred_depth = 0;
     h->regime_depth = 0;
+    return MSED_OK;
+}
+
+int msed_set_rk_stages_per_launch(msed_handle *h, int stages)
+{
+    if (!h) return MSED_ERR_ARG;
+    if (stages != 2 && stages != 4) return fail(h, MSED_ERR_ARG, "Runge-Kutta stages per launch must be 2 or 4");
+    h->rk_stages = stages;
     return MSED_OK;
 }
 

@@ -28,6 +28,11 @@ constexpr int TU_CHAIN_MAX_STEPS = 16;   // steps per launch: bounds the work a 
 cudaError_t tu_launch_rk_pair(int model, int method, int which, const KParams &p, cudaStream_t s);
 cudaError_t tu_enable_rk_smem();
 
+// rk_quad_kernel (msed_rkquad.cuh): the four stages of a Runge-Kutta call in one launch, thread per column
+cudaError_t tu_launch_rk_quad(int model, int method, const KParams &p, cudaStream_t s);
+cudaError_t tu_enable_rk_quad_smem();
+constexpr int TU_RK_QUAD_MIN_LAYERS = 5;
+
 // spinup_kernel (msed_spinup.cuh): the 1-D pre-simulation of a batch of members, warp per member, knum <= 64
 cudaError_t tu_launch_spinup(int model, const KParams &p, const SpinupArgs &a, cudaStream_t s);
 

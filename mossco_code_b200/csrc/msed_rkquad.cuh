@@ -1,0 +1,316 @@
+// msed_rkquad.cuh -- included inside namespace msed after msed_pair.cuh.
+//
+// All four stages of a Runge-Kutta call (solver_library.F90:142-185) in ONE pass over HBM, thread per column.
+//
+// rk_pair_kernel chains the stages two by two and an RK4 call costs seven state passes; on a tile too large for
+// a warp per column (rk_chain_kernel) those two launches run at the HBM roofline of the bytes they move and the
+// fp64 pipe idles.  Here the one-layer-lag chaining of pair_kernel is taken to four stages: in iteration k of
+// the walk down the column
+//     stage 1 evaluates layer k   of the state c               (read from the input ring),
+//     stage 2 evaluates layer k-1 of  c + a21 dt k1            (link slot 2 + stage 1's fresh layer k),
+//     stage 3 evaluates layer k-2 of the third stage state     (link slot 3 + stage 2's fresh layer k-1),
+//     stage 4 evaluates layer k-3 of the fourth stage state    (link slot 4 + stage 3's fresh layer k-2)
+//             and stores the new state of layer k-3 -- in place: the ring has long fetched that layer.
+// A stage hands the layer it has just produced to the next stage in registers (as that stage's "layer below")
+// and through a one-layer link slot in shared memory (as the next iteration's "current layer"); the weighted
+// sums of the k_i travel in registers from stage to stage, one iteration at a time; the base state of stages
+// 2-4 is still in the input ring (8 slots: layers k-3 .. k+1 in use, k+2 .. k+4 in flight).  The state is read
+// once and written once per CALL (2 passes instead of 7), nothing else touches HBM.
+//
+// The stage formulas and the inline arithmetic are those of rk_pair_kernel / the staged column_kernel ops, so
+// the three paths give bit-identical results (tests/test_gpu_fusion.py).  Same scope as rk_pair_kernel (no
+// distributed POM flux cascade, profile != 3, closed-form porosity), and knum >= 5 (the peeled head and tail
+// of the walk); anything else stays with the stage pairs.
+//
+// Shared memory: (8 ring + 3 link) layers x 8 variables x 128 columns x 8 B = 88 KB per CTA, two CTAs per SM,
+// 255 registers per thread: eight warps per SM, each with four independent RHS evaluations in flight.
+
+constexpr int RKQ_RING = 8;                                   // input ring slots (power of two)
+constexpr uint32_t RKQ_STAGE_B = NV * ROW_BYTES;              // one layer of one CTA
+constexpr size_t RKQ_SMEM_BYTES = (size_t)(RKQ_RING + 3) * RKQ_STAGE_B;
+constexpr int RKQ_MIN_LAYERS = 5;
+
+#ifndef MSED_RKQUAD_MIN_BLOCKS
+#define MSED_RKQUAD_MIN_BLOCKS 2
+#endif
+
+template <int MODEL, bool IS38>
+__global__ void __launch_bounds__(COL_BLOCK, MSED_RKQUAD_MIN_BLOCKS)
+rk_quad_kernel(const __grid_constant__ KParams p)
+{
+    extern __shared__ __align__(16) double ring[];
+    const Ctl *ctl = p.ctl;
+    if (ctl->stop || ctl->steps_done >= ctl->steps_target) return;
+    const int cur = ctl->cur;
+    const bool do_clip = ctl->do_clip != 0;
+    const double dt = ctl->dt;
+    const double third = 1.0 / 3.0;
+    // the FABM diagnostics (msed_get_field) describe the last get_rhs call, i.e. the stage-4 input state: the last
+    // call of a sequence stores it where the staged path leaves it (the spare buffer)
+    const bool keep_c1 = ctl->steps_done + 1 >= ctl->steps_target;
+
+    const int col = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
+    if (col >= p.col_end) return;
+    if (p.mask[col] != 0) return;
+
+    const int K = p.K;
+    const size_t ld = p.ld;
+    const size_t plane = (size_t)K * ld;
+    double *conc = p.buf[cur] + col;          // read through the ring, rewritten three layers behind
+    double *g_c1 = p.buf[1 - cur] + col;      // keep_c1 only
+    double *g_out = conc;
+
+    const uint32_t sbase = smem_u32(ring) + threadIdx.x * 8u;
+    const uint32_t lk2 = sbase + RKQ_RING * RKQ_STAGE_B, lk3 = lk2 + RKQ_STAGE_B, lk4 = lk3 + RKQ_STAGE_B;
+    auto slot = [&](int L) __attribute__((always_inline)) -> uint32_t {
+        return sbase + (uint32_t)(L & (RKQ_RING - 1)) * RKQ_STAGE_B;
+    };
+    const double *g_in = conc;
+    int k_fetch = 0;
+    auto fetch_next = [&]() __attribute__((always_inline)) {
+        if (k_fetch < K) {
+            const uint32_t sa = slot(k_fetch);
+            const double *g = g_in;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                cp_async8(sa + n * ROW_BYTES, g);
+                g += plane;
+            }
+            g_in += ld;
+        }
+        ++k_fetch;
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < RKQ_RING - 4; ++s) fetch_next();      // layers 0 .. 3
+
+    const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
+    auto por_at = [&](int kk) __attribute__((always_inline)) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
+    const double temp = ld_ro(p.bdys + col);
+    double cpart, cdiss, fT;
+    column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
+
+    // upper boundary of one stage: F[n] = Flux(1) (diff3d :782-803) from the stage's own layer-1 state
+    auto top_boundary = [&](const double (&c0)[NV], double (&F)[NV], bool write_fluxes) __attribute__((always_inline)) {
+        double Dp, Dd;
+        const double por0 = por_at(0);
+        top_coeffs(cpart, cdiss, por0, p.bf[0], Dp, Dd);
+        const double rdz0 = 1.0 / p.dz[0];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const bool part = n < NPART;
+            const int bc = part ? p.bcup_part : p.bcup_diss;
+            double f = 0.0;
+            if (bc == 1 || bc == 4) {
+                f = ld_ro(p.fluxes + (size_t)n * ld + col);
+            } else if (bc == 2) {
+                const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
+                const double C1 = part ? MSED_MUL(c0[n], por0) : c0[n];
+                f = top_flux_dirichlet(part ? Dp : Dd, C1, Cup, rdz0);
+            } else if (bc != 3 && n > 0) {
+                f = F[n - 1];
+            }
+            F[n] = f;
+            if (write_fluxes && !part) p.fluxes[(size_t)n * ld + col] = f;  // driver :692
+        }
+    };
+
+    // state-independent coefficients of a layer and of its lower interface (every stage needs the same ones, one
+    // iteration after the other): -D/dzc of the interface for particulates / solutes, 1/(porosity*dz)
+    struct LayerCoef { double mDp, mDd, rpd; };
+    auto make_coef = [&](auto has_next_tag, int kk, double porc, double porn) __attribute__((always_inline)) -> LayerCoef {
+        LayerCoef lc;
+        lc.mDp = lc.mDd = 0.0;
+        if (decltype(has_next_tag)::value)
+            interface_coeffs(cpart, cdiss, porc, porn, p.bf[kk + 1], p.rdzc[kk], lc.mDp, lc.mDd);
+        lc.rpd = fast_rcp(MSED_MUL(porc, p.dz[kk]));
+        return lc;
+    };
+    // right-hand side of one layer (the inline arithmetic of column_kernel)
+    auto layer_rates = [&](auto has_next_tag, const LayerCoef &lc, double porc, double porn, const double (&cc)[NV],
+                           const double (&cn)[NV], double (&F)[NV], double (&rhs)[NV]) __attribute__((always_inline)) {
+        double Fn[NV];
+        if (decltype(has_next_tag)::value) {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                if (n < NPART) Fn[n] = flux_particulate(lc.mDp, cn[n], porn, cc[n], porc);
+                else Fn[n] = flux_dissolved(lc.mDd, cn[n], cc[n]);
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) Fn[n] = 0.0;
+        }
+        double r[NV];
+        if (MODEL == MSED_MODEL_OMEXDIA_P) {
+            omexdia_rates(p.om, cc, fT, r, nullptr);
+        } else {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) r[n] = 0.0;
+        }
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            rhs[n] = layer_rhs(F[n], Fn[n], lc.rpd, r[n]);
+            F[n] = Fn[n];
+        }
+    };
+
+    // ---- what travels from iteration to iteration in registers ---------------------------------------------
+    double F1[NV], F2[NV], F3[NV], F4[NV];     // flux through the upper interface of each stage's next layer
+    // weighted sums of the k_i, handed from stage to stage (the layer a stage finishes in iteration k is the
+    // next stage's layer in iteration k+1):
+    //   RK4   x12 = 0.5 k1      x23 = 0.5 k1 + k2             x34 = x23 + k3                (:147-160)
+    //   RK38  x12 = k1          x23 = P = k1 - k2, x23b = Q = k1 + 3 k2     x34 = Q + 3 k3  (:169-182)
+    // Each is consumed by its stage before the stage in front of it writes the next layer's value into the same
+    // registers (the updates sit at the end of the iteration, last stage first): no copies.
+    double x12[NV], x23[NV], x23b[NV], x34[NV];
+    LayerCoef cf2, cf3, cf4;                   // coefficients of the layers stages 2-4 are about to evaluate
+    double pm3 = 0.0, pm2 = 0.0, pm1 = 0.0, pk = por_at(0), pk1 = por_at(1);   // porosity of layers k-3 .. k+1
+#pragma unroll
+    for (int n = 0; n < NV; ++n) F1[n] = F2[n] = F3[n] = F4[n] = x12[n] = x23[n] = x23b[n] = x34[n] = 0.0;
+    cf2.mDp = cf2.mDd = cf2.rpd = 0.0;
+    cf3 = cf2;
+    cf4 = cf2;
+    bool nanf = false;
+
+    // One iteration of the walk.  Mk: what stage k does in it -- 0 nothing, 1 the first layer of the column (upper
+    // boundary first), 2 an inner layer, 3 the last layer (closed bottom).  Stage s works on layer k - (s-1).
+    auto iteration = [&](auto m1, auto m2, auto m3, auto m4, int k) __attribute__((always_inline)) {
+        constexpr int M1 = decltype(m1)::value, M2 = decltype(m2)::value, M3 = decltype(m3)::value, M4 = decltype(m4)::value;
+        using Y = std::true_type;
+        using N = std::false_type;
+        // the link slots hold what the previous iteration produced: read them before this iteration's results
+        // take their place
+        double c2[NV], c3[NV], c4[NV];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            if (M2) c2[n] = lds64(lk2 + n * ROW_BYTES);
+            if (M3) c3[n] = lds64(lk3 + n * ROW_BYTES);
+            if (M4) c4[n] = lds64(lk4 + n * ROW_BYTES);
+        }
+        double y2n[NV], y3n[NV], y4n[NV];      // the layer stages 1-3 produce in this iteration
+        double rhs1[NV], rhs2[NV], rhs3[NV];
+        LayerCoef cf1n = cf2;
+        if (M1) {                              // ---- stage 1, layer k: k1 = f(c) ------------------------------
+            fetch_next();                      // layer k+4 into the slot layer k-4 has left
+            cp_async_wait<RKQ_RING - 5>();     // layer k+1 has landed
+            const uint32_t sc = slot(k), sn = slot(k + 1);
+            double cc[NV], cn[NV];
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                cc[n] = lds64(sc + n * ROW_BYTES);
+                cn[n] = (M1 != 3) ? lds64(sn + n * ROW_BYTES) : 0.0;
+            }
+            if (M1 == 1) top_boundary(cc, F1, false);
+            if (M1 != 3) { cf1n = make_coef(Y{}, k, pk, pk1); layer_rates(Y{}, cf1n, pk, pk1, cc, cn, F1, rhs1); }
+            else         { cf1n = make_coef(N{}, k, pk, pk1); layer_rates(N{}, cf1n, pk, pk1, cc, cn, F1, rhs1); }
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                if (!IS38) y2n[n] = fma(0.5 * dt, rhs1[n], cc[n]);      // :147  c1 = c + 0.5*dt*k1
+                else       y2n[n] = fma(third * dt, rhs1[n], cc[n]);    // :169  c1 = c + third*dt*k1
+                sts64(lk2 + n * ROW_BYTES, y2n[n]);
+            }
+        }
+        if (M2) {                              // ---- stage 2, layer k-1: k2 = f(c1) ---------------------------
+            const uint32_t sb = slot(k - 1);
+            if (M2 == 1) top_boundary(c2, F2, false);
+            if (M2 != 3) layer_rates(Y{}, cf2, pm1, pk, c2, y2n, F2, rhs2);
+            else         layer_rates(N{}, cf2, pm1, pk, c2, c2, F2, rhs2);
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double base = lds64(sb + n * ROW_BYTES);
+                if (!IS38) y3n[n] = fma(0.5 * dt, rhs2[n], base);                        // :152  c1 = c + 0.5*dt*k2
+                else       y3n[n] = fma(dt, fma(-third, x12[n], rhs2[n]), base);         // :174  c1 = c + dt*(k2 - third*k1)
+                sts64(lk3 + n * ROW_BYTES, y3n[n]);
+            }
+        }
+        if (M3) {                              // ---- stage 3, layer k-2: k3 = f(c1) ---------------------------
+            const uint32_t sb = slot(k - 2);
+            if (M3 == 1) top_boundary(c3, F3, false);
+            if (M3 != 3) layer_rates(Y{}, cf3, pm2, pm1, c3, y3n, F3, rhs3);
+            else         layer_rates(N{}, cf3, pm2, pm1, c3, c3, F3, rhs3);
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double base = lds64(sb + n * ROW_BYTES);
+                if (!IS38) y4n[n] = fma(dt, rhs3[n], base);                              // :156  c1 = c + dt*k3
+                else       y4n[n] = fma(dt, MSED_ADD(x23[n], rhs3[n]), base);            // :178  c1 = c + dt*(P + k3)
+                sts64(lk4 + n * ROW_BYTES, y4n[n]);
+            }
+            if (keep_c1) {
+#pragma unroll
+                for (int n = 0; n < NV; ++n) g_c1[(size_t)n * plane] = y4n[n];
+            }
+            g_c1 += ld;
+        }
+        if (M4) {                              // ---- stage 4, layer k-3: k4 = f(c1), the new state ------------
+            const uint32_t sb = slot(k - 3);
+            double rhs[NV], raw[NV];
+            if (M4 == 1) top_boundary(c4, F4, true);
+            if (M4 != 3) layer_rates(Y{}, cf4, pm3, pm2, c4, y4n, F4, rhs);
+            else         layer_rates(N{}, cf4, pm3, pm2, c4, c4, F4, rhs);
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const double base = lds64(sb + n * ROW_BYTES);
+                if (!IS38) raw[n] = fma(dt * third, fma(0.5, rhs[n], x34[n]), base);       // :160
+                else       raw[n] = fma(dt * 1.0 / 8.0, MSED_ADD(x34[n], rhs[n]), base);   // :182
+            }
+            if (do_clip) {                     // check_NaN + clip (component :1718-1732)
+#pragma unroll
+                for (int n = 0; n < NV; ++n) {
+                    if (n & 1) nanf |= either_nan(raw[n - 1], raw[n]);
+                    raw[n] = clip_min(raw[n], p.om.minimum[n]);
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < NV; ++n) g_out[(size_t)n * plane] = raw[n];
+            g_out += ld;
+        }
+        // hand-over to the next iteration, last stage first (see x12 .. x34 above)
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            if (!IS38) {
+                if (M3) x34[n] = MSED_ADD(x23[n], rhs3[n]);            // :156  acc += k3
+                if (M2) x23[n] = MSED_ADD(x12[n], rhs2[n]);            // :152  acc = 0.5*k1 + k2
+                if (M1) x12[n] = MSED_MUL(0.5, rhs1[n]);               // :147  acc = 0.5*k1
+            } else {
+                if (M3) x34[n] = fma(3.0, rhs3[n], x23b[n]);           // :178  Q += 3*k3
+                if (M2) {                                              // :174  P = k1-k2 ; Q = k1+3*k2
+                    x23[n] = MSED_SUB(x12[n], rhs2[n]);
+                    x23b[n] = fma(3.0, rhs2[n], x12[n]);
+                }
+                if (M1) x12[n] = rhs1[n];
+            }
+        }
+        cf4 = cf3;
+        cf3 = cf2;
+        if (M1) cf2 = cf1n;
+        pm3 = pm2;
+        pm2 = pm1;
+        pm1 = pk;
+        pk = pk1;
+        if (M1 == 1 || M1 == 2) pk1 = (k + 2 < K) ? por_at(k + 2) : 0.0;
+    };
+
+    {
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
+        using I3 = std::integral_constant<int, 3>;
+        iteration(I1{}, I0{}, I0{}, I0{}, 0);
+        iteration(I2{}, I1{}, I0{}, I0{}, 1);
+        iteration(I2{}, I2{}, I1{}, I0{}, 2);
+        iteration(I2{}, I2{}, I2{}, I1{}, 3);
+#ifdef MSED_RKQUAD_UNROLL
+        MSED_UNROLL_PRAGMA(MSED_RKQUAD_UNROLL)
+#else
+#pragma unroll 1
+#endif
+        for (int k = 4; k < K - 1; ++k) iteration(I2{}, I2{}, I2{}, I2{}, k);   // steady state
+        iteration(I3{}, I2{}, I2{}, I2{}, K - 1);
+        iteration(I0{}, I3{}, I2{}, I2{}, K);
+        iteration(I0{}, I0{}, I3{}, I2{}, K + 1);
+        iteration(I0{}, I0{}, I0{}, I3{}, K + 2);
+    }
+    cp_async_wait<0>();
+
+    if (nanf) atomicOr(&p.ctl->flags[1], 1);
+}

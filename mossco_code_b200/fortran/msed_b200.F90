@@ -199,6 +199,10 @@ module msed_b200
     integer(c_int) function msed_set_exchange_order(h, chunk_major) bind(c, name='msed_set_exchange_order')
       import; type(c_ptr), value :: h; integer(c_int), value :: chunk_major
     end function
+    !> Runge-Kutta calls with a thread per column: 4 stages per launch (default) or 2
+    integer(c_int) function msed_set_rk_stages_per_launch(h, stages) bind(c, name='msed_set_rk_stages_per_launch')
+      import; type(c_ptr), value :: h; integer(c_int), value :: stages
+    end function
     !> 1-D pre-simulation, fabm_sediment_component.F90:557-632
     integer(c_int) function msed_spinup_column(cfg, bdys1d, fluxes1d, nsteps, method, conc1d, info) &
         bind(c, name='msed_spinup_column')

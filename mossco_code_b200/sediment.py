@@ -318,6 +318,11 @@ class SedimentDriver:
             mode = self.FUSION_MODES[mode]
         self._check(self._lib.msed_set_step_fusion(self._h, int(mode)))
 
+    def set_rk_stages_per_launch(self, stages: int):
+        """Runge-Kutta calls with a thread per column: 4 stages per launch (one pass over the state per call,
+        the default for knum >= 5) or 2 (stage pairs).  Bit-identical results."""
+        self._check(self._lib.msed_set_rk_stages_per_launch(self._h, int(stages)))
+
     def set_exchange_chunks(self, nchunks: int):
         self._check(self._lib.msed_set_exchange_chunks(self._h, int(nchunks)))
 

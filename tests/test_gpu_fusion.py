@@ -12,12 +12,17 @@ DT = 360.0
 
 
 def _run(case, fusion, method, nsteps, calls=1, mutate=None, **cfgkw):
+    # Runge-Kutta with a thread per column: "quad" = four stages per launch (rk_quad_kernel), "pairs" = two
+    rk_stages = 4 if fusion == "quad" else 2
+    if fusion == "quad":
+        fusion = "pairs"
     from mossco_code_b200 import SedimentDriver, default_config
     kw = dict(inum=case.inum, jnum=case.jnum, knum=case.knum, dzmin=case.dzmin, dt_min=1.0)
     kw.update(cfgkw)
     cfg = default_config(**kw)
     with SedimentDriver(cfg) as sed:
         sed.set_step_fusion(fusion)
+        sed.set_rk_stages_per_launch(rk_stages)
         sed.set_mask(case.mask)
         sed.init_concentrations()
         sed.set_boundary(case.bdys, case.fluxes)
@@ -223,19 +228,24 @@ def test_fusion_stream_porosity_uses_single_steps(gpu):
     assert on["launches"] == off["launches"]
 
 
-# ---- Runge-Kutta stage pairs (msed_rkpair.cuh) --------------------------------------------------------
+# ---- Runge-Kutta stages fused (msed_rkpair.cuh, msed_rkquad.cuh, msed_chain.cuh) ------------------------
+RK_MODES = ["pairs", "quad", "chains"]
+
+
 @pytest.mark.parametrize("method", [1, 3])
-@pytest.mark.parametrize("knum", [2, 3, 4, 20, 40])
-@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("knum", [2, 3, 4, 5, 6, 7, 20, 40])
+@pytest.mark.parametrize("mode", RK_MODES)
 def test_rk_stage_fusion_is_bit_identical(gpu, oracle, method, knum, mode):
-    """Runge-Kutta calls fused two stages per launch (mode pairs: rk_pair_kernel, thread per column) or four stages
-    and several calls per launch with the column in registers (mode chains: rk_chain_kernel, warp per column)."""
+    """Runge-Kutta calls fused two stages per launch (mode pairs: rk_pair_kernel, thread per column), four stages per
+    launch (mode quad: rk_quad_kernel, thread per column, one pass over the state per call; knum < 5 falls back to
+    pairs) or four stages and several calls per launch with the column in registers (mode chains: rk_chain_kernel,
+    warp per column)."""
     case = make_case("rkf", 37, 21, knum, 0.003, seed=55 + knum, land_fraction=0.2, smooth_temperature=True)
     on = _run(case, mode, method, 5, calls=2)
     off = _run(case, False, method, 5, calls=2)
     _same(on, off)
     assert on["launches"] < off["launches"]                 # two launches per step, or one per four steps, instead of four
-    if mode == "chains":
+    if mode == "chains" or (mode == "quad" and knum >= 5):
         assert on["launches"] < _run(case, "pairs", method, 5, calls=2)["launches"]
     ref = oracle.OracleSediment(37, 21, knum, 0.003, mask2d=case.mask, dt_min=1.0)
     ref.init_concentrations(); ref.set_boundary(case.bdys, case.fluxes)
@@ -248,7 +258,7 @@ def test_rk_stage_fusion_is_bit_identical(gpu, oracle, method, knum, mode):
 @pytest.mark.parametrize("kw", [dict(bcup_dissolved_variables=1), dict(bioturbation_profile=2),
                                 dict(bcup_dissolved_variables=0),
                                 dict(minimum=[1., 2., 3., 0.5, 30., 1., 2., 150.]), dict(model=1)])
-@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("mode", RK_MODES)
 def test_rk_stage_fusion_variants(gpu, method, kw, mode):
     case = make_case("rkfv", 19, 9, 15, 0.004, seed=9)
 
@@ -262,7 +272,7 @@ def test_rk_stage_fusion_variants(gpu, method, kw, mode):
 
 
 @pytest.mark.parametrize("method", [1, 3])
-@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("mode", RK_MODES)
 def test_rk_stage_fusion_nan_stops_at_the_same_step(gpu, method, mode):
     case = make_case("rkfn", 12, 8, 15, 0.004, seed=3)
     kw = dict(rnit=5.0e5, rODUox=5.0e5)                     # explicit RK blows up within a few steps

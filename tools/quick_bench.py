@@ -22,6 +22,7 @@ ap.add_argument("--perturb", type=float, default=0.1)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--fusion", choices=["on", "off", "pairs", "chains"], default="on")
 ap.add_argument("--land", type=float, default=0.0)
+ap.add_argument("--rk-stages", type=int, default=4, help="Runge-Kutta, thread per column: stages per launch (4 or 2)")
 a = ap.parse_args()
 dzmin = 0.0015 if a.knum == 40 else 0.002
 t0 = time.time()
@@ -32,6 +33,7 @@ if a.land > 0:
     sed.set_mask(case.mask)
 sed.init_concentrations()
 sed.set_step_fusion({"on": "auto"}.get(a.fusion, a.fusion))
+sed.set_rk_stages_per_launch(a.rk_stages)
 sed.set_boundary(case.bdys, case.fluxes)
 print(f"setup {time.time()-t0:.1f}s")
 sed.step(360.0, a.method, a.spin)
