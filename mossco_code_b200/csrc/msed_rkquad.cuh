@@ -22,12 +22,17 @@
 // distributed POM flux cascade, profile != 3, closed-form porosity), and knum >= 5 (the peeled head and tail
 // of the walk); anything else stays with the stage pairs.
 //
-// Shared memory: (8 ring + 3 link) layers x 8 variables x 128 columns x 8 B = 88 KB per CTA, two CTAs per SM,
-// 255 registers per thread: eight warps per SM, each with four independent RHS evaluations in flight.
+// Shared memory: (8 ring + 3 link) layers x 8 variables x 128 columns x 8 B = 88 KB per CTA, plus 9 KB of layer
+// coefficients (three per layer, made by stage 1, read by the others): two CTAs per SM fit the 200 KB carve-out
+// that leaves the L1 its 56 KB; 255 registers per thread: eight warps per SM, each with four independent RHS
+// evaluations in flight.
 
-constexpr int RKQ_RING = 8;                                   // input ring slots (power of two)
+constexpr int RKQ_RING = 6;                                   // input ring slots: layers k-3 .. k+1 in use, k+2 in flight
 constexpr uint32_t RKQ_STAGE_B = NV * ROW_BYTES;              // one layer of one CTA
-constexpr size_t RKQ_SMEM_BYTES = (size_t)(RKQ_RING + 3) * RKQ_STAGE_B;
+constexpr int RKQ_COEF_ROWS = 3;                              // LayerCoef: mDp, mDd, rpd
+constexpr int RKQ_COEF_SLOTS = 3;                             // layers k-2 .. k (k-3 is read before k takes its slot)
+// ring, three link slots, two weighted sums of the k_i, layer coefficients
+constexpr size_t RKQ_SMEM_BYTES = (size_t)(RKQ_RING + 3 + 2) * RKQ_STAGE_B + RKQ_COEF_SLOTS * RKQ_COEF_ROWS * ROW_BYTES;
 constexpr int RKQ_MIN_LAYERS = 5;
 
 #ifndef MSED_RKQUAD_MIN_BLOCKS
@@ -61,15 +66,27 @@ rk_quad_kernel(const __grid_constant__ KParams p)
     double *g_out = conc;
 
     const uint32_t sbase = smem_u32(ring) + threadIdx.x * 8u;
+    auto q_lds = [&](uint32_t addr) __attribute__((always_inline)) -> double { return lds64(addr); };
+    auto q_sts = [&](uint32_t addr, double v) __attribute__((always_inline)) { sts64(addr, v); };
+    auto stg64 = [](double *g, double v) __attribute__((always_inline)) {
+        asm volatile("st.global.f64 [%0], %1;" ::"l"(g), "d"(v) : "memory");
+    };
     const uint32_t lk2 = sbase + RKQ_RING * RKQ_STAGE_B, lk3 = lk2 + RKQ_STAGE_B, lk4 = lk3 + RKQ_STAGE_B;
-    auto slot = [&](int L) __attribute__((always_inline)) -> uint32_t {
-        return sbase + (uint32_t)(L & (RKQ_RING - 1)) * RKQ_STAGE_B;
+    const uint32_t xsa = lk4 + RKQ_STAGE_B;   // x34 of the layer stage 4 evaluates next
+    const uint32_t xsb = xsa + RKQ_STAGE_B;   // x23 (RK4) / x23b (RK4-3/8) of the layer stage 3 evaluates next
+    const uint32_t cfb = xsb + RKQ_STAGE_B;   // layer coefficients: slot (layer mod 3) x {mDp, mDd, rpd}
+    int kmod = 0;                              // k mod RKQ_RING (the ring is not a power of two: counted, not divided)
+    auto slot = [&](int rel) __attribute__((always_inline)) -> uint32_t {   // ring slot of layer k + rel, rel = -3 .. 2
+        int sidx = kmod + rel;
+        if (sidx < 0) sidx += RKQ_RING;
+        if (sidx >= RKQ_RING) sidx -= RKQ_RING;
+        return sbase + (uint32_t)sidx * RKQ_STAGE_B;
     };
     const double *g_in = conc;
-    int k_fetch = 0;
+    int k_fetch = 0, fmod = 0;
     auto fetch_next = [&]() __attribute__((always_inline)) {
         if (k_fetch < K) {
-            const uint32_t sa = slot(k_fetch);
+            const uint32_t sa = sbase + (uint32_t)fmod * RKQ_STAGE_B;
             const double *g = g_in;
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
@@ -79,10 +96,11 @@ rk_quad_kernel(const __grid_constant__ KParams p)
             g_in += ld;
         }
         ++k_fetch;
+        fmod = (fmod == RKQ_RING - 1) ? 0 : fmod + 1;
         cp_async_commit();
     };
 #pragma unroll
-    for (int s = 0; s < RKQ_RING - 4; ++s) fetch_next();      // layers 0 .. 3
+    for (int s = 0; s < RKQ_RING - 4; ++s) fetch_next();      // layers 0 and 1
 
     const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
     auto por_at = [&](int kk) __attribute__((always_inline)) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
@@ -162,14 +180,25 @@ rk_quad_kernel(const __grid_constant__ KParams p)
     //   RK38  x12 = k1          x23 = P = k1 - k2, x23b = Q = k1 + 3 k2     x34 = Q + 3 k3  (:169-182)
     // Each is consumed by its stage before the stage in front of it writes the next layer's value into the same
     // registers (the updates sit at the end of the iteration, last stage first): no copies.
-    double x12[NV], x23[NV], x23b[NV], x34[NV];
-    LayerCoef cf2, cf3, cf4;                   // coefficients of the layers stages 2-4 are about to evaluate
-    double pm3 = 0.0, pm2 = 0.0, pm1 = 0.0, pk = por_at(0), pk1 = por_at(1);   // porosity of layers k-3 .. k+1
+    double x12[NV], x23[NV];   // (x34 and x23 / x23b live in shared memory: see xsa, xsb)
+    // The state-independent coefficients of a layer are made once, by stage 1, and wait for the other stages in a
+    // three-slot ring in shared memory (as registers they were 18 of the 255, and the kernel spilled in its loop).
+    int kmod3 = 0;                             // k mod 3
+    auto coef_addr = [&](int back) __attribute__((always_inline)) -> uint32_t {   // slot of layer k - back, back = 0..3
+        int sidx = kmod3 - (back % 3);
+        if (sidx < 0) sidx += 3;
+        return cfb + (uint32_t)sidx * (RKQ_COEF_ROWS * ROW_BYTES);
+    };
+    auto coef_load = [&](int back) __attribute__((always_inline)) -> LayerCoef {
+        const uint32_t a = coef_addr(back);
+        LayerCoef lc;
+        lc.mDp = lds64(a);
+        lc.mDd = lds64(a + ROW_BYTES);
+        lc.rpd = lds64(a + 2 * ROW_BYTES);
+        return lc;
+    };
 #pragma unroll
-    for (int n = 0; n < NV; ++n) F1[n] = F2[n] = F3[n] = F4[n] = x12[n] = x23[n] = x23b[n] = x34[n] = 0.0;
-    cf2.mDp = cf2.mDd = cf2.rpd = 0.0;
-    cf3 = cf2;
-    cf4 = cf2;
+    for (int n = 0; n < NV; ++n) F1[n] = F2[n] = F3[n] = F4[n] = x12[n] = x23[n] = 0.0;
     bool nanf = false;
 
     // One iteration of the walk.  Mk: what stage k does in it -- 0 nothing, 1 the first layer of the column (upper
@@ -183,75 +212,92 @@ rk_quad_kernel(const __grid_constant__ KParams p)
         double c2[NV], c3[NV], c4[NV];
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
-            if (M2) c2[n] = lds64(lk2 + n * ROW_BYTES);
-            if (M3) c3[n] = lds64(lk3 + n * ROW_BYTES);
-            if (M4) c4[n] = lds64(lk4 + n * ROW_BYTES);
+            if (M2) c2[n] = q_lds(lk2 + n * ROW_BYTES);
+            if (M3) c3[n] = q_lds(lk3 + n * ROW_BYTES);
+            if (M4) c4[n] = q_lds(lk4 + n * ROW_BYTES);
         }
         double y2n[NV], y3n[NV], y4n[NV];      // the layer stages 1-3 produce in this iteration
         double rhs1[NV], rhs2[NV], rhs3[NV];
-        LayerCoef cf1n = cf2;
+        LayerCoef cf4;
+        if (M4) cf4 = coef_load(3);            // (its slot is the one stage 1 fills below)
         if (M1) {                              // ---- stage 1, layer k: k1 = f(c) ------------------------------
-            fetch_next();                      // layer k+4 into the slot layer k-4 has left
+            fetch_next();                      // layer k+2 into the slot layer k-4 has left
             cp_async_wait<RKQ_RING - 5>();     // layer k+1 has landed
-            const uint32_t sc = slot(k), sn = slot(k + 1);
+            const uint32_t sc = slot(0), sn = slot(1);
             double cc[NV], cn[NV];
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
-                cc[n] = lds64(sc + n * ROW_BYTES);
-                cn[n] = (M1 != 3) ? lds64(sn + n * ROW_BYTES) : 0.0;
+                cc[n] = q_lds(sc + n * ROW_BYTES);
+                cn[n] = (M1 != 3) ? q_lds(sn + n * ROW_BYTES) : 0.0;
             }
             if (M1 == 1) top_boundary(cc, F1, false);
-            if (M1 != 3) { cf1n = make_coef(Y{}, k, pk, pk1); layer_rates(Y{}, cf1n, pk, pk1, cc, cn, F1, rhs1); }
-            else         { cf1n = make_coef(N{}, k, pk, pk1); layer_rates(N{}, cf1n, pk, pk1, cc, cn, F1, rhs1); }
+            const double pk = por_at(k), pk1 = (M1 != 3) ? por_at(k + 1) : 0.0;
+            LayerCoef cf1;
+            if (M1 != 3) { cf1 = make_coef(Y{}, k, pk, pk1); layer_rates(Y{}, cf1, pk, pk1, cc, cn, F1, rhs1); }
+            else         { cf1 = make_coef(N{}, k, pk, pk1); layer_rates(N{}, cf1, pk, pk1, cc, cn, F1, rhs1); }
+            {
+                const uint32_t a = coef_addr(0);
+                q_sts(a, cf1.mDp);
+                q_sts(a + ROW_BYTES, cf1.mDd);
+                q_sts(a + 2 * ROW_BYTES, cf1.rpd);
+            }
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
                 if (!IS38) y2n[n] = fma(0.5 * dt, rhs1[n], cc[n]);      // :147  c1 = c + 0.5*dt*k1
                 else       y2n[n] = fma(third * dt, rhs1[n], cc[n]);    // :169  c1 = c + third*dt*k1
-                sts64(lk2 + n * ROW_BYTES, y2n[n]);
+                q_sts(lk2 + n * ROW_BYTES, y2n[n]);
             }
         }
         if (M2) {                              // ---- stage 2, layer k-1: k2 = f(c1) ---------------------------
-            const uint32_t sb = slot(k - 1);
+            const uint32_t sb = slot(-1);
             if (M2 == 1) top_boundary(c2, F2, false);
-            if (M2 != 3) layer_rates(Y{}, cf2, pm1, pk, c2, y2n, F2, rhs2);
-            else         layer_rates(N{}, cf2, pm1, pk, c2, c2, F2, rhs2);
+            const LayerCoef cf2 = coef_load(1);
+            if (M2 != 3) layer_rates(Y{}, cf2, por_at(k - 1), por_at(k), c2, y2n, F2, rhs2);
+            else         layer_rates(N{}, cf2, por_at(k - 1), 0.0, c2, c2, F2, rhs2);
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
-                const double base = lds64(sb + n * ROW_BYTES);
+                const double base = q_lds(sb + n * ROW_BYTES);
                 if (!IS38) y3n[n] = fma(0.5 * dt, rhs2[n], base);                        // :152  c1 = c + 0.5*dt*k2
                 else       y3n[n] = fma(dt, fma(-third, x12[n], rhs2[n]), base);         // :174  c1 = c + dt*(k2 - third*k1)
-                sts64(lk3 + n * ROW_BYTES, y3n[n]);
+                q_sts(lk3 + n * ROW_BYTES, y3n[n]);
             }
         }
         if (M3) {                              // ---- stage 3, layer k-2: k3 = f(c1) ---------------------------
-            const uint32_t sb = slot(k - 2);
+            const uint32_t sb = slot(-2);
             if (M3 == 1) top_boundary(c3, F3, false);
-            if (M3 != 3) layer_rates(Y{}, cf3, pm2, pm1, c3, y3n, F3, rhs3);
-            else         layer_rates(N{}, cf3, pm2, pm1, c3, c3, F3, rhs3);
+            const LayerCoef cf3 = coef_load(2);
+            if (M3 != 3) layer_rates(Y{}, cf3, por_at(k - 2), por_at(k - 1), c3, y3n, F3, rhs3);
+            else         layer_rates(N{}, cf3, por_at(k - 2), 0.0, c3, c3, F3, rhs3);
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
-                const double base = lds64(sb + n * ROW_BYTES);
+                const double base = q_lds(sb + n * ROW_BYTES);
                 if (!IS38) y4n[n] = fma(dt, rhs3[n], base);                              // :156  c1 = c + dt*k3
                 else       y4n[n] = fma(dt, MSED_ADD(x23[n], rhs3[n]), base);            // :178  c1 = c + dt*(P + k3)
-                sts64(lk4 + n * ROW_BYTES, y4n[n]);
+                q_sts(lk4 + n * ROW_BYTES, y4n[n]);
             }
             if (keep_c1) {
-#pragma unroll
-                for (int n = 0; n < NV; ++n) g_c1[(size_t)n * plane] = y4n[n];
+                double *gc = g_c1;   // (pointer steps instead of n*plane offsets: those were eight more loop invariants in
+#pragma unroll               //  a kernel that already spills its uniform registers)
+                for (int n = 0; n < NV; ++n) {
+                    stg64(gc, y4n[n]);
+                    gc += plane;
+                    asm volatile("" : "+l"(gc));
+                }
             }
             g_c1 += ld;
         }
         if (M4) {                              // ---- stage 4, layer k-3: k4 = f(c1), the new state ------------
-            const uint32_t sb = slot(k - 3);
+            const uint32_t sb = slot(-3);
             double rhs[NV], raw[NV];
             if (M4 == 1) top_boundary(c4, F4, true);
-            if (M4 != 3) layer_rates(Y{}, cf4, pm3, pm2, c4, y4n, F4, rhs);
-            else         layer_rates(N{}, cf4, pm3, pm2, c4, c4, F4, rhs);
+            if (M4 != 3) layer_rates(Y{}, cf4, por_at(k - 3), por_at(k - 2), c4, y4n, F4, rhs);
+            else         layer_rates(N{}, cf4, por_at(k - 3), 0.0, c4, c4, F4, rhs);
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
-                const double base = lds64(sb + n * ROW_BYTES);
-                if (!IS38) raw[n] = fma(dt * third, fma(0.5, rhs[n], x34[n]), base);       // :160
-                else       raw[n] = fma(dt * 1.0 / 8.0, MSED_ADD(x34[n], rhs[n]), base);   // :182
+                const double base = q_lds(sb + n * ROW_BYTES);
+                const double x34 = q_lds(xsa + n * ROW_BYTES);
+                if (!IS38) raw[n] = fma(dt * third, fma(0.5, rhs[n], x34), base);          // :160
+                else       raw[n] = fma(dt * 1.0 / 8.0, MSED_ADD(x34, rhs[n]), base);      // :182
             }
             if (do_clip) {                     // check_NaN + clip (component :1718-1732)
 #pragma unroll
@@ -260,34 +306,33 @@ rk_quad_kernel(const __grid_constant__ KParams p)
                     raw[n] = clip_min(raw[n], p.om.minimum[n]);
                 }
             }
+            double *go = g_out;
 #pragma unroll
-            for (int n = 0; n < NV; ++n) g_out[(size_t)n * plane] = raw[n];
+            for (int n = 0; n < NV; ++n) {   // (the empty asm keeps the steps: folded into n*plane offsets they are
+                stg64(go, raw[n]);           // fourteen more uniform registers, which the kernel does not have)
+                go += plane;
+                asm volatile("" : "+l"(go));
+            }
             g_out += ld;
         }
         // hand-over to the next iteration, last stage first (see x12 .. x34 above)
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
             if (!IS38) {
-                if (M3) x34[n] = MSED_ADD(x23[n], rhs3[n]);            // :156  acc += k3
-                if (M2) x23[n] = MSED_ADD(x12[n], rhs2[n]);            // :152  acc = 0.5*k1 + k2
-                if (M1) x12[n] = MSED_MUL(0.5, rhs1[n]);               // :147  acc = 0.5*k1
+                if (M3) q_sts(xsa + n * ROW_BYTES, MSED_ADD(q_lds(xsb + n * ROW_BYTES), rhs3[n]));   // :156  acc += k3
+                if (M2) q_sts(xsb + n * ROW_BYTES, MSED_ADD(x12[n], rhs2[n]));                       // :152  acc = 0.5*k1 + k2
+                if (M1) x12[n] = MSED_MUL(0.5, rhs1[n]);                                             // :147  acc = 0.5*k1
             } else {
-                if (M3) x34[n] = fma(3.0, rhs3[n], x23b[n]);           // :178  Q += 3*k3
-                if (M2) {                                              // :174  P = k1-k2 ; Q = k1+3*k2
+                if (M3) q_sts(xsa + n * ROW_BYTES, fma(3.0, rhs3[n], q_lds(xsb + n * ROW_BYTES)));   // :178  Q += 3*k3
+                if (M2) {                                                                            // :174  P = k1-k2 ; Q = k1+3*k2
                     x23[n] = MSED_SUB(x12[n], rhs2[n]);
-                    x23b[n] = fma(3.0, rhs2[n], x12[n]);
+                    q_sts(xsb + n * ROW_BYTES, fma(3.0, rhs2[n], x12[n]));
                 }
                 if (M1) x12[n] = rhs1[n];
             }
         }
-        cf4 = cf3;
-        cf3 = cf2;
-        if (M1) cf2 = cf1n;
-        pm3 = pm2;
-        pm2 = pm1;
-        pm1 = pk;
-        pk = pk1;
-        if (M1 == 1 || M1 == 2) pk1 = (k + 2 < K) ? por_at(k + 2) : 0.0;
+        kmod = (kmod == RKQ_RING - 1) ? 0 : kmod + 1;
+        kmod3 = (kmod3 == 2) ? 0 : kmod3 + 1;
     };
 
     {
