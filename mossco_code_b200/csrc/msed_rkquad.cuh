@@ -252,13 +252,15 @@ rk_quad_kernel(const __grid_constant__ KParams p)
             const uint32_t sb = slot(-1);
             if (M2 == 1) top_boundary(c2, F2, false);
             const LayerCoef cf2 = coef_load(1);
+            double base[NV];   // (read in one go, ahead of their use: a load next to its use inside the ordered
+#pragma unroll             //  ld.shared / st.shared sequence exposes its latency eight times per stage)
+            for (int n = 0; n < NV; ++n) base[n] = q_lds(sb + n * ROW_BYTES);
             if (M2 != 3) layer_rates(Y{}, cf2, por_at(k - 1), por_at(k), c2, y2n, F2, rhs2);
             else         layer_rates(N{}, cf2, por_at(k - 1), 0.0, c2, c2, F2, rhs2);
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
-                const double base = q_lds(sb + n * ROW_BYTES);
-                if (!IS38) y3n[n] = fma(0.5 * dt, rhs2[n], base);                        // :152  c1 = c + 0.5*dt*k2
-                else       y3n[n] = fma(dt, fma(-third, x12[n], rhs2[n]), base);         // :174  c1 = c + dt*(k2 - third*k1)
+                if (!IS38) y3n[n] = fma(0.5 * dt, rhs2[n], base[n]);                     // :152  c1 = c + 0.5*dt*k2
+                else       y3n[n] = fma(dt, fma(-third, x12[n], rhs2[n]), base[n]);      // :174  c1 = c + dt*(k2 - third*k1)
                 q_sts(lk3 + n * ROW_BYTES, y3n[n]);
             }
         }
@@ -266,13 +268,15 @@ rk_quad_kernel(const __grid_constant__ KParams p)
             const uint32_t sb = slot(-2);
             if (M3 == 1) top_boundary(c3, F3, false);
             const LayerCoef cf3 = coef_load(2);
+            double base[NV];
+#pragma unroll
+            for (int n = 0; n < NV; ++n) base[n] = q_lds(sb + n * ROW_BYTES);
             if (M3 != 3) layer_rates(Y{}, cf3, por_at(k - 2), por_at(k - 1), c3, y3n, F3, rhs3);
             else         layer_rates(N{}, cf3, por_at(k - 2), 0.0, c3, c3, F3, rhs3);
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
-                const double base = q_lds(sb + n * ROW_BYTES);
-                if (!IS38) y4n[n] = fma(dt, rhs3[n], base);                              // :156  c1 = c + dt*k3
-                else       y4n[n] = fma(dt, MSED_ADD(x23[n], rhs3[n]), base);            // :178  c1 = c + dt*(P + k3)
+                if (!IS38) y4n[n] = fma(dt, rhs3[n], base[n]);                           // :156  c1 = c + dt*k3
+                else       y4n[n] = fma(dt, MSED_ADD(x23[n], rhs3[n]), base[n]);         // :178  c1 = c + dt*(P + k3)
                 q_sts(lk4 + n * ROW_BYTES, y4n[n]);
             }
             if (keep_c1) {
@@ -288,16 +292,19 @@ rk_quad_kernel(const __grid_constant__ KParams p)
         }
         if (M4) {                              // ---- stage 4, layer k-3: k4 = f(c1), the new state ------------
             const uint32_t sb = slot(-3);
-            double rhs[NV], raw[NV];
+            double rhs[NV], raw[NV], base[NV], x34[NV];
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                base[n] = q_lds(sb + n * ROW_BYTES);
+                x34[n] = q_lds(xsa + n * ROW_BYTES);
+            }
             if (M4 == 1) top_boundary(c4, F4, true);
             if (M4 != 3) layer_rates(Y{}, cf4, por_at(k - 3), por_at(k - 2), c4, y4n, F4, rhs);
             else         layer_rates(N{}, cf4, por_at(k - 3), 0.0, c4, c4, F4, rhs);
 #pragma unroll
             for (int n = 0; n < NV; ++n) {
-                const double base = q_lds(sb + n * ROW_BYTES);
-                const double x34 = q_lds(xsa + n * ROW_BYTES);
-                if (!IS38) raw[n] = fma(dt * third, fma(0.5, rhs[n], x34), base);          // :160
-                else       raw[n] = fma(dt * 1.0 / 8.0, MSED_ADD(x34, rhs[n]), base);      // :182
+                if (!IS38) raw[n] = fma(dt * third, fma(0.5, rhs[n], x34[n]), base[n]);          // :160
+                else       raw[n] = fma(dt * 1.0 / 8.0, MSED_ADD(x34[n], rhs[n]), base[n]);      // :182
             }
             if (do_clip) {                     // check_NaN + clip (component :1718-1732)
 #pragma unroll
@@ -316,14 +323,18 @@ rk_quad_kernel(const __grid_constant__ KParams p)
             g_out += ld;
         }
         // hand-over to the next iteration, last stage first (see x12 .. x34 above)
+        double xb[NV];
+#pragma unroll
+        for (int n = 0; n < NV; ++n)
+            if (M3) xb[n] = q_lds(xsb + n * ROW_BYTES);
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
             if (!IS38) {
-                if (M3) q_sts(xsa + n * ROW_BYTES, MSED_ADD(q_lds(xsb + n * ROW_BYTES), rhs3[n]));   // :156  acc += k3
+                if (M3) q_sts(xsa + n * ROW_BYTES, MSED_ADD(xb[n], rhs3[n]));                        // :156  acc += k3
                 if (M2) q_sts(xsb + n * ROW_BYTES, MSED_ADD(x12[n], rhs2[n]));                       // :152  acc = 0.5*k1 + k2
                 if (M1) x12[n] = MSED_MUL(0.5, rhs1[n]);                                             // :147  acc = 0.5*k1
             } else {
-                if (M3) q_sts(xsa + n * ROW_BYTES, fma(3.0, rhs3[n], q_lds(xsb + n * ROW_BYTES)));   // :178  Q += 3*k3
+                if (M3) q_sts(xsa + n * ROW_BYTES, fma(3.0, rhs3[n], xb[n]));                        // :178  Q += 3*k3
                 if (M2) {                                                                            // :174  P = k1-k2 ; Q = k1+3*k2
                     x23[n] = MSED_SUB(x12[n], rhs2[n]);
                     q_sts(xsb + n * ROW_BYTES, fma(3.0, rhs2[n], x12[n]));
