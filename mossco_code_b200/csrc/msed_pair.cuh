@@ -372,12 +372,31 @@ pair_kernel(const __grid_constant__ KParams p)
         return lc;
     };
     // step 2, layer j: state from the c1 window, result to HBM
-    auto stage_b = [&](auto has_next_tag, auto clip_tag, int j, const LayerCoef &lc) __attribute__((always_inline)) {
+#ifdef MSED_PAIR_PRELOAD_B
+    // (experiment) In the steady state the layer stage B evaluates was written by stage A one iteration ago: read
+    // ahead of stage A's stores of this iteration, it lets B's reaction rates run beside A's arithmetic -- the
+    // ld.shared / st.shared statements keep their order, so a load behind A's stores waits for all of A.
+    double ccB[NV];
+    auto preload_b = [&](int j) __attribute__((always_inline)) {
+        const uint32_t wj = wbase + (uint32_t)(j & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
+#pragma unroll
+        for (int n = 0; n < NV; ++n) ccB[n] = lds64(wj + n * ROW_BYTES);
+    };
+#endif
+    auto stage_b = [&](auto has_next_tag, auto clip_tag, int j, const LayerCoef &lc, auto preloaded_tag) __attribute__((always_inline)) {
         const uint32_t wj = wbase + (uint32_t)(j & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
         const uint32_t wn = wbase + (uint32_t)((j + 1) & (PAIR_WIN - 1)) * (NV * ROW_BYTES);
         double cc[NV];
+#ifdef MSED_PAIR_PRELOAD_B
+        if (decltype(preloaded_tag)::value) {
 #pragma unroll
-        for (int n = 0; n < NV; ++n) cc[n] = lds64(wj + n * ROW_BYTES);
+            for (int n = 0; n < NV; ++n) cc[n] = ccB[n];
+        } else
+#endif
+        {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) cc[n] = lds64(wj + n * ROW_BYTES);
+        }
         double *go = g_out;
         if (DENIT) {
             double dn = 0.0;
@@ -400,20 +419,23 @@ pair_kernel(const __grid_constant__ KParams p)
         if (K == 1) {  // degenerate column: both stages see a closed bottom right away
             coef_prev = stage_a(N{}, clip_a, up_tag, 0);
             top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
-            stage_b(N{}, clip_b, 0, coef_prev);
+            stage_b(N{}, clip_b, 0, coef_prev, N{});
             return;
         }
         coef_prev = stage_a(Y{}, clip_a, up_tag, 0);
         top_boundary([&](int n) { return lds64(wbase + n * ROW_BYTES); }, por_at(0), FB, true);
         MSED_PAIR_UNROLL_PRAGMA
         for (int k = 1; k < K - 1; ++k) {  // steady state: stage A on layer k, stage B on layer k-1
+#ifdef MSED_PAIR_PRELOAD_B
+            preload_b(k - 1);
+#endif
             const LayerCoef lc = stage_a(Y{}, clip_a, up_tag, k);
-            stage_b(Y{}, clip_b, k - 1, coef_prev);
+            stage_b(Y{}, clip_b, k - 1, coef_prev, Y{});
             coef_prev = lc;
         }
         const LayerCoef last = stage_a(N{}, clip_a, up_tag, K - 1);
-        stage_b(Y{}, clip_b, K - 2, coef_prev);
-        stage_b(N{}, clip_b, K - 1, last);
+        stage_b(Y{}, clip_b, K - 2, coef_prev, N{});
+        stage_b(N{}, clip_b, K - 1, last, N{});
     };
     {
         using Y = std::true_type;

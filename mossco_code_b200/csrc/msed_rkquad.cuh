@@ -105,6 +105,17 @@ rk_quad_kernel(const __grid_constant__ KParams p)
     const double por_surf = (p.por_mode == 2) ? ld_ro(p.por + col) : 1.0;
     auto por_at = [&](int kk) __attribute__((always_inline)) -> double { return __dmul_rn(por_surf, p.portab[kk]); };
     const double temp = ld_ro(p.bdys + col);
+    // the upper-boundary value of every variable (an input flux or a concentration above the bed): every stage needs
+    // them once, in the first four iterations -- read here in one go, beside the temperature, they cost one trip to
+    // L2 / HBM per column instead of one per stage and variable at the head of the walk
+    double ub[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+        const int bc = (n < NPART) ? p.bcup_part : p.bcup_diss;
+        ub[n] = 0.0;
+        if (bc == 1 || bc == 4) ub[n] = ld_ro(p.fluxes + (size_t)n * ld + col);          // :783,:792
+        else if (bc == 2) ub[n] = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);            // :786
+    }
     double cpart, cdiss, fT;
     column_constants<MODEL, false>(p, temp, cpart, cdiss, fT);
 
@@ -120,9 +131,9 @@ rk_quad_kernel(const __grid_constant__ KParams p)
             const int bc = part ? p.bcup_part : p.bcup_diss;
             double f = 0.0;
             if (bc == 1 || bc == 4) {
-                f = ld_ro(p.fluxes + (size_t)n * ld + col);
+                f = ub[n];
             } else if (bc == 2) {
-                const double Cup = ld_ro(p.bdys + (size_t)(n + 1) * ld + col);
+                const double Cup = ub[n];
                 const double C1 = part ? MSED_MUL(c0[n], por0) : c0[n];
                 f = top_flux_dirichlet(part ? Dp : Dd, C1, Cup, rdz0);
             } else if (bc != 3 && n > 0) {
