@@ -130,3 +130,14 @@ def test_large_time_step_rk_negative_concentrations(gpu, oracle):
     ref.ode_solver(1800.0, 1)
     assert np.isfinite(ref.conc).all()
     assert scaled_err(got, ref.conc) <= 1e-10
+
+
+def test_rk_stages_per_launch_argument_is_checked(gpu):
+    """msed_set_rk_stages_per_launch takes 2 (stage pairs) or 4 (the whole call in one launch), nothing else."""
+    from mossco_code_b200 import MsedError, SedimentDriver, default_config
+    with SedimentDriver(default_config(inum=4, jnum=3, knum=8, dzmin=0.01)) as sed:
+        sed.set_rk_stages_per_launch(2)
+        sed.set_rk_stages_per_launch(4)
+        for bad in (0, 1, 3, 8):
+            with pytest.raises(MsedError):
+                sed.set_rk_stages_per_launch(bad)
