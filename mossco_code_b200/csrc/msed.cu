@@ -366,12 +366,22 @@ cudaError_t launch_rk_chain(const msed_handle *h, int method, const KParams &p, 
     return tu_launch_rk_chain(h->cfg.model, method, clip, p, m, h->stream);
 }
 
-// one launch = two chained Runge-Kutta stages (msed_rkpair.cuh); which = 0 for stages 1+2, 1 for 3+4
-cudaError_t launch_rk_quad(const msed_handle *h, int method, const KParams &p)
+// one launch = the four stages of a Runge-Kutta call (msed_rkquad.cuh)
+cudaError_t launch_rk_quad(const msed_handle *h, int method, const KParams &pin)
 {
+    KParams p = pin;
+    if (h->colmap) {  // masked tile: run over the wet columns of [col0, col_end) only (as launch_pair)
+        const auto lo = std::lower_bound(h->wet_idx.begin(), h->wet_idx.end(), pin.col0);
+        const auto hi = std::lower_bound(h->wet_idx.begin(), h->wet_idx.end(), pin.col_end);
+        p.col0 = (int)(lo - h->wet_idx.begin());
+        p.col_end = (int)(hi - h->wet_idx.begin());
+        p.colmap = h->colmap;
+        if (p.col_end <= p.col0) return cudaSuccess;  // all land: nothing to launch
+    }
     return tu_launch_rk_quad(h->cfg.model, method, p, h->stream);
 }
 
+// one launch = two chained Runge-Kutta stages (msed_rkpair.cuh); which = 0 for stages 1+2, 1 for 3+4
 cudaError_t launch_rk_pair(const msed_handle *h, int method, int which, const KParams &p)
 {
     return tu_launch_rk_pair(h->cfg.model, method, which, p, h->stream);

@@ -54,8 +54,11 @@ rk_quad_kernel(const __grid_constant__ KParams p)
     // call of a sequence stores it where the staged path leaves it (the spare buffer)
     const bool keep_c1 = ctl->steps_done + 1 >= ctl->steps_target;
 
-    const int col = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
-    if (col >= p.col_end) return;
+    // On a tile with land the launch runs over the list of wet columns (KParams::colmap, as pair_kernel does): a CTA
+    // of mostly land columns would hold its 97 KB of shared memory for a few wet warps.
+    const int t = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
+    if (t >= p.col_end) return;
+    const int col = p.colmap ? p.colmap[t] : t;
     if (p.mask[col] != 0) return;
 
     const int K = p.K;
