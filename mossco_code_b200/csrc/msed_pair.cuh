@@ -141,7 +141,9 @@ pair_kernel(const __grid_constant__ KParams p)
     }
     const int col = COLMAP ? p.colmap[t] : t;   // COLMAP: the tile has land (a separate instantiation, so the
                                                 // land-free kernel keeps its register allocation)
-    if (!BULK && p.mask[col] != 0) return;  // conc stays missing_value in both buffers
+    // conc of a land column stays missing_value in both buffers; the wet-column list holds no land column
+    // (msed_set_mask builds both), so that feed skips the look-up: one dependent trip to L2 less at the head
+    if (!BULK && !COLMAP && p.mask[col] != 0) return;
 
     const int K = p.K;
     const size_t ld = p.ld;

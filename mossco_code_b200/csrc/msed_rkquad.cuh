@@ -59,7 +59,7 @@ rk_quad_kernel(const __grid_constant__ KParams p)
     const int t = p.col0 + blockIdx.x * COL_BLOCK + threadIdx.x;
     if (t >= p.col_end) return;
     const int col = p.colmap ? p.colmap[t] : t;
-    if (p.mask[col] != 0) return;
+    if (!p.colmap && p.mask[col] != 0) return;   // (the list holds wet columns only: msed_set_mask builds both)
 
     const int K = p.K;
     const size_t ld = p.ld;
