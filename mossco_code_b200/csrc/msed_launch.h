@@ -14,6 +14,7 @@ cudaError_t tu_launch_column(int model, bool profile3, bool stream_por, int op, 
 // OVR <- p.in_ovr; the caller has already converted col0/col_end to a range of the wet-column list
 cudaError_t tu_launch_pair(int model, bool adaptive, const KParams &p, cudaStream_t s);
 cudaError_t tu_enable_pair_smem();
+constexpr int TU_PAIR_CTAS_PER_SM = 384 / COL_BLOCK;   // resident pair_kernel CTAs per SM (msed_pair.cuh, PAIR_MIN_BLOCKS)
 
 // chain_kernel (msed_chain.cuh): nsteps ode_solver calls per launch, warp per column, knum <= 64
 cudaError_t tu_launch_chain(int model, bool adaptive, bool clip, const KParams &p, int nsteps, cudaStream_t s);
