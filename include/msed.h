@@ -232,7 +232,7 @@ int msed_set_step_fusion(msed_handle *h, int mode);
  * used) or 2 (stages 1+2 and 3+4, seven state passes per call, rk_pair_kernel).  Environment MSED_RK_STAGES.
  * Bit-identical results either way, and to the staged path (step fusion off). */
 int msed_set_rk_stages_per_launch(msed_handle *h, int stages);
-/* number of column chunks msed_run_exchange uses (0 = choose from the tile size: 1 to 8, always the
+/* number of column chunks msed_run_exchange uses (0 = choose from the tile size: 1, 4 or 8 -- 8 from 2^19 columns on --, always the
  * asynchronous sequence; 1 = the plain sequence of the three separate calls, no overlap) */
 int msed_set_exchange_chunks(msed_handle *h, int nchunks);
 /* order in which msed_run_exchange walks a coupling interval that consists of fused pairs only: 0 = step by

@@ -1163,6 +1163,10 @@ int msed_create(const msed_config *cfg, msed_handle **out)
     if (const char *e = std::getenv("MSED_CHAIN_MAX_COLS")) h->chain_max_cols = std::atoll(e);
     if (const char *e = std::getenv("MSED_EXCHANGE_CHUNK_MAJOR")) h->chunk_major = std::atoi(e) != 0;
     if (const char *e = std::getenv("MSED_RK_STAGES")) h->rk_stages = std::atoi(e) == 2 ? 2 : 4;
+    if (const char *e = std::getenv("MSED_EXCHANGE_CHUNKS")) {   // initial msed_set_exchange_chunks value (0 = auto)
+        const int n = std::atoi(e);
+        if (n >= 0 && n <= 16) h->exchange_chunks = n;
+    }
     if (const char *e = std::getenv("MSED_STEP_FUSION")) {  // initial msed_set_step_fusion mode (0..3)
         const int mode = std::atoi(e);
         if (mode >= 0 && mode <= 3) h->step_fusion = mode;
@@ -1688,7 +1692,8 @@ int msed_run_exchange(msed_handle *h, double dt, int method, double run_seconds,
     // sequence below still saves the host synchronisations of the three separate calls, which dominate a
     // Run of a few tens of microseconds; msed_set_exchange_chunks(1) asks for the plain sequence
     const bool auto_chunks = nchunks == 0;
-    if (auto_chunks) nchunks = h->ncol >= (1 << 20) ? 8 : (h->ncol >= (1 << 17) ? 4 : 1);
+    // (C3, 10^6 columns: e2e 52.5 G cell-updates/s with 6 or 8 chunks, 50.0 with 4, 47.5 with 3 -- profiles/r02_s24_*)
+    if (auto_chunks) nchunks = h->ncol >= (1 << 19) ? 8 : (h->ncol >= (1 << 17) ? 4 : 1);
     const bool pipelined = (nchunks > 1 || auto_chunks) && (method == MSED_EULER || method == MSED_ADAPTIVE_EULER) &&
                            !h->cfg.adaptive_solver_diagnostics && (nfull + (rem > 0.0 ? 1 : 0)) > 0 &&
                            (size_t)NV * h->K >= 12 + NV;
