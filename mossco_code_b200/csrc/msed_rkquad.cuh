@@ -14,7 +14,7 @@
 // A stage hands the layer it has just produced to the next stage in registers (as that stage's "layer below")
 // and through a one-layer link slot in shared memory (as the next iteration's "current layer"); the weighted
 // sums of the k_i travel in registers from stage to stage, one iteration at a time; the base state of stages
-// 2-4 is still in the input ring (8 slots: layers k-3 .. k+1 in use, k+2 .. k+4 in flight).  The state is read
+// 2-4 is still in the input ring (6 slots: layers k-3 .. k+1 in use, k+2 in flight).  The state is read
 // once and written once per CALL (2 passes instead of 7), nothing else touches HBM.
 //
 // The stage formulas and the inline arithmetic are those of rk_pair_kernel / the staged column_kernel ops, so
@@ -22,10 +22,10 @@
 // distributed POM flux cascade, profile != 3, closed-form porosity), and knum >= 5 (the peeled head and tail
 // of the walk); anything else stays with the stage pairs.
 //
-// Shared memory: (8 ring + 3 link) layers x 8 variables x 128 columns x 8 B = 88 KB per CTA, plus 9 KB of layer
-// coefficients (three per layer, made by stage 1, read by the others): two CTAs per SM fit the 200 KB carve-out
-// that leaves the L1 its 56 KB; 255 registers per thread: eight warps per SM, each with four independent RHS
-// evaluations in flight.
+// Shared memory: (6 ring + 3 link + 2 k-sum) layers x 8 variables x 128 columns x 8 B = 88 KB per CTA, plus 9 KB of
+// layer coefficients (three per layer, made by stage 1, read by the others; RK4-3/8 keeps its third k sum there
+// instead): two CTAs per SM fit the 200 KB carve-out that leaves the L1 its 56 KB; 255 registers per thread: eight
+// warps per SM, each with four independent RHS evaluations in flight.
 
 constexpr int RKQ_RING = 6;                                   // input ring slots: layers k-3 .. k+1 in use, k+2 in flight
 constexpr uint32_t RKQ_STAGE_B = NV * ROW_BYTES;              // one layer of one CTA
@@ -195,6 +195,11 @@ rk_quad_kernel(const __grid_constant__ KParams p)
     // Each is consumed by its stage before the stage in front of it writes the next layer's value into the same
     // registers (the updates sit at the end of the iteration, last stage first): no copies.
     double x12[NV], x23[NV];   // (x34 and x23 / x23b live in shared memory: see xsa, xsb)
+    // RK4-3/8 carries one sum more than RK4 (P and Q beside k1): with the coefficient ring it spilled in its loop.  It
+    // gives the ring's shared memory to P instead and makes the coefficients of a layer anew in every stage (14 fp64
+    // instructions per stage and layer: cheaper than the reloads of the spills).
+    constexpr bool COEF_RING = !IS38;
+    const uint32_t xsp = cfb;                  // IS38: x23 = P of the layer stage 3 evaluates next
     // The state-independent coefficients of a layer are made once, by stage 1, and wait for the other stages in a
     // three-slot ring in shared memory (as registers they were 18 of the 255, and the kernel spilled in its loop).
     int kmod3 = 0;                             // k mod 3
@@ -233,7 +238,7 @@ rk_quad_kernel(const __grid_constant__ KParams p)
         double y2n[NV], y3n[NV], y4n[NV];      // the layer stages 1-3 produce in this iteration
         double rhs1[NV], rhs2[NV], rhs3[NV];
         LayerCoef cf4;
-        if (M4) cf4 = coef_load(3);            // (its slot is the one stage 1 fills below)
+        if (M4 && COEF_RING) cf4 = coef_load(3);   // (its slot is the one stage 1 fills below)
         if (M1) {                              // ---- stage 1, layer k: k1 = f(c) ------------------------------
             fetch_next();                      // layer k+2 into the slot layer k-4 has left
             cp_async_wait<RKQ_RING - 5>();     // layer k+1 has landed
@@ -249,7 +254,7 @@ rk_quad_kernel(const __grid_constant__ KParams p)
             LayerCoef cf1;
             if (M1 != 3) { cf1 = make_coef(Y{}, k, pk, pk1); layer_rates(Y{}, cf1, pk, pk1, cc, cn, F1, rhs1); }
             else         { cf1 = make_coef(N{}, k, pk, pk1); layer_rates(N{}, cf1, pk, pk1, cc, cn, F1, rhs1); }
-            {
+            if (COEF_RING) {
                 const uint32_t a = coef_addr(0);
                 q_sts(a, cf1.mDp);
                 q_sts(a + ROW_BYTES, cf1.mDd);
@@ -265,7 +270,9 @@ rk_quad_kernel(const __grid_constant__ KParams p)
         if (M2) {                              // ---- stage 2, layer k-1: k2 = f(c1) ---------------------------
             const uint32_t sb = slot(-1);
             if (M2 == 1) top_boundary(c2, F2, false);
-            const LayerCoef cf2 = coef_load(1);
+            const LayerCoef cf2 = COEF_RING ? coef_load(1)
+                                            : (M2 != 3 ? make_coef(Y{}, k - 1, por_at(k - 1), por_at(k))
+                                                       : make_coef(N{}, k - 1, por_at(k - 1), 0.0));
             double base[NV];   // (read in one go, ahead of their use: a load next to its use inside the ordered
 #pragma unroll             //  ld.shared / st.shared sequence exposes its latency eight times per stage)
             for (int n = 0; n < NV; ++n) base[n] = q_lds(sb + n * ROW_BYTES);
@@ -281,7 +288,13 @@ rk_quad_kernel(const __grid_constant__ KParams p)
         if (M3) {                              // ---- stage 3, layer k-2: k3 = f(c1) ---------------------------
             const uint32_t sb = slot(-2);
             if (M3 == 1) top_boundary(c3, F3, false);
-            const LayerCoef cf3 = coef_load(2);
+            const LayerCoef cf3 = COEF_RING ? coef_load(2)
+                                            : (M3 != 3 ? make_coef(Y{}, k - 2, por_at(k - 2), por_at(k - 1))
+                                                       : make_coef(N{}, k - 2, por_at(k - 2), 0.0));
+            if (IS38) {
+#pragma unroll
+                for (int n = 0; n < NV; ++n) x23[n] = q_lds(xsp + n * ROW_BYTES);
+            }
             double base[NV];
 #pragma unroll
             for (int n = 0; n < NV; ++n) base[n] = q_lds(sb + n * ROW_BYTES);
@@ -312,6 +325,8 @@ rk_quad_kernel(const __grid_constant__ KParams p)
                 base[n] = q_lds(sb + n * ROW_BYTES);
                 x34[n] = q_lds(xsa + n * ROW_BYTES);
             }
+            if (!COEF_RING) cf4 = (M4 != 3) ? make_coef(Y{}, k - 3, por_at(k - 3), por_at(k - 2))
+                                            : make_coef(N{}, k - 3, por_at(k - 3), 0.0);
             if (M4 == 1) top_boundary(c4, F4, true);
             if (M4 != 3) layer_rates(Y{}, cf4, por_at(k - 3), por_at(k - 2), c4, y4n, F4, rhs);
             else         layer_rates(N{}, cf4, por_at(k - 3), 0.0, c4, c4, F4, rhs);
@@ -350,7 +365,7 @@ rk_quad_kernel(const __grid_constant__ KParams p)
             } else {
                 if (M3) q_sts(xsa + n * ROW_BYTES, fma(3.0, rhs3[n], xb[n]));                        // :178  Q += 3*k3
                 if (M2) {                                                                            // :174  P = k1-k2 ; Q = k1+3*k2
-                    x23[n] = MSED_SUB(x12[n], rhs2[n]);
+                    q_sts(xsp + n * ROW_BYTES, MSED_SUB(x12[n], rhs2[n]));
                     q_sts(xsb + n * ROW_BYTES, fma(3.0, rhs2[n], x12[n]));
                 }
                 if (M1) x12[n] = rhs1[n];
