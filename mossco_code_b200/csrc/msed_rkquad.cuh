@@ -13,7 +13,8 @@
 //             and stores the new state of layer k-3 -- in place: the ring has long fetched that layer.
 // A stage hands the layer it has just produced to the next stage in registers (as that stage's "layer below")
 // and through a one-layer link slot in shared memory (as the next iteration's "current layer"); the weighted
-// sums of the k_i travel in registers from stage to stage, one iteration at a time; the base state of stages
+// sums of the k_i go from stage to stage one iteration at a time (the first in registers, the others through shared
+// memory, read where they are consumed); the base state of stages
 // 2-4 is still in the input ring (6 slots: layers k-3 .. k+1 in use, k+2 in flight).  The state is read
 // once and written once per CALL (2 passes instead of 7), nothing else touches HBM.
 //
